@@ -1,0 +1,128 @@
+/*
+ * libroomnet — C ABI of the B200-native RoomNet inference path.
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one piece of
+ * the reference's Python→TensorFlow (or Java→TFLite) seam; the reference
+ * interface each one stands in for is cited as  <file>:<line>  relative to the
+ * upstream repository (ironhide23586/RoomNet).
+ *
+ * Conventions: extern "C", opaque handle, int status (0 = RN_OK), no exceptions
+ * cross the boundary, all buffers are caller-owned HOST memory unless the name
+ * ends in _device.  A handle may be used from several threads; calls on one
+ * handle are serialised internally (tf.Session.run is thread-safe too, but the
+ * reference only ever calls it from one thread: infer.py:79-82).
+ * There is NO CPU fallback: every inference entry point fails with
+ * RN_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef ROOMNET_H_
+#define ROOMNET_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RN_ABI_VERSION 1
+#define RN_MAX_DEVICES 16
+
+typedef struct rn_handle rn_handle;
+
+enum rn_status {
+  RN_OK = 0,
+  RN_ERR_INVALID_ARG = 1,   /* bad pointer / size / enum (TF: InvalidArgumentError on a shape mismatch) */
+  RN_ERR_IO = 2,            /* checkpoint file missing or unreadable (TF: NotFoundError in Saver.restore) */
+  RN_ERR_FORMAT = 3,        /* checkpoint corrupt, CRC mismatch, tensor missing or wrong shape */
+  RN_ERR_NOT_LOADED = 4,    /* inference before weights were loaded (TF: FailedPrecondition, uninitialised variable) */
+  RN_ERR_CUDA = 5,          /* CUDA runtime / driver error, or no usable device */
+  RN_ERR_INTERNAL = 6
+};
+
+enum rn_precision {
+  RN_PREC_FP32 = 0,  /* fp32 FMA on CUDA cores end to end; budget: max|dlogit| <= 1e-3 */
+  RN_PREC_FP16 = 1,  /* 16-bit tensor-core path: fp16 operands, fp32 accumulate (tcgen05 kind::f16); budget 2e-2 */
+  RN_PREC_BF16 = 2   /* same kernels with bf16 operands; measured to MISS the 2e-2 budget on flat images */
+};
+
+/* Replaces the constructor arguments of the reference model object:
+ *   RoomNet(num_classes, im_side, ..., optimized_inference=True)   network.py:21-48
+ * plus what TensorFlow decided implicitly (device placement, network.py:89). */
+typedef struct rn_config {
+  int32_t abi_version;              /* RN_ABI_VERSION */
+  int32_t im_side;                  /* network.py:21  (224 for the shipped checkpoint, infer.py:26) */
+  int32_t num_classes;              /* network.py:21  (6, infer.py:22) */
+  int32_t precision;                /* enum rn_precision */
+  int32_t n_devices;                /* >=1; images of one call are split contiguously over the replicas.
+                                       0 = host-only handle (load + fold only; inference returns RN_ERR_CUDA) */
+  int32_t devices[RN_MAX_DEVICES];  /* CUDA ordinals */
+  int32_t max_batch;                /* per-replica micro-batch held resident on the device (0 = default) */
+} rn_config;
+
+/* network.py:21-48 (graph construction) + network.py:87-91 (session creation). */
+int rn_create(const rn_config* cfg, rn_handle** out);
+
+/* Classifier.close()                                    mobile/.../tflite/Classifier.java:291-301
+ * (tf.Session teardown on the Python side; the reference never closes its session). */
+int rn_destroy(rn_handle* h);
+
+/* Saver.restore(sess, model_path)                      network.py:122
+ * Reads <prefix>.index / <prefix>.data-00000-of-00001 (TF V2 bundle), verifies the
+ * per-tensor CRC32C, folds every frozen BatchNorm forward into the next
+ * conv/dense layer (fp64), packs and uploads the result to every replica. */
+int rn_load_tf_checkpoint(rn_handle* h, const char* prefix);
+
+/* Same restore from caller-held arrays (variable name → fp32 data), for callers
+ * that already hold the variables (network.py:46 vars_to_keep).  shapes[i] has
+ * ranks[i] entries. */
+int rn_load_tensors(rn_handle* h, int32_t n, const char* const* names, const float* const* data,
+                    const int64_t* const* shapes, const int32_t* ranks);
+
+/* dense/kernel override for im_side != 224: the shipped dense/kernel is [64,32]
+ * and only fits im_side 224 (network.py:231-234).  Call before rn_load_*. */
+int rn_set_dense0(rn_handle* h, const float* kernel /* [flat_len,32] */, int32_t flat_len);
+
+/* RoomNet.infer(im_in)                                  network.py:128-135
+ * n pre-sized images, NHWC uint8 BGR [n, S, S, 3].  Normalisation
+ * ((x[..., ::-1]/255)*2-1, network.py:129) happens on the device.
+ * Outputs (any may be NULL): top1 int64[n] (= tf.argmax of the softmax,
+ * network.py:45, first maximum wins), probs f32[n,C] (network.py:44),
+ * logits f32[n,C] (= out_op, ReLU6-clipped, network.py:43/214). */
+int rn_infer_u8_bgr(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits);
+
+/* sess.run(outs_final, {x_tensor: im})                  network.py:131-134, :155
+ * and Interpreter.run(imgData, labelProbArray)          ClassifierFloatMobileNet.java:97
+ * Raw feed: NHWC float32 RGB in [-1,1], [n, S, S, 3]. */
+int rn_infer_f32_rgb(rn_handle* h, const float* nhwc, int32_t n, int64_t* top1, float* probs, float* logits);
+
+/* Interpreter.run on the quantised demo path            ClassifierQuantizedMobileNet.java:94
+ * NHWC uint8 RGB (Bitmap channel order, Classifier.java:226-243). */
+int rn_infer_u8_rgb(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits);
+
+/* Device-resident variant of rn_infer_u8_bgr on replica 0: d_nhwc, d_top1 (int64),
+ * d_probs, d_logits are device pointers on devices[0]; work is enqueued on
+ * `cuda_stream` (a cudaStream_t, NULL = the replica's own stream) and NOT
+ * synchronised.  Used to time the kernels without PCIe in the loop. */
+int rn_infer_u8_bgr_device(rn_handle* h, const void* d_nhwc, int32_t n, void* d_top1, void* d_probs,
+                           void* d_logits, void* cuda_stream);
+
+/* RoomNet.center_crop + cv2.resize                      network.py:137-146, :149-152
+ * Host-side geometry helper: writes the crop rectangle the reference would take. */
+int rn_center_crop_rect(int32_t h, int32_t w, int32_t* y0, int32_t* x0, int32_t* side);
+
+/* Introspection used by the parity tests (no reference analogue). */
+int rn_flat_len(const rn_handle* h);                       /* network.py:231-232 */
+int rn_num_kernel_launches(const rn_handle* h);            /* launches enqueued by the last inference call */
+int rn_get_folded(rn_handle* h, const char* name, float* out, int64_t capacity, int64_t* size);
+int rn_debug_activation(rn_handle* h, int32_t layer, float* out, int64_t capacity, int64_t* size, int32_t dims[4]);
+int rn_get_stats(rn_handle* h, double* p50_ms, double* p99_ms, int64_t* calls, int64_t* images);
+int rn_reset_stats(rn_handle* h);
+
+/* Error text of the last failing call on this handle (or of rn_create when h is NULL). */
+const char* rn_last_error(const rn_handle* h);
+const char* rn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROOMNET_H_ */

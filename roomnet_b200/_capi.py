@@ -1,0 +1,207 @@
+"""ctypes binding of libroomnet.so (include/roomnet.h).
+
+The library is the product; this module only marshals pointers.  There is no
+Python/NumPy fallback: if the shared library is missing, importing fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libroomnet.so")
+
+RN_ABI_VERSION = 1
+RN_MAX_DEVICES = 16
+
+RN_OK, RN_ERR_INVALID_ARG, RN_ERR_IO, RN_ERR_FORMAT, RN_ERR_NOT_LOADED, RN_ERR_CUDA, RN_ERR_INTERNAL = range(7)
+RN_PREC_FP32, RN_PREC_FP16, RN_PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": RN_PREC_FP32, "fp16": RN_PREC_FP16, "bf16": RN_PREC_BF16}
+
+
+class RoomNetError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libroomnet error %d: %s" % (code, msg))
+        self.code = code
+
+
+class RnConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("im_side", C.c_int32),
+        ("num_classes", C.c_int32),
+        ("precision", C.c_int32),
+        ("n_devices", C.c_int32),
+        ("devices", C.c_int32 * RN_MAX_DEVICES),
+        ("max_batch", C.c_int32),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C roomnet_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64p, f32p = C.c_void_p, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_float)
+    sigs = {
+        "rn_create": ([C.POINTER(RnConfig), C.POINTER(vp)], C.c_int),
+        "rn_destroy": ([vp], C.c_int),
+        "rn_load_tf_checkpoint": ([vp, C.c_char_p], C.c_int),
+        "rn_load_tensors": ([vp, i32, C.POINTER(C.c_char_p), C.POINTER(f32p), C.POINTER(i64p), C.POINTER(i32)], C.c_int),
+        "rn_set_dense0": ([vp, f32p, i32], C.c_int),
+        "rn_infer_u8_bgr": ([vp, vp, i32, vp, vp, vp], C.c_int),
+        "rn_infer_u8_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
+        "rn_infer_f32_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
+        "rn_infer_u8_bgr_device": ([vp, vp, i32, vp, vp, vp, vp], C.c_int),
+        "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
+        "rn_flat_len": ([vp], C.c_int),
+        "rn_num_kernel_launches": ([vp], C.c_int),
+        "rn_get_folded": ([vp, C.c_char_p, f32p, C.c_int64, i64p], C.c_int),
+        "rn_debug_activation": ([vp, i32, f32p, C.c_int64, i64p, C.POINTER(i32)], C.c_int),
+        "rn_get_stats": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p, i64p], C.c_int),
+        "rn_reset_stats": ([vp], C.c_int),
+        "rn_last_error": ([vp], C.c_char_p),
+        "rn_version": ([], C.c_char_p),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    return lib
+
+
+lib = _load()
+EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
+            "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_u8_bgr_device",
+            "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_last_error", "rn_version"]
+
+
+class Handle:
+    """Thin RAII wrapper over rn_handle."""
+
+    def __init__(self, im_side=224, num_classes=6, precision="fp16", devices=(0,), max_batch=0):
+        cfg = RnConfig()
+        cfg.abi_version = RN_ABI_VERSION
+        cfg.im_side = im_side
+        cfg.num_classes = num_classes
+        cfg.precision = PRECISIONS[precision] if isinstance(precision, str) else int(precision)
+        devices = list(devices)
+        cfg.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            cfg.devices[i] = d
+        cfg.max_batch = max_batch
+        self.im_side, self.num_classes = im_side, num_classes
+        self._h = C.c_void_p()
+        rc = lib.rn_create(C.byref(cfg), C.byref(self._h))
+        if rc != RN_OK:
+            raise RoomNetError(rc, lib.rn_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != RN_OK:
+            raise RoomNetError(rc, lib.rn_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib.rn_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def load_tf_checkpoint(self, prefix):
+        self._check(lib.rn_load_tf_checkpoint(self._h, os.fsencode(prefix)))
+
+    def load_tensors(self, tensors: dict):
+        names = list(tensors)
+        arrs = [np.ascontiguousarray(tensors[k], dtype=np.float32) for k in names]
+        shapes = [np.asarray(a.shape, dtype=np.int64) for a in arrs]
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+        c_data = (C.POINTER(C.c_float) * n)(*[a.ctypes.data_as(C.POINTER(C.c_float)) for a in arrs])
+        c_shapes = (C.POINTER(C.c_int64) * n)(*[s.ctypes.data_as(C.POINTER(C.c_int64)) for s in shapes])
+        c_ranks = (C.c_int32 * n)(*[a.ndim for a in arrs])
+        self._check(lib.rn_load_tensors(self._h, n, c_names, c_data, c_shapes, c_ranks))
+
+    def set_dense0(self, kernel):
+        k = np.ascontiguousarray(kernel, dtype=np.float32)
+        self._check(lib.rn_set_dense0(self._h, k.ctypes.data_as(C.POINTER(C.c_float)), k.shape[0]))
+
+    def _infer(self, fn, x, dtype, want_logits):
+        x = np.asarray(x)
+        if x.ndim != 4 or x.shape[1:] != (self.im_side, self.im_side, 3):
+            # TF raises InvalidArgumentError for a feed that does not match the placeholder shape
+            raise RoomNetError(RN_ERR_INVALID_ARG, "input must be [n,%d,%d,3], got %s"
+                               % (self.im_side, self.im_side, x.shape))
+        x = np.ascontiguousarray(x, dtype=dtype)
+        n = x.shape[0]
+        top1 = np.empty((n,), np.int64)
+        probs = np.empty((n, self.num_classes), np.float32)
+        logits = np.empty((n, self.num_classes), np.float32) if want_logits else None
+        self._check(fn(self._h, x.ctypes.data, n, top1.ctypes.data, probs.ctypes.data,
+                       logits.ctypes.data if want_logits else None))
+        return (top1, probs, logits) if want_logits else (top1, probs)
+
+    def infer_u8_bgr(self, x, want_logits=False):
+        return self._infer(lib.rn_infer_u8_bgr, x, np.uint8, want_logits)
+
+    def infer_u8_rgb(self, x, want_logits=False):
+        return self._infer(lib.rn_infer_u8_rgb, x, np.uint8, want_logits)
+
+    def infer_f32_rgb(self, x, want_logits=False):
+        return self._infer(lib.rn_infer_f32_rgb, x, np.float32, want_logits)
+
+    def infer_raw(self, fn_name, in_ptr, n, top1_ptr, probs_ptr, logits_ptr):
+        """Pointer-level call (pinned host buffers owned by the caller)."""
+        self._check(getattr(lib, fn_name)(self._h, in_ptr, n, top1_ptr, probs_ptr, logits_ptr))
+
+    def infer_u8_bgr_device(self, d_in, n, d_top1, d_probs, d_logits, stream=None):
+        self._check(lib.rn_infer_u8_bgr_device(self._h, d_in, n, d_top1, d_probs, d_logits, stream))
+
+    @property
+    def flat_len(self):
+        return lib.rn_flat_len(self._h)
+
+    @property
+    def kernel_launches(self):
+        return lib.rn_num_kernel_launches(self._h)
+
+    def get_folded(self, name):
+        size = C.c_int64()
+        self._check(lib.rn_get_folded(self._h, name.encode(), None, 0, C.byref(size)))
+        out = np.empty((size.value,), np.float32)
+        self._check(lib.rn_get_folded(self._h, name.encode(), out.ctypes.data_as(C.POINTER(C.c_float)),
+                                      size.value, C.byref(size)))
+        return out
+
+    def debug_activation(self, layer):
+        size = C.c_int64()
+        dims = (C.c_int32 * 4)()
+        self._check(lib.rn_debug_activation(self._h, layer, None, 0, C.byref(size), dims))
+        out = np.empty((size.value,), np.float32)
+        self._check(lib.rn_debug_activation(self._h, layer, out.ctypes.data_as(C.POINTER(C.c_float)),
+                                            size.value, C.byref(size), dims))
+        return out.reshape(tuple(dims))
+
+    def stats(self):
+        p50, p99 = C.c_double(), C.c_double()
+        calls, images = C.c_int64(), C.c_int64()
+        self._check(lib.rn_get_stats(self._h, C.byref(p50), C.byref(p99), C.byref(calls), C.byref(images)))
+        return dict(p50_ms=p50.value, p99_ms=p99.value, calls=calls.value, images=images.value)
+
+    def reset_stats(self):
+        self._check(lib.rn_reset_stats(self._h))
+
+
+def center_crop_rect(h, w):
+    y0, x0, side = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.rn_center_crop_rect(h, w, C.byref(y0), C.byref(x0), C.byref(side))
+    if rc != RN_OK:
+        raise RoomNetError(rc, "bad image size")
+    return y0.value, x0.value, side.value
+
+
+def version():
+    return lib.rn_version().decode()

@@ -1,0 +1,332 @@
+// C ABI façade + replica scheduler (see include/roomnet.h for the reference
+// interface each entry point replaces).
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "engine.h"
+#include "fold.h"
+#include "roomnet.h"
+#include "tf_bundle.h"
+
+using rn::InputKind;
+
+struct rn_handle {
+  rn_config cfg{};
+  rn::NetShape shape{};
+  std::vector<std::unique_ptr<rn::Replica>> replicas;
+  rn::FoldedNet folded;
+  bool loaded = false;
+  bool has_dense0 = false;
+  rn::Tensor dense0;
+  std::string err;
+  std::mutex mu;
+  int last_launches = 0;
+  std::vector<double> lat_ms;
+  int64_t calls = 0, images = 0;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+int Fail(rn_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+int LoadCommon(rn_handle* h, const rn::TensorMap& vars) {
+  std::string err;
+  if (!rn::FoldNetwork(vars, h->shape, h->has_dense0 ? &h->dense0 : nullptr, &h->folded, &err))
+    return Fail(h, RN_ERR_FORMAT, err);
+  for (auto& r : h->replicas) {
+    if (r->Upload(h->folded) != cudaSuccess) return Fail(h, RN_ERR_CUDA, r->error());
+  }
+  h->loaded = true;
+  return RN_OK;
+}
+
+int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1, float* probs, float* logits) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!in || n < 0) return Fail(h, RN_ERR_INVALID_ARG, "null input or negative batch size");
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+  if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+  if (n == 0) return RN_OK;
+  auto t0 = std::chrono::steady_clock::now();
+  const int g = static_cast<int>(h->replicas.size());
+  const int C = h->shape.num_classes;
+  const size_t per =
+      static_cast<size_t>(h->shape.im_side) * h->shape.im_side * 3 * (kind == InputKind::kF32Rgb ? 4 : 1);
+  // contiguous, as-even-as-possible split of [0, n) over the replicas
+  std::vector<int> begin(g + 1, 0);
+  for (int r = 0; r < g; ++r) begin[r + 1] = begin[r] + n / g + (r < n % g ? 1 : 0);
+  std::vector<cudaError_t> status(g, cudaSuccess);
+  auto run = [&](int r) {
+    int b = begin[r], m = begin[r + 1] - begin[r];
+    if (m == 0) return;
+    status[r] = h->replicas[r]->InferHost(static_cast<const char*>(in) + per * b, kind, m, top1 ? top1 + b : nullptr,
+                                          probs ? probs + static_cast<size_t>(b) * C : nullptr,
+                                          logits ? logits + static_cast<size_t>(b) * C : nullptr);
+  };
+  if (g == 1) {
+    run(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int r = 0; r < g; ++r) th.emplace_back(run, r);
+    for (auto& t : th) t.join();
+  }
+  h->last_launches = 0;
+  for (int r = 0; r < g; ++r) {
+    if (status[r] != cudaSuccess) return Fail(h, RN_ERR_CUDA, h->replicas[r]->error());
+    h->last_launches += h->replicas[r]->last_launches();
+  }
+  double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (h->lat_ms.size() < (1u << 20)) h->lat_ms.push_back(ms);
+  h->calls += 1;
+  h->images += n;
+  return RN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rn_version(void) { return "roomnet_b200 0.1 (sm_100a)"; }
+
+const char* rn_last_error(const rn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rn_create(const rn_config* cfg, rn_handle** out) {
+  g_create_error.clear();
+  if (!cfg || !out) {
+    g_create_error = "null config or output pointer";
+    return RN_ERR_INVALID_ARG;
+  }
+  *out = nullptr;
+  if (cfg->abi_version != RN_ABI_VERSION) {
+    g_create_error = "rn_config.abi_version mismatch";
+    return RN_ERR_INVALID_ARG;
+  }
+  if (cfg->precision < RN_PREC_FP32 || cfg->precision > RN_PREC_BF16) {
+    g_create_error = "unknown precision";
+    return RN_ERR_INVALID_ARG;
+  }
+  // n_devices == 0 makes a host-only handle: checkpoint parsing and BN folding work
+  // (rn_load_*, rn_get_folded), every inference entry point fails with RN_ERR_CUDA.
+  if (cfg->n_devices < 0 || cfg->n_devices > RN_MAX_DEVICES) {
+    g_create_error = "n_devices out of range";
+    return RN_ERR_INVALID_ARG;
+  }
+  if (cfg->num_classes < 1 || cfg->num_classes > 32) {
+    g_create_error = "num_classes out of range (1..32)";
+    return RN_ERR_INVALID_ARG;
+  }
+  auto h = std::make_unique<rn_handle>();
+  h->cfg = *cfg;
+  std::string err;
+  if (!rn::MakeNetShape(cfg->im_side, cfg->num_classes, &h->shape, &err)) {
+    g_create_error = err;
+    return RN_ERR_INVALID_ARG;
+  }
+  int mb = cfg->max_batch;
+  if (mb <= 0) {
+    // resident micro-batch: bounded by activation memory, which grows with im_side^2
+    double scale = (224.0 * 224.0) / (static_cast<double>(cfg->im_side) * cfg->im_side);
+    mb = std::max(1, std::min(256, static_cast<int>(64 * scale)));
+  }
+  h->cfg.max_batch = mb;
+  for (int i = 0; i < cfg->n_devices; ++i) {
+    auto r = std::make_unique<rn::Replica>(cfg->devices[i], h->shape, cfg->precision, mb);
+    if (r->Init() != cudaSuccess) {
+      g_create_error = r->error();
+      return RN_ERR_CUDA;
+    }
+    h->replicas.push_back(std::move(r));
+  }
+  *out = h.release();
+  return RN_OK;
+}
+
+int rn_destroy(rn_handle* h) {
+  delete h;
+  return RN_OK;
+}
+
+int rn_load_tf_checkpoint(rn_handle* h, const char* prefix) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!prefix) return Fail(h, RN_ERR_INVALID_ARG, "null checkpoint prefix");
+  rn::TensorMap vars;
+  std::string err;
+  rn::BundleError be = rn::ReadBundle(prefix, &vars, &err);
+  if (be == rn::BundleError::kIo) return Fail(h, RN_ERR_IO, err);
+  if (be != rn::BundleError::kOk) return Fail(h, RN_ERR_FORMAT, err);
+  return LoadCommon(h, vars);
+}
+
+int rn_load_tensors(rn_handle* h, int32_t n, const char* const* names, const float* const* data,
+                    const int64_t* const* shapes, const int32_t* ranks) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (n < 0 || !names || !data || !shapes || !ranks) return Fail(h, RN_ERR_INVALID_ARG, "null argument");
+  rn::TensorMap vars;
+  for (int i = 0; i < n; ++i) {
+    if (!names[i] || !data[i] || ranks[i] < 0 || ranks[i] > 8 || (ranks[i] && !shapes[i]))
+      return Fail(h, RN_ERR_INVALID_ARG, "bad tensor entry " + std::to_string(i));
+    rn::Tensor t;
+    t.shape.assign(shapes[i], shapes[i] + ranks[i]);
+    for (auto d : t.shape)
+      if (d < 0) return Fail(h, RN_ERR_INVALID_ARG, "negative dimension");
+    t.data.assign(data[i], data[i] + t.numel());
+    vars[names[i]] = std::move(t);
+  }
+  return LoadCommon(h, vars);
+}
+
+int rn_set_dense0(rn_handle* h, const float* kernel, int32_t flat_len) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!kernel) return Fail(h, RN_ERR_INVALID_ARG, "null kernel");
+  if (flat_len != h->shape.flat_len)
+    return Fail(h, RN_ERR_INVALID_ARG,
+                "dense/kernel override has " + std::to_string(flat_len) + " rows but im_side " +
+                    std::to_string(h->shape.im_side) + " flattens to " + std::to_string(h->shape.flat_len));
+  h->dense0.shape = {flat_len, h->shape.dense_out[0]};
+  h->dense0.data.assign(kernel, kernel + static_cast<size_t>(flat_len) * h->shape.dense_out[0]);
+  h->has_dense0 = true;
+  return RN_OK;
+}
+
+int rn_infer_u8_bgr(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits) {
+  return Infer(h, nhwc, InputKind::kU8Bgr, n, top1, probs, logits);
+}
+int rn_infer_u8_rgb(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits) {
+  return Infer(h, nhwc, InputKind::kU8Rgb, n, top1, probs, logits);
+}
+int rn_infer_f32_rgb(rn_handle* h, const float* nhwc, int32_t n, int64_t* top1, float* probs, float* logits) {
+  return Infer(h, nhwc, InputKind::kF32Rgb, n, top1, probs, logits);
+}
+
+int rn_infer_u8_bgr_device(rn_handle* h, const void* d_nhwc, int32_t n, void* d_top1, void* d_probs, void* d_logits,
+                           void* cuda_stream) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!d_nhwc || n < 0) return Fail(h, RN_ERR_INVALID_ARG, "null input or negative batch size");
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+  if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+  if (n == 0) return RN_OK;
+  rn::Replica* r = h->replicas[0].get();
+  cudaError_t e = r->InferDevice(d_nhwc, InputKind::kU8Bgr, n, static_cast<long long*>(d_top1),
+                                 static_cast<float*>(d_probs), static_cast<float*>(d_logits),
+                                 static_cast<cudaStream_t>(cuda_stream));
+  if (e != cudaSuccess) return Fail(h, RN_ERR_CUDA, r->error());
+  h->last_launches = r->last_launches();
+  return RN_OK;
+}
+
+int rn_center_crop_rect(int32_t hgt, int32_t wid, int32_t* y0, int32_t* x0, int32_t* side) {
+  if (hgt <= 0 || wid <= 0 || !y0 || !x0 || !side) return RN_ERR_INVALID_ARG;
+  // reference network.py:139: offset = abs((w - h) // 2) with Python floor division
+  int d = wid - hgt;
+  int fl = d >= 0 ? d / 2 : -((-d + 1) / 2);
+  int off = fl < 0 ? -fl : fl;
+  *y0 = 0;
+  *x0 = 0;
+  if (hgt < wid) {
+    *x0 = off;
+    *side = hgt;
+  } else if (wid < hgt) {
+    *y0 = off;
+    *side = wid;
+  } else {
+    *side = hgt;
+  }
+  return RN_OK;
+}
+
+int rn_flat_len(const rn_handle* h) { return h ? h->shape.flat_len : -1; }
+int rn_num_kernel_launches(const rn_handle* h) { return h ? h->last_launches : -1; }
+
+int rn_get_folded(rn_handle* h, const char* name, float* out, int64_t capacity, int64_t* size) {
+  if (!h || !name || !size) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded");
+  const std::vector<double>* v = nullptr;
+  std::string nm(name);
+  auto layer_of = [&](const std::string& prefix, int limit, int* idx) {
+    if (nm.compare(0, prefix.size(), prefix) != 0) return false;
+    size_t pos = prefix.size();
+    int i = 0;
+    bool any = false;
+    while (pos < nm.size() && nm[pos] >= '0' && nm[pos] <= '9') {
+      i = i * 10 + (nm[pos++] - '0');
+      any = true;
+    }
+    if (!any || i >= limit || pos >= nm.size() || nm[pos] != '/') return false;
+    *idx = i;
+    nm = nm.substr(pos + 1);
+    return true;
+  };
+  int i = 0;
+  const rn::FoldedNet& f = h->folded;
+  if (nm == "conv0_u8bgr/w") v = &f.conv0_u8bgr.w;
+  else if (nm == "conv0_u8bgr/b") v = &f.conv0_u8bgr.b;
+  else if (nm == "conv0_u8rgb/w") v = &f.conv0_u8rgb.w;
+  else if (nm == "conv0_u8rgb/b") v = &f.conv0_u8rgb.b;
+  else if (nm == "conv0_f32rgb/w") v = &f.conv0_f32rgb.w;
+  else if (nm == "conv0_f32rgb/b") v = &f.conv0_f32rgb.b;
+  else if (layer_of("conv", rn::kNumConvs, &i)) v = nm == "w" ? &f.conv[i].w : nm == "b" ? &f.conv[i].b : nullptr;
+  else if (layer_of("join", rn::kNumConvs, &i)) v = nm == "a" ? &f.join[i].a : nm == "b" ? &f.join[i].b : nm == "c" ? &f.join[i].c : nullptr;
+  else if (layer_of("dense", rn::kNumDense, &i)) v = nm == "w" ? &f.dense[i].w : nm == "b" ? &f.dense[i].b : nullptr;
+  if (!v || v->empty()) return Fail(h, RN_ERR_INVALID_ARG, std::string("unknown folded tensor '") + name + "'");
+  *size = static_cast<int64_t>(v->size());
+  if (out) {
+    if (capacity < *size) return Fail(h, RN_ERR_INVALID_ARG, "output buffer too small");
+    for (size_t k = 0; k < v->size(); ++k) out[k] = static_cast<float>((*v)[k]);
+  }
+  return RN_OK;
+}
+
+int rn_debug_activation(rn_handle* h, int32_t layer, float* out, int64_t capacity, int64_t* size, int32_t dims[4]) {
+  if (!h || !size || !dims) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::vector<float> v;
+  int d[4];
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle has no activations");
+  if (h->replicas[0]->DebugActivation(layer, &v, d) != cudaSuccess) return Fail(h, RN_ERR_CUDA, h->replicas[0]->error());
+  for (int k = 0; k < 4; ++k) dims[k] = d[k];
+  *size = static_cast<int64_t>(v.size());
+  if (out) {
+    if (capacity < *size) return Fail(h, RN_ERR_INVALID_ARG, "output buffer too small");
+    std::memcpy(out, v.data(), v.size() * sizeof(float));
+  }
+  return RN_OK;
+}
+
+int rn_get_stats(rn_handle* h, double* p50_ms, double* p99_ms, int64_t* calls, int64_t* images) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  std::vector<double> v = h->lat_ms;
+  std::sort(v.begin(), v.end());
+  auto pct = [&](double p) { return v.empty() ? 0.0 : v[std::min(v.size() - 1, static_cast<size_t>(p * v.size()))]; };
+  if (p50_ms) *p50_ms = pct(0.50);
+  if (p99_ms) *p99_ms = pct(0.99);
+  if (calls) *calls = h->calls;
+  if (images) *images = h->images;
+  return RN_OK;
+}
+
+int rn_reset_stats(rn_handle* h) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  h->lat_ms.clear();
+  h->calls = h->images = 0;
+  return RN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+#include "engine.h"
+
+#include <cstring>
+
+#include "roomnet.h"
+
+namespace rn {
+
+#define RN_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      err_ = std::string(#expr) + ": " + cudaGetErrorString(_e) + " (device " + std::to_string(device_) + ")"; \
+      return _e;                                                                                        \
+    }                                                                                                   \
+  } while (0)
+
+namespace {
+size_t InputBytesPerImage(const NetShape& s, InputKind k) {
+  return static_cast<size_t>(s.im_side) * s.im_side * 3 * (k == InputKind::kF32Rgb ? 4 : 1);
+}
+}  // namespace
+
+Replica::Replica(int device, const NetShape& shape, int precision, int max_batch)
+    : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
+  half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
+  first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
+}
+
+Replica::~Replica() {
+  cudaSetDevice(device_);
+  if (compute_) cudaStreamSynchronize(compute_);
+  if (copy_) cudaStreamSynchronize(copy_);
+  for (void* p : allocs_) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h_in_[i]) cudaFreeHost(h_in_[i]);
+    if (h_out_[i]) cudaFreeHost(h_out_[i]);
+    if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
+    if (ev_done_[i]) cudaEventDestroy(ev_done_[i]);
+  }
+  if (compute_) cudaStreamDestroy(compute_);
+  if (copy_) cudaStreamDestroy(copy_);
+}
+
+cudaError_t Replica::Alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+  if (e == cudaSuccess) allocs_.push_back(*p);
+  return e;
+}
+
+cudaError_t Replica::Init() {
+  int count = 0;
+  RN_CUDA(cudaGetDeviceCount(&count));
+  if (device_ < 0 || device_ >= count) {
+    err_ = "CUDA device " + std::to_string(device_) + " does not exist (" + std::to_string(count) + " visible)";
+    return cudaErrorInvalidDevice;
+  }
+  RN_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  RN_CUDA(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major != 10) {
+    err_ = "device " + std::to_string(device_) + " is sm_" + std::to_string(prop.major * 10 + prop.minor) +
+           "; libroomnet is built for sm_100a only (no fallback path)";
+    return cudaErrorNoKernelImageForDevice;
+  }
+  RN_CUDA(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
+  RN_CUDA(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    RN_CUDA(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming));
+    RN_CUDA(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
+  }
+  const size_t B = static_cast<size_t>(max_batch_);
+  const int C = shape_.num_classes;
+  size_t scratch = 0;
+  for (int i = first_f32_layer_ == 0 ? 0 : first_f32_layer_; i < kNumConvs; ++i) {
+    const ConvShape& cs = shape_.conv[i];
+    scratch = std::max(scratch, static_cast<size_t>(cs.conv_side) * cs.conv_side * cs.cout);
+  }
+  RN_CUDA(Alloc(reinterpret_cast<void**>(&conv_scratch_), scratch * B * sizeof(float)));
+  for (int i = 0; i < kNumConvs; ++i) {
+    const ConvShape& cs = shape_.conv[i];
+    size_t elems = static_cast<size_t>(cs.out_side) * cs.out_side * cs.cout * B;
+    bool f32_needed = i >= first_f32_layer_ || i == first_f32_layer_ - 1;
+    if (f32_needed) {
+      RN_CUDA(Alloc(reinterpret_cast<void**>(&pooled_[i]), elems * sizeof(float)));
+      if (cs.join_src >= 0) RN_CUDA(Alloc(reinterpret_cast<void**>(&joined_[i]), elems * sizeof(float)));
+    }
+    if (i < first_f32_layer_) {
+      size_t bytes = ChunkedBytes(max_batch_, cs.out_side, cs.cout);
+      RN_CUDA(Alloc(&act_h_[i], bytes));
+      RN_CUDA(cudaMemset(act_h_[i], 0, bytes));
+      if (cs.join_src >= 0) {
+        RN_CUDA(Alloc(&join_h_[i], bytes));
+        RN_CUDA(cudaMemset(join_h_[i], 0, bytes));
+      }
+    }
+  }
+  const size_t in_bytes = InputBytesPerImage(shape_, InputKind::kF32Rgb) * B;
+  for (int i = 0; i < 2; ++i) {
+    RN_CUDA(Alloc(&d_in_[i], in_bytes));
+    RN_CUDA(cudaMallocHost(&h_in_[i], in_bytes));
+    RN_CUDA(Alloc(reinterpret_cast<void**>(&d_top1_[i]), B * sizeof(long long)));
+    RN_CUDA(Alloc(reinterpret_cast<void**>(&d_probs_[i]), B * C * sizeof(float)));
+    RN_CUDA(Alloc(reinterpret_cast<void**>(&d_logits_[i]), B * C * sizeof(float)));
+    RN_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_out_[i]), B * (sizeof(long long) + 2 * C * sizeof(float))));
+  }
+  RN_CUDA(Alloc(reinterpret_cast<void**>(&d_pre_), B * C * sizeof(float)));
+  return cudaSuccess;
+}
+
+cudaError_t Replica::UploadF32(const std::vector<double>& v, float** dptr) {
+  std::vector<float> f(v.size());
+  for (size_t i = 0; i < v.size(); ++i) f[i] = static_cast<float>(v[i]);
+  if (!*dptr) RN_CUDA(Alloc(reinterpret_cast<void**>(dptr), f.size() * sizeof(float)));
+  RN_CUDA(cudaMemcpy(*dptr, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return cudaSuccess;
+}
+
+cudaError_t Replica::Upload(const FoldedNet& f) {
+  RN_CUDA(cudaSetDevice(device_));
+  RN_CUDA(cudaStreamSynchronize(compute_));
+  const FoldedConv* c0[3] = {&f.conv0_u8bgr, &f.conv0_u8rgb, &f.conv0_f32rgb};
+  for (int k = 0; k < 3; ++k) {
+    RN_CUDA(UploadF32(c0[k]->w, &w0_[k]));
+    RN_CUDA(UploadF32(c0[k]->b, &b0_[k]));
+  }
+  for (int i = 1; i < kNumConvs; ++i) {
+    RN_CUDA(UploadF32(f.conv[i].w, &cw_[i]));
+    RN_CUDA(UploadF32(f.conv[i].b, &cb_[i]));
+  }
+  for (int i = 0; i < kNumConvs; ++i) {
+    if (shape_.conv[i].join_src < 0) continue;
+    RN_CUDA(UploadF32(f.join[i].a, &ja_[i]));
+    RN_CUDA(UploadF32(f.join[i].b, &jb_[i]));
+    RN_CUDA(UploadF32(f.join[i].c, &jc_[i]));
+  }
+  float* dw[4] = {const_cast<float*>(dense_.w[0]), const_cast<float*>(dense_.w[1]), const_cast<float*>(dense_.w[2]),
+                  const_cast<float*>(dense_.w[3])};
+  float* db[4] = {const_cast<float*>(dense_.b[0]), const_cast<float*>(dense_.b[1]), const_cast<float*>(dense_.b[2]),
+                  const_cast<float*>(dense_.b[3])};
+  for (int i = 0; i < kNumDense; ++i) {
+    RN_CUDA(UploadF32(f.dense[i].w, &dw[i]));
+    RN_CUDA(UploadF32(f.dense[i].b, &db[i]));
+    dense_.w[i] = dw[i];
+    dense_.b[i] = db[i];
+    dense_.out[i] = shape_.dense_out[i];
+  }
+  if (precision_ != RN_PREC_FP32) {
+    for (int i = 1; i < first_f32_layer_; ++i) {
+      const ConvShape& cs = shape_.conv[i];
+      TcConvLayer& L = tc_[i];
+      L.cin = cs.cin;
+      L.cout = cs.cout;
+      L.in_side = cs.in_side;
+      L.pool_k = cs.pool_k;
+      L.pool_s = cs.pool_s;
+      L.out_side = cs.out_side;
+      L.cout_parts = cs.cout > 64 ? cs.cout / 64 : 1;
+      L.bias = cb_[i];
+      size_t part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, nullptr);
+      std::vector<uint8_t> host(part_bytes * L.cout_parts);
+      PackTcWeights(f.conv[i].w.data(), cs.cin, cs.cout, L.cout_parts, half_kind_, host.data());
+      void* d = const_cast<void*>(L.w_packed);
+      if (!d) RN_CUDA(Alloc(&d, host.size()));
+      RN_CUDA(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+      L.w_packed = d;
+      L.w_bytes = part_bytes;
+    }
+  }
+  loaded_ = true;
+  return cudaSuccess;
+}
+
+cudaError_t Replica::TailF32(int first_layer, int n, cudaStream_t st) {
+  for (int i = first_layer; i < kNumConvs; ++i) {
+    const ConvShape& cs = shape_.conv[i];
+    const float* in = shape_.conv[i - 1].join_src >= 0 ? joined_[i - 1] : pooled_[i - 1];
+    float* conv_out = cs.pool_k ? conv_scratch_ : pooled_[i];
+    RN_CUDA(Conv3x3Relu6F32<float>(in, cw_[i], cb_[i], conv_out, n, cs.in_side, cs.in_side, cs.cin, cs.cout, st));
+    ++last_launches_;
+    if (cs.pool_k) {
+      RN_CUDA(AvgPoolF32(conv_scratch_, pooled_[i], n, cs.conv_side, cs.conv_side, cs.cout, cs.pool_k, cs.pool_s, st));
+      ++last_launches_;
+    }
+    if (cs.join_src >= 0) {
+      RN_CUDA(JoinF32(pooled_[i], pooled_[cs.join_src], joined_[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
+                      shape_.conv[cs.join_src].out_side, cs.cout, st));
+      ++last_launches_;
+    }
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Replica::ForwardF32(const void* d_in, InputKind kind, int n, cudaStream_t st) {
+  const ConvShape& c0 = shape_.conv[0];
+  const int k = static_cast<int>(kind);
+  if (kind == InputKind::kF32Rgb)
+    RN_CUDA(Conv3x3Relu6F32<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], conv_scratch_, n, c0.in_side,
+                                   c0.in_side, 3, c0.cout, st));
+  else
+    RN_CUDA(Conv3x3Relu6F32<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], conv_scratch_, n, c0.in_side,
+                                     c0.in_side, 3, c0.cout, st));
+  RN_CUDA(AvgPoolF32(conv_scratch_, pooled_[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
+  last_launches_ += 2;
+  return TailF32(1, n, st);
+}
+
+cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, cudaStream_t st) {
+  const ConvShape& c0 = shape_.conv[0];
+  const int k = static_cast<int>(kind);
+  if (kind == InputKind::kF32Rgb)
+    RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side, half_kind_, st));
+  else
+    RN_CUDA(Conv0PoolH<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side,
+                                half_kind_, st));
+  ++last_launches_;
+  for (int i = 1; i < first_f32_layer_; ++i) {
+    const ConvShape& cs = shape_.conv[i];
+    const void* in = shape_.conv[i - 1].join_src >= 0 ? join_h_[i - 1] : act_h_[i - 1];
+    RN_CUDA(ConvTc(tc_[i], in, act_h_[i], n, half_kind_, st));
+    ++last_launches_;
+    if (cs.join_src >= 0) {
+      RN_CUDA(JoinH(act_h_[i], act_h_[cs.join_src], join_h_[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
+                    shape_.conv[cs.join_src].out_side, cs.cout, half_kind_, st));
+      ++last_launches_;
+    }
+  }
+  const int last = first_f32_layer_ - 1;
+  const ConvShape& cl = shape_.conv[last];
+  RN_CUDA(ChunkedToF32(act_h_[last], pooled_[last], n, cl.out_side, cl.cout, half_kind_, st));
+  ++last_launches_;
+  return TailF32(first_f32_layer_, n, st);
+}
+
+cudaError_t Replica::ForwardDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
+                                   float* d_logits, cudaStream_t st) {
+  if (n <= 0 || n > max_batch_) {
+    err_ = "micro-batch size out of range";
+    return cudaErrorInvalidValue;
+  }
+  cudaError_t e = precision_ == RN_PREC_FP32 ? ForwardF32(d_in, kind, n, st) : ForwardTc(d_in, kind, n, st);
+  if (e != cudaSuccess) return e;
+  const ConvShape& cl = shape_.conv[kNumConvs - 1];
+  const float* flat = cl.join_src >= 0 ? joined_[kNumConvs - 1] : pooled_[kNumConvs - 1];
+  RN_CUDA(DenseTailF32(flat, n, shape_.flat_len, dense_, d_top1, d_probs, d_logits, d_pre_, st));
+  ++last_launches_;
+  last_n_ = n;
+  return cudaSuccess;
+}
+
+cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
+                                 float* d_logits, cudaStream_t st) {
+  RN_CUDA(cudaSetDevice(device_));
+  if (!st) st = compute_;
+  last_launches_ = 0;
+  const size_t per = InputBytesPerImage(shape_, kind);
+  const int C = shape_.num_classes;
+  for (int off = 0; off < n; off += max_batch_) {
+    int m = std::min(max_batch_, n - off);
+    cudaError_t e = ForwardDevice(static_cast<const char*>(d_in) + per * off, kind, m, d_top1 ? d_top1 + off : nullptr,
+                                  d_probs ? d_probs + static_cast<size_t>(off) * C : nullptr,
+                                  d_logits ? d_logits + static_cast<size_t>(off) * C : nullptr, st);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits) {
+  RN_CUDA(cudaSetDevice(device_));
+  last_launches_ = 0;
+  const size_t per = InputBytesPerImage(shape_, kind);
+  const int C = shape_.num_classes;
+  cudaPointerAttributes attr;
+  bool pinned_in = cudaPointerGetAttributes(&attr, h_in) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may set a sticky-less error
+  const size_t out_stride = sizeof(long long) + 2 * C * sizeof(float);
+  struct Pending {
+    int off = 0, m = 0;
+    bool active = false;
+  } pend[2];
+  auto drain = [&](int slot) -> cudaError_t {
+    if (!pend[slot].active) return cudaSuccess;
+    RN_CUDA(cudaEventSynchronize(ev_done_[slot]));
+    const int off = pend[slot].off, m = pend[slot].m;
+    const char* base = h_out_[slot];
+    if (top1) std::memcpy(top1 + off, base, m * sizeof(long long));
+    if (probs) std::memcpy(probs + static_cast<size_t>(off) * C, base + max_batch_ * sizeof(long long), m * C * sizeof(float));
+    if (logits)
+      std::memcpy(logits + static_cast<size_t>(off) * C, base + max_batch_ * (sizeof(long long) + C * sizeof(float)),
+                  m * C * sizeof(float));
+    pend[slot].active = false;
+    return cudaSuccess;
+  };
+  (void)out_stride;
+  int k = 0;
+  for (int off = 0; off < n; off += max_batch_, ++k) {
+    const int slot = k & 1;
+    const int m = std::min(max_batch_, n - off);
+    cudaError_t e = drain(slot);  // slot buffers (d_in_, h_in_, outputs) are free after this
+    if (e != cudaSuccess) return e;
+    const char* src = static_cast<const char*>(h_in) + per * off;
+    if (!pinned_in) {
+      std::memcpy(h_in_[slot], src, per * m);
+      src = static_cast<const char*>(h_in_[slot]);
+    }
+    RN_CUDA(cudaMemcpyAsync(d_in_[slot], src, per * m, cudaMemcpyHostToDevice, copy_));
+    RN_CUDA(cudaEventRecord(ev_h2d_[slot], copy_));
+    RN_CUDA(cudaStreamWaitEvent(compute_, ev_h2d_[slot], 0));
+    e = ForwardDevice(d_in_[slot], kind, m, d_top1_[slot], d_probs_[slot], d_logits_[slot], compute_);
+    if (e != cudaSuccess) return e;
+    char* base = h_out_[slot];
+    RN_CUDA(cudaMemcpyAsync(base, d_top1_[slot], m * sizeof(long long), cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[slot], m * C * sizeof(float),
+                            cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[slot],
+                            m * C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaEventRecord(ev_done_[slot], compute_));
+    pend[slot].off = off;
+    pend[slot].m = m;
+    pend[slot].active = true;
+  }
+  for (int s = 0; s < 2; ++s) {
+    cudaError_t e = drain((k + s) & 1);
+    if (e != cudaSuccess) return e;
+  }
+  RN_CUDA(cudaGetLastError());
+  return cudaSuccess;
+}
+
+cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dims[4]) {
+  RN_CUDA(cudaSetDevice(device_));
+  if (layer < 0 || layer >= kNumConvs || last_n_ <= 0) {
+    err_ = "no activation recorded for that layer";
+    return cudaErrorInvalidValue;
+  }
+  const ConvShape& cs = shape_.conv[layer];
+  dims[0] = last_n_;
+  dims[1] = dims[2] = cs.out_side;
+  dims[3] = cs.cout;
+  size_t elems = static_cast<size_t>(last_n_) * cs.out_side * cs.out_side * cs.cout;
+  out->resize(elems);
+  RN_CUDA(cudaStreamSynchronize(compute_));
+  const float* src = nullptr;
+  float* tmp = nullptr;
+  if (layer >= first_f32_layer_ || (layer == first_f32_layer_ - 1 && cs.join_src < 0)) {
+    src = cs.join_src >= 0 ? joined_[layer] : pooled_[layer];
+  } else {
+    RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), elems * sizeof(float)));
+    const void* h = cs.join_src >= 0 ? join_h_[layer] : act_h_[layer];
+    cudaError_t e = ChunkedToF32(h, tmp, last_n_, cs.out_side, cs.cout, half_kind_, compute_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(compute_);
+    if (e != cudaSuccess) {
+      cudaFree(tmp);
+      RN_CUDA(e);
+    }
+    src = tmp;
+  }
+  cudaError_t e = cudaMemcpy(out->data(), src, elems * sizeof(float), cudaMemcpyDeviceToHost);
+  if (tmp) cudaFree(tmp);
+  RN_CUDA(e);
+  return cudaSuccess;
+}
+
+}  // namespace rn

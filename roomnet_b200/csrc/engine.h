@@ -1,0 +1,95 @@
+// One inference replica = one GPU: folded weights, resident activation buffers,
+// pinned staging, two streams.  Replaces what tf.Session held for the reference
+// (network.py:87-91) on a single device.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "fold.h"
+#include "kernels.h"
+
+namespace rn {
+
+enum class InputKind : int { kU8Bgr = 0, kU8Rgb = 1, kF32Rgb = 2 };
+
+class Replica {
+ public:
+  Replica(int device, const NetShape& shape, int precision, int max_batch);
+  ~Replica();
+  Replica(const Replica&) = delete;
+  Replica& operator=(const Replica&) = delete;
+
+  cudaError_t Init();
+  cudaError_t Upload(const FoldedNet& f);
+  bool loaded() const { return loaded_; }
+  int device() const { return device_; }
+  int max_batch() const { return max_batch_; }
+
+  // n <= max_batch images already resident on this device; enqueues on `st`, no sync.
+  cudaError_t ForwardDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
+                            float* d_logits, cudaStream_t st);
+  // Arbitrary n from host memory (pinned or pageable), double-buffered micro-batches; synchronous.
+  cudaError_t InferHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits);
+  // Arbitrary n, device-resident input/outputs, micro-batched on `st` (nullptr = own stream); no sync.
+  cudaError_t InferDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
+                          float* d_logits, cudaStream_t st);
+
+  int last_launches() const { return last_launches_; }
+  // Debug: copies the output of conv layer `layer` (pooled, after the residual join where there is
+  // one) of the last micro-batch to host as NHWC fp32.
+  cudaError_t DebugActivation(int layer, std::vector<float>* out, int dims[4]);
+  const std::string& error() const { return err_; }
+
+ private:
+  cudaError_t ForwardF32(const void* d_in, InputKind kind, int n, cudaStream_t st);
+  cudaError_t ForwardTc(const void* d_in, InputKind kind, int n, cudaStream_t st);
+  cudaError_t TailF32(int first_layer, int n, cudaStream_t st);
+  cudaError_t Alloc(void** p, size_t bytes);
+  cudaError_t UploadF32(const std::vector<double>& v, float** dptr);
+
+  int device_, precision_, max_batch_;
+  NetShape shape_;
+  bool loaded_ = false;
+  std::string err_;
+  int last_launches_ = 0;
+  int last_n_ = 0;
+
+  cudaStream_t compute_ = nullptr, copy_ = nullptr;
+  cudaEvent_t ev_h2d_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
+  std::vector<void*> allocs_;
+
+  // weights (fp32, HWIO folded)
+  float* w0_[3] = {nullptr, nullptr, nullptr};  // conv0 per InputKind
+  float* b0_[3] = {nullptr, nullptr, nullptr};
+  float* cw_[kNumConvs] = {};
+  float* cb_[kNumConvs] = {};
+  float* ja_[kNumConvs] = {};
+  float* jb_[kNumConvs] = {};
+  float* jc_[kNumConvs] = {};
+  DenseParams dense_{};
+  // 16-bit packed weights
+  TcConvLayer tc_[kNumConvs] = {};
+  HalfKind half_kind_ = HalfKind::kF16;
+
+  // activations
+  float* conv_scratch_ = nullptr;
+  float* pooled_[kNumConvs] = {};
+  float* joined_[kNumConvs] = {};
+  void* act_h_[kNumConvs] = {};
+  void* join_h_[kNumConvs] = {};
+  int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
+
+  // staging
+  void* d_in_[2] = {nullptr, nullptr};
+  void* h_in_[2] = {nullptr, nullptr};
+  long long* d_top1_[2] = {nullptr, nullptr};
+  float* d_probs_[2] = {nullptr, nullptr};
+  float* d_logits_[2] = {nullptr, nullptr};
+  float* d_pre_ = nullptr;
+  char* h_out_[2] = {nullptr, nullptr};
+};
+
+}  // namespace rn

@@ -1,0 +1,64 @@
+// Kernel launch wrappers shared by the engine.  All kernels are hand-written for
+// sm_100a; nothing here dispatches to cuDNN/cuBLAS.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstddef>
+#include <cstdint>
+
+namespace rn {
+
+struct DenseParams {
+  const float* w[4];  // [in][out], BN of the producer folded in
+  const float* b[4];
+  int out[4];
+};
+
+// ---- fp32 CUDA-core kernels (kernels_f32.cu) --------------------------------
+template <typename TIn>
+cudaError_t Conv3x3Relu6F32(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin,
+                            int Cout, cudaStream_t st);
+cudaError_t AvgPoolF32(const float* in, float* out, int N, int H, int W, int C, int k, int s, cudaStream_t st);
+cudaError_t JoinF32(const float* p, const float* src, float* out, const float* A, const float* B, const float* C,
+                    int N, int S, int SS, int Ch, cudaStream_t st);
+cudaError_t DenseTailF32(const float* flat, int N, int flat_len, const DenseParams& dp, long long* top1, float* probs,
+                         float* logits, float* pre_relu6, cudaStream_t st);
+
+// ---- 16-bit tensor-core path (kernels_tc.cu) --------------------------------
+// Activation layout between tensor-core layers ("chunked rows"):
+//   T[n][y][cb][x][8]  16-bit elements, cb = channel / 8.  One (n, y, cb) plane row
+//   is W*16 contiguous bytes, so a row segment is ONE 1-D TMA bulk copy and lands in
+//   shared memory already in the UMMA no-swizzle K-major core-matrix order.
+enum class HalfKind : int { kF16 = 0, kBF16 = 1 };
+
+struct TcConvLayer {
+  int cin, cout;          // logical channels of the conv
+  int in_side;            // input spatial size (square)
+  int pool_k, pool_s;     // 0/0 = no pooling
+  int out_side;           // pooled output size
+  const void* w_packed;   // device, packed by PackTcWeights
+  size_t w_bytes;         // bytes per cout-part
+  int cout_parts;         // cout is processed in `cout_parts` passes of cout/cout_parts channels
+  const float* bias;      // device [cout]
+};
+
+// Size in bytes of an activation tensor in chunked layout, incl. over-read slack.
+size_t ChunkedBytes(int n, int side, int channels);
+
+// Host-side weight packer: HWIO fp64 -> per-part shared-memory image of the conv_tc kernel.
+size_t PackTcWeights(const double* w_hwio, int cin, int cout, int cout_parts, HalfKind kind, void* out_host);
+
+cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st);
+
+// conv0 (3->8, CUDA cores, fp32 math) + ReLU6 + 3x3/1 avg-pool, writes chunked 16-bit.
+template <typename TIn>
+cudaError_t Conv0PoolH(const TIn* in, const float* w, const float* b, void* out, int N, int S, HalfKind kind,
+                       cudaStream_t st);
+// out = A*p + B*resize(src) + C on chunked 16-bit tensors.
+cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, const float* B, const float* C, int N,
+                  int S, int SS, int Ch, HalfKind kind, cudaStream_t st);
+// chunked 16-bit -> NHWC fp32
+cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, cudaStream_t st);
+
+}  // namespace rn

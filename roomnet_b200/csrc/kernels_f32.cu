@@ -1,0 +1,250 @@
+// FP32 CUDA-core kernels (RN_PREC_FP32 path and the small-channel front/tail of
+// the 16-bit path).  Layout: NHWC fp32 activations, HWIO folded weights.
+//
+// Folded layer form:  p' = pool(relu6(conv_W(p) + b))
+//   conv3x3_relu6_kernel : reference network.py:184-186 (conv2d VALID + ReLU6)
+//   avgpool_kernel       : reference network.py:188-191 (avg_pool VALID)
+//   join_kernel          : reference network.py:199-203 (+resize_bilinear, BN) as A*p+B*resize(p0)+C
+//   dense_tail_kernel    : reference network.py:210-223, :231-237, :44-45
+#include "kernels.h"
+
+namespace rn {
+
+namespace {
+
+__device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
+
+// ---------------------------------------------------------------------------
+// Direct 3x3 VALID convolution + bias + ReLU6.
+// Block = 16x16 output pixels, each thread owns one pixel and COG output channels.
+// Input channels are consumed in chunks of CC through shared memory:
+//   tile [CC][18][18+1]  (channel-major so that a warp's x-consecutive reads hit
+//                         consecutive banks), weights [9][CC][COG] (warp-broadcast).
+// ---------------------------------------------------------------------------
+constexpr int kTile = 16;
+constexpr int kHalo = kTile + 2;
+
+template <typename TIn>
+__device__ __forceinline__ float load_as_float(const TIn* p) {
+  return static_cast<float>(*p);
+}
+
+template <int CC, int COG, typename TIn>
+__global__ void __launch_bounds__(kTile* kTile)
+    conv3x3_relu6_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                         float* __restrict__ out, int H, int W, int Cin, int Cout) {
+  __shared__ float s_in[CC][kHalo][kHalo + 1];
+  __shared__ __align__(16) float s_w[9][CC][COG];
+
+  const int OH = H - 2, OW = W - 2;
+  const int groups = Cout / COG;
+  const int n = blockIdx.z / groups;
+  const int co0 = (blockIdx.z % groups) * COG;
+  const int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;
+  const int oy0 = blockIdx.y * kTile, ox0 = blockIdx.x * kTile;
+  const TIn* in_n = in + static_cast<size_t>(n) * H * W * Cin;
+
+  float acc[COG];
+#pragma unroll
+  for (int o = 0; o < COG; ++o) acc[o] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += CC) {
+    // stage the input halo tile: consecutive threads walk (x, c) so global reads stay contiguous
+    for (int idx = threadIdx.x; idx < kHalo * kHalo * CC; idx += kTile * kTile) {
+      int c = idx % CC;
+      int px = (idx / CC) % kHalo;
+      int py = idx / (CC * kHalo);
+      int iy = oy0 + py, ix = ox0 + px;
+      float v = 0.f;
+      if (iy < H && ix < W && c0 + c < Cin) v = load_as_float(in_n + (static_cast<size_t>(iy) * W + ix) * Cin + c0 + c);
+      s_in[c][py][px] = v;
+    }
+    for (int idx = threadIdx.x; idx < 9 * CC * COG; idx += kTile * kTile) {
+      int o = idx % COG;
+      int c = (idx / COG) % CC;
+      int tap = idx / (COG * CC);
+      float v = 0.f;
+      if (c0 + c < Cin) v = w[(static_cast<size_t>(tap) * Cin + c0 + c) * Cout + co0 + o];
+      s_w[tap][c][o] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+      for (int c = 0; c < CC; ++c) {
+        const float a = s_in[c][ty + dy][tx + dx];
+#pragma unroll
+        for (int o = 0; o < COG; ++o) acc[o] = fmaf(a, s_w[tap][c][o], acc[o]);
+      }
+    }
+    __syncthreads();
+  }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  if (oy < OH && ox < OW) {
+    float* o_ptr = out + ((static_cast<size_t>(n) * OH + oy) * OW + ox) * Cout + co0;
+#pragma unroll
+    for (int o = 0; o < COG; ++o) o_ptr[o] = relu6f(acc[o] + bias[co0 + o]);
+  }
+}
+
+// k x k / stride s VALID average pooling, one thread per output element (c fastest).
+__global__ void avgpool_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C,
+                               int k, int s, int OH, int OW) {
+  const size_t total = static_cast<size_t>(N) * OH * OW * C;
+  const float inv = 1.f / static_cast<float>(k * k);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int c = static_cast<int>(i % C);
+    size_t r = i / C;
+    int ox = static_cast<int>(r % OW);
+    r /= OW;
+    int oy = static_cast<int>(r % OH);
+    int n = static_cast<int>(r / OH);
+    const float* p = in + ((static_cast<size_t>(n) * H + oy * s) * W + ox * s) * C + c;
+    float acc = 0.f;
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) acc += p[(static_cast<size_t>(dy) * W + dx) * C];
+    out[i] = acc * inv;
+  }
+}
+
+// out = A*p + B*resize_bilinear_legacy(src) + C   (TF-1.13 ResizeBilinear, align_corners=False)
+__global__ void join_kernel(const float* __restrict__ p, const float* __restrict__ src, float* __restrict__ out,
+                            const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ Cc,
+                            int N, int S, int SS, int C) {
+  const size_t total = static_cast<size_t>(N) * S * S * C;
+  const float scale = static_cast<float>(SS) / static_cast<float>(S);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    int c = static_cast<int>(i % C);
+    size_t r = i / C;
+    int x = static_cast<int>(r % S);
+    r /= S;
+    int y = static_cast<int>(r % S);
+    int n = static_cast<int>(r / S);
+    float fy = static_cast<float>(y) * scale, fx = static_cast<float>(x) * scale;
+    int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
+    int y1 = min(y0 + 1, SS - 1), x1 = min(x0 + 1, SS - 1);
+    float ty = fy - static_cast<float>(y0), tx = fx - static_cast<float>(x0);
+    const float* s_n = src + static_cast<size_t>(n) * SS * SS * C + c;
+    float tl = s_n[(static_cast<size_t>(y0) * SS + x0) * C], tr = s_n[(static_cast<size_t>(y0) * SS + x1) * C];
+    float bl = s_n[(static_cast<size_t>(y1) * SS + x0) * C], br = s_n[(static_cast<size_t>(y1) * SS + x1) * C];
+    float top = tl + (tr - tl) * tx;
+    float bot = bl + (br - bl) * tx;
+    float res = top + (bot - top) * ty;
+    out[i] = fmaf(A[c], p[i], fmaf(B[c], res, Cc[c]));
+  }
+}
+
+// Dense head: 4 x (matmul + bias + ReLU6), softmax, argmax.  One warp per image.
+// Layer widths after the first are <= 32 so a lane owns one output unit.
+__global__ void dense_tail_kernel(const float* __restrict__ flat, int N, int flat_len, DenseParams dp,
+                                  long long* __restrict__ top1, float* __restrict__ probs,
+                                  float* __restrict__ logits, float* __restrict__ pre_relu6) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (warp >= N) return;
+  const float* x = flat + static_cast<size_t>(warp) * flat_len;
+  // layer 0: flat_len -> n0 (<=32): lane o accumulates its column in index order (deterministic)
+  float v = 0.f;
+  {
+    const int on = dp.out[0];
+    if (lane < on) {
+      float acc = 0.f;
+      for (int r = 0; r < flat_len; ++r) acc = fmaf(x[r], dp.w[0][static_cast<size_t>(r) * on + lane], acc);
+      v = relu6f(acc + dp.b[0][lane]);
+    }
+  }
+  float pre = 0.f;
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+    const int in = dp.out[l - 1], on = dp.out[l];
+    float acc = 0.f;
+    for (int r = 0; r < in; ++r) {
+      float xr = __shfl_sync(0xffffffffu, v, r);
+      if (lane < on) acc = fmaf(xr, dp.w[l][r * on + lane], acc);
+    }
+    if (lane < on) acc += dp.b[l][lane];
+    pre = acc;
+    v = relu6f(acc);
+  }
+  const int C = dp.out[3];
+  // softmax over the ReLU6-clipped logits (reference network.py:43-44), argmax of the softmax (:45)
+  float m = lane < C ? v : -INFINITY;
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float e = lane < C ? expf(v - m) : 0.f;
+  float s = e;
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float prob = e / s;
+  // first index of the maximum probability
+  float best = lane < C ? prob : -1.f;
+  int bi = lane;
+  for (int o = 16; o; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane < C) {
+    if (probs) probs[static_cast<size_t>(warp) * C + lane] = prob;
+    if (logits) logits[static_cast<size_t>(warp) * C + lane] = v;
+    if (pre_relu6) pre_relu6[static_cast<size_t>(warp) * C + lane] = pre;
+  }
+  if (lane == 0 && top1) top1[warp] = bi;
+}
+
+template <int CC, int COG, typename TIn>
+void launch_conv(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin, int Cout,
+                 cudaStream_t st) {
+  dim3 grid((W - 2 + kTile - 1) / kTile, (H - 2 + kTile - 1) / kTile, N * (Cout / COG));
+  conv3x3_relu6_kernel<CC, COG, TIn><<<grid, kTile * kTile, 0, st>>>(in, w, b, out, H, W, Cin, Cout);
+}
+
+}  // namespace
+
+template <typename TIn>
+cudaError_t Conv3x3Relu6F32(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin,
+                            int Cout, cudaStream_t st) {
+  if (Cin == 3 && Cout % 8 == 0)
+    launch_conv<3, 8, TIn>(in, w, b, out, N, H, W, Cin, Cout, st);
+  else if (Cin % 8 == 0 && Cout % 16 == 0)
+    launch_conv<8, 16, TIn>(in, w, b, out, N, H, W, Cin, Cout, st);
+  else if (Cin % 8 == 0 && Cout % 8 == 0)
+    launch_conv<8, 8, TIn>(in, w, b, out, N, H, W, Cin, Cout, st);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+template cudaError_t Conv3x3Relu6F32<float>(const float*, const float*, const float*, float*, int, int, int, int,
+                                            int, cudaStream_t);
+template cudaError_t Conv3x3Relu6F32<uint8_t>(const uint8_t*, const float*, const float*, float*, int, int, int,
+                                              int, int, cudaStream_t);
+
+cudaError_t AvgPoolF32(const float* in, float* out, int N, int H, int W, int C, int k, int s, cudaStream_t st) {
+  int OH = (H - k) / s + 1, OW = (W - k) / s + 1;
+  size_t total = static_cast<size_t>(N) * OH * OW * C;
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  avgpool_kernel<<<blocks, 256, 0, st>>>(in, out, N, H, W, C, k, s, OH, OW);
+  return cudaGetLastError();
+}
+
+cudaError_t JoinF32(const float* p, const float* src, float* out, const float* A, const float* B, const float* C,
+                    int N, int S, int SS, int Ch, cudaStream_t st) {
+  size_t total = static_cast<size_t>(N) * S * S * Ch;
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  join_kernel<<<blocks, 256, 0, st>>>(p, src, out, A, B, C, N, S, SS, Ch);
+  return cudaGetLastError();
+}
+
+cudaError_t DenseTailF32(const float* flat, int N, int flat_len, const DenseParams& dp, long long* top1, float* probs,
+                         float* logits, float* pre_relu6, cudaStream_t st) {
+  int warps_per_block = 4;
+  int blocks = (N + warps_per_block - 1) / warps_per_block;
+  dense_tail_kernel<<<blocks, warps_per_block * 32, 0, st>>>(flat, N, flat_len, dp, top1, probs, logits, pre_relu6);
+  return cudaGetLastError();
+}
+
+}  // namespace rn

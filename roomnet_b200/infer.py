@@ -1,0 +1,125 @@
+"""Drop-in ``classify_im_dir`` over the B200 path.
+
+Behavioural contract taken from the reference (infer.py:65-100): given a model
+and a directory, write ``<dir>_classified/<Label>/<file>`` (the image with two
+overlaid text lines, or a plain copy when ``overlay=False``) and
+``<dir>_classified_results.xls`` (header IMAGE_NAME / PREDICTED_LABEL, one row
+per file: name, label, confidence as a string), and return the xls path.
+
+What is different: files are decoded up front and go through the network in
+batches of ``BATCH`` images (one C-ABI call each) instead of one
+``Session.run`` per file (reference infer.py:79-82).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import struct
+from glob import glob
+
+import cv2
+
+from .network import RoomNet
+
+CLASS_LABELS = ['Backyard', 'Bathroom', 'Bedroom', 'Frontyard', 'Kitchen', 'LivingRoom']  # reference infer.py:22
+INPUT_MODEL_PATH = './final_model/roomnet'       # reference infer.py:24
+INPUT_IMAGES_DIR = './test_images/set2/images'   # reference infer.py:25
+IMG_SIDE = 224                                   # reference infer.py:26
+BATCH = 256
+
+
+class _Biff2Sheet:
+    """Single-sheet BIFF2 ``.xls`` writer for when xlwt is absent (it is, in this image).
+
+    File = BOF(0x0009) · one LABEL(0x0004) record per cell · EOF(0x000A).
+    Offers the two calls the results table needs: write(row, col, value), save(path).
+    """
+
+    def __init__(self):
+        self._cells = []
+
+    def write(self, row, col, value):
+        self._cells.append((row, col, str(value)))
+
+    def save(self, path):
+        with open(path, 'wb') as f:
+            f.write(struct.pack('<HHHH', 0x0009, 4, 2, 0x10))
+            for row, col, text in self._cells:
+                payload = text.encode('latin-1', 'replace')[:255]
+                f.write(struct.pack('<HHHH3sB', 0x0004, 8 + len(payload), row, col, b'\0\0\0', len(payload)))
+                f.write(payload)
+            f.write(struct.pack('<HH', 0x000A, 0))
+
+
+def _results_table():
+    """(workbook, sheet) — xlwt when importable (reference infer.py:75-76), BIFF2 writer otherwise."""
+    try:
+        import xlwt
+    except ImportError:
+        sheet = _Biff2Sheet()
+        return sheet, sheet
+    book = xlwt.Workbook()
+    return book, book.add_sheet('classification_results')
+
+
+def _annotate(image, label, confidence):
+    """The two overlay lines of reference infer.py:87-92 (positions, font scale and colours kept)."""
+    height, width = image.shape[:2]
+    scale = (height / 720.) * .85
+    lines = (("Predicted Class: " + label, .90, (0, 255, 0)),
+             ("Confidence: " + str(round(confidence * 100, 2)) + " %", .95, (255, 0, 0)))
+    for text, rel_y, colour in lines:
+        cv2.putText(image, text, (int(.5 * width), int(rel_y * height)), cv2.FONT_HERSHEY_SIMPLEX, scale, colour, 1,
+                    cv2.LINE_AA)
+    return image
+
+
+def _read_images(paths):
+    images = []
+    for path in paths:
+        image = cv2.imread(path)
+        if image is None:
+            # the reference dies in center_crop (network.py:138) on an unreadable file; keep the exception type
+            raise AttributeError("'NoneType' object has no attribute 'shape' (cv2.imread failed on %s)" % path)
+        images.append(image)
+    return images
+
+
+def classify_im_dir(nn, imgs_dir, overlay=True):
+    print('Classifying images in', imgs_dir)
+    paths = glob(imgs_dir + '/*')
+    out_dir = imgs_dir + '_classified'
+    xl_fpath = out_dir + '_results.xls'
+    for label in CLASS_LABELS:
+        os.makedirs(os.path.join(out_dir, label), exist_ok=True)
+    print('Beginning inference..')
+    workbook, sheet = _results_table()
+    sheet.write(0, 0, 'IMAGE_NAME')
+    sheet.write(0, 1, 'PREDICTED_LABEL')
+    row = 1
+    for start in range(0, len(paths), BATCH):
+        chunk = paths[start:start + BATCH]
+        images = _read_images(chunk)
+        top1, probs = nn.infer_optimized_batch(images)
+        for path, image, cls, prob in zip(chunk, images, top1, probs):
+            label, confidence = CLASS_LABELS[cls], prob[cls]
+            name = path.split(os.sep)[-1]
+            target_dir = out_dir + os.sep + label
+            print(path, '--->', label, confidence)
+            if overlay:
+                cv2.imwrite(target_dir + os.sep + name, _annotate(image, label, confidence))
+            else:
+                shutil.copy(path, target_dir)
+            sheet.write(row, 0, name)
+            sheet.write(row, 1, label)
+            sheet.write(row, 2, str(confidence))
+            row += 1
+    workbook.save(xl_fpath)
+    return xl_fpath
+
+
+if __name__ == '__main__':
+    model = RoomNet(num_classes=len(CLASS_LABELS), im_side=IMG_SIDE, compute_bn_mean_var=False,
+                    optimized_inference=True)
+    model.load(INPUT_MODEL_PATH)
+    classify_im_dir(model, INPUT_IMAGES_DIR)
