@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Headline benchmark: RoomNet@224x224 inference images/s (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of synthetic images
+(configs[1]: batch 256 per GPU, 16-bit tensor-core path).  `value` is measured with
+inputs resident in HBM (CUDA events on the launching stream); `e2e` goes through the
+reference-facing C-ABI call rn_infer_u8_bgr with pinned HOST buffers, host<->device
+copies inside the timed region.  `--impl reference` times the CPU restatement of the
+reference (oracle/, torch-CPU conv kernels; TensorFlow 1.13.1 itself is not installable)
+on the box's host cores.
+
+One process per GPU: `python bench.py` (N=1) or under torchrun (reads RANK/LOCAL_RANK/
+WORLD_SIZE); replicas are independent, no collective is on the data path — the only
+communication is the barrier/max-reduction of the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_IMAGE_224 = 4_486_397_472  # 10 convs (2*MAC) + dense head
+BATCH_PER_GPU = 256
+N_INPUT_SETS = 4  # 4 x 38.5 MB of distinct uint8 inputs > 126 MB L2
+
+
+def conv_flops(layer_idx: int, side: int = 224) -> int:
+    from oracle.roomnet_oracle import CONV_BLOCKS, spatial_trace
+    tr = spatial_trace(side)
+    chans = [3]
+    for (f, _, _, _, d) in CONV_BLOCKS:
+        chans += [f] * d
+    t = tr[layer_idx]
+    return 2 * t["conv"] * t["conv"] * chans[layer_idx + 1] * 9 * chans[layer_idx]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(tflops=p.get("bf16_tflops_sustained", 1388.5), tflops_burst=p.get("bf16_tflops", 1645.4),
+                    hbm=p.get("hbm_gbs", 6536.0), source="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def cpu_reference_throughput(n_images: int, warmup: int = 3):
+    """Batch-1, sequential, through the reference's call shape (infer.py:79-82 → infer_optimized)."""
+    import numpy as np
+    import torch
+
+    from oracle.roomnet_oracle import RoomNetOracle, synthetic_suite
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    oracle = RoomNetOracle(dtype=np.float32, conv_backend="torch").load()
+    imgs = synthetic_suite(max(n_images, 1))
+    for i in range(warmup):
+        oracle.infer_optimized(imgs[i % len(imgs)])
+    lat = []
+    t0 = time.perf_counter()
+    for i in range(n_images):
+        t1 = time.perf_counter()
+        oracle.infer_optimized(imgs[i])
+        lat.append(time.perf_counter() - t1)
+    dt = time.perf_counter() - t0
+    return n_images / dt, cores, statistics.median(lat) * 1e3
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    per_step = 16  # bounded sample: 16 batch-1 images per step
+    ips, cores, p50 = cpu_reference_throughput(per_step * max(args.steps, 1), warmup=max(args.warmup, 1))
+    sample = "%d batch-1 synthetic 224x224 images per step, sequential, torch-CPU fp32 oracle" % per_step
+    line = {
+        "impl": "reference", "metric": "images_per_sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step / ips * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "RoomNet final_model @224x224, CPU restatement of the reference TF graph "
+                               "(TensorFlow 1.13.1 not installable), batch 1", "p50_ms": p50},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--max-batch", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oracle.roomnet_oracle import synthetic_suite
+    from oracle.tf_bundle import default_checkpoint_prefix
+    from roomnet_b200 import _capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.batch
+    h = _capi.Handle(precision=args.precision, devices=(local_rank,), max_batch=args.max_batch)
+    h.load_tf_checkpoint(default_checkpoint_prefix())
+
+    # synthetic inputs: the 64-image parity suite tiled to the batch, N_INPUT_SETS distinct rolls
+    suite = synthetic_suite(64)
+    host_sets = []
+    for s in range(N_INPUT_SETS):
+        idx = (np.arange(B) + 17 * s + 5 * rank) % 64
+        t = torch.from_numpy(np.ascontiguousarray(suite[idx])).pin_memory()
+        host_sets.append(t)
+    dev_sets = [t.to(dev) for t in host_sets]
+    d_top1 = torch.empty(B, dtype=torch.int64, device=dev)
+    d_probs = torch.empty(B, 6, dtype=torch.float32, device=dev)
+    d_logits = torch.empty(B, 6, dtype=torch.float32, device=dev)
+    h_top1 = torch.empty(B, dtype=torch.int64).pin_memory()
+    h_probs = torch.empty(B, 6, dtype=torch.float32).pin_memory()
+    stream = torch.cuda.Stream(device=dev)
+
+    def step_device(i):
+        h.infer_u8_bgr_device(dev_sets[i % N_INPUT_SETS].data_ptr(), B, d_top1.data_ptr(), d_probs.data_ptr(),
+                              d_logits.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- correctness guard: the timed path must reproduce the oracle's top-1 on this batch ----
+    step_device(0)
+    stream.synchronize()
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "suite64.npz"))
+    idx0 = (np.arange(B) + 5 * rank) % 64
+    if not np.array_equal(d_top1.cpu().numpy(), golden["argmax"][idx0]):
+        raise SystemExit("bench: top-1 differs from the golden vectors — refusing to time a wrong kernel")
+    launches_per_step = h.kernel_launches
+
+    # ---- device-resident timing ----
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step_device(i)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_dev = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev = float(t.item())
+    value = world * B * args.steps / (ms_dev * 1e-3)
+
+    # ---- per-kernel times (CUDA events between launches on the launching stream), rank 0 ----
+    prof = []
+    if rank == 0:
+        h.set_profiling(True)
+        for i in range(args.steps):
+            step_device(i)
+        stream.synchronize()
+        prof = h.get_profile()
+        h.set_profiling(False)
+    barrier()
+
+    # ---- end to end through the reference-facing call, pinned host buffers ----
+    def step_host(i):
+        h.infer_raw("rn_infer_u8_bgr", host_sets[i % N_INPUT_SETS].data_ptr(), B, h_top1.data_ptr(),
+                    h_probs.data_ptr(), None)
+
+    for i in range(args.warmup):
+        step_host(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(i)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * B * args.steps / float(t.item())
+    barrier()
+
+    if rank == 0:
+        peaks = load_peaks()
+        roofline = None
+        if prof:
+            total_ms = sum(p["ms"] for p in prof)
+            top = max(prof, key=lambda p: p["ms"])
+            layer = int("".join(ch for ch in top["name"] if ch.isdigit()) or 0) if top["name"].startswith("conv") else None
+            if layer is not None:
+                flops_per_launch = conv_flops(layer) * B * args.steps / top["launches"]
+                achieved = flops_per_launch / (top["ms"] / top["launches"] * 1e-3) / 1e12
+                roofline = {"bound": "tensor", "kernel": top["name"], "achieved": achieved, "peak": peaks["tflops"],
+                            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                            "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
+                            "share_of_step": top["ms"] / total_ms,
+                            "whole_path": {"achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
+                                           "frac": value / world * FLOP_PER_IMAGE_224 / 1e12 / peaks["tflops"]},
+                            "kernels_ms_per_step": {p["name"]: round(p["ms"] / args.steps, 4) for p in prof}}
+        cpu = None
+        if not args.no_cpu_baseline:
+            ips, cores, p50 = cpu_reference_throughput(64)
+            cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "p50_ms": p50,
+                   "sample": "64 batch-1 synthetic 224x224 images, sequential (BASELINE config 1), torch-CPU fp32 "
+                             "restatement of the reference graph (TensorFlow 1.13.1 not installable)"}
+        line = {
+            "metric": "images_per_sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": "RoomNet final_model @224x224 inference, batch %d per GPU, BN folded, %s operands / "
+                                   "fp32 accumulate" % (B, args.precision),
+                       "batch_per_gpu": B, "l2_policy": "%d distinct input batches (%.0f MB) cycled; activations "
+                                                        "(%.0f MB per micro-batch) exceed L2" % (
+                                                            N_INPUT_SETS, N_INPUT_SETS * B * 150528 / 1e6, 14.3 * 64),
+                       "parallelism": "replicas x%d (no collective)" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 224 * 224 * 3,
+                    "d2h_bytes_per_step": B * (8 + 24)},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

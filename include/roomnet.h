@@ -117,6 +117,10 @@ int rn_get_folded(rn_handle* h, const char* name, float* out, int64_t capacity, 
 int rn_debug_activation(rn_handle* h, int32_t layer, float* out, int64_t capacity, int64_t* size, int32_t dims[4]);
 int rn_get_stats(rn_handle* h, double* p50_ms, double* p99_ms, int64_t* calls, int64_t* images);
 int rn_reset_stats(rn_handle* h);
+/* Per-kernel device times of replica 0 (CUDA events recorded between launches on the launching
+ * stream) accumulated since profiling was enabled / last read; used by bench.py for the roofline. */
+int rn_set_profiling(rn_handle* h, int32_t enabled);
+int rn_get_profile(rn_handle* h, int32_t capacity, int32_t* count, char names[][32], double* ms, int32_t* launches);
 
 /* Error text of the last failing call on this handle (or of rn_create when h is NULL). */
 const char* rn_last_error(const rn_handle* h);

@@ -63,6 +63,8 @@ def _load():
         "rn_debug_activation": ([vp, i32, f32p, C.c_int64, i64p, C.POINTER(i32)], C.c_int),
         "rn_get_stats": ([vp, C.POINTER(C.c_double), C.POINTER(C.c_double), i64p, i64p], C.c_int),
         "rn_reset_stats": ([vp], C.c_int),
+        "rn_set_profiling": ([vp, i32], C.c_int),
+        "rn_get_profile": ([vp, i32, C.POINTER(i32), vp, C.POINTER(C.c_double), C.POINTER(i32)], C.c_int),
         "rn_last_error": ([vp], C.c_char_p),
         "rn_version": ([], C.c_char_p),
     }
@@ -77,7 +79,8 @@ lib = _load()
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_u8_bgr_device",
             "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
-            "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_last_error", "rn_version"]
+            "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
+            "rn_last_error", "rn_version"]
 
 
 class Handle:
@@ -190,6 +193,18 @@ class Handle:
         calls, images = C.c_int64(), C.c_int64()
         self._check(lib.rn_get_stats(self._h, C.byref(p50), C.byref(p99), C.byref(calls), C.byref(images)))
         return dict(p50_ms=p50.value, p99_ms=p99.value, calls=calls.value, images=images.value)
+
+    def set_profiling(self, on):
+        self._check(lib.rn_set_profiling(self._h, 1 if on else 0))
+
+    def get_profile(self):
+        cap = 64
+        names = (C.c_char * 32 * cap)()
+        ms = (C.c_double * cap)()
+        launches = (C.c_int32 * cap)()
+        count = C.c_int32()
+        self._check(lib.rn_get_profile(self._h, cap, C.byref(count), C.cast(names, C.c_void_p), ms, launches))
+        return [dict(name=names[i].value.decode(), ms=ms[i], launches=launches[i]) for i in range(min(cap, count.value))]
 
     def reset_stats(self):
         self._check(lib.rn_reset_stats(self._h))

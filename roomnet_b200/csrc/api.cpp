@@ -321,6 +321,31 @@ int rn_get_stats(rn_handle* h, double* p50_ms, double* p99_ms, int64_t* calls, i
   return RN_OK;
 }
 
+int rn_set_profiling(rn_handle* h, int32_t enabled) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  for (auto& r : h->replicas) r->set_profiling(enabled != 0);
+  return RN_OK;
+}
+
+int rn_get_profile(rn_handle* h, int32_t capacity, int32_t* count, char names[][32], double* ms, int32_t* launches) {
+  if (!h || !count) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle");
+  std::vector<rn::Replica::KernelTime> v;
+  if (h->replicas[0]->ProfileResults(&v) != cudaSuccess) return Fail(h, RN_ERR_CUDA, h->replicas[0]->error());
+  *count = static_cast<int32_t>(v.size());
+  for (int i = 0; i < *count && i < capacity; ++i) {
+    if (names) {
+      std::strncpy(names[i], v[i].name.c_str(), 31);
+      names[i][31] = 0;
+    }
+    if (ms) ms[i] = v[i].ms;
+    if (launches) launches[i] = v[i].launches;
+  }
+  return RN_OK;
+}
+
 int rn_reset_stats(rn_handle* h) {
   if (!h) return RN_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(h->mu);

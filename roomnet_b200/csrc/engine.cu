@@ -32,6 +32,7 @@ Replica::~Replica() {
   if (compute_) cudaStreamSynchronize(compute_);
   if (copy_) cudaStreamSynchronize(copy_);
   for (void* p : allocs_) cudaFree(p);
+  for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (h_in_[i]) cudaFreeHost(h_in_[i]);
     if (h_out_[i]) cudaFreeHost(h_out_[i]);
@@ -171,21 +172,55 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
   return cudaSuccess;
 }
 
+void Replica::Mark(const char* name, cudaStream_t st) {
+  if (name) ++last_launches_;
+  if (!profiling_) return;
+  if (prof_used_ == prof_events_.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    prof_events_.push_back(e);
+    prof_names_.push_back("");
+  }
+  cudaEventRecord(prof_events_[prof_used_], st);
+  prof_names_[prof_used_] = name ? name : "";  // name of the kernel that ENDS at this event
+  ++prof_used_;
+}
+
+cudaError_t Replica::ProfileResults(std::vector<KernelTime>* out) {
+  RN_CUDA(cudaSetDevice(device_));
+  RN_CUDA(cudaDeviceSynchronize());
+  out->clear();
+  for (size_t i = 1; i < prof_used_; ++i) {
+    if (prof_names_[i].empty()) continue;  // start marker of a micro-batch
+    float ms = 0.f;
+    RN_CUDA(cudaEventElapsedTime(&ms, prof_events_[i - 1], prof_events_[i]));
+    auto it = std::find_if(out->begin(), out->end(), [&](const KernelTime& k) { return k.name == prof_names_[i]; });
+    if (it == out->end()) {
+      out->push_back(KernelTime{prof_names_[i], 0.0, 0});
+      it = out->end() - 1;
+    }
+    it->ms += ms;
+    it->launches += 1;
+  }
+  prof_used_ = 0;
+  return cudaSuccess;
+}
+
 cudaError_t Replica::TailF32(int first_layer, int n, cudaStream_t st) {
   for (int i = first_layer; i < kNumConvs; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const float* in = shape_.conv[i - 1].join_src >= 0 ? joined_[i - 1] : pooled_[i - 1];
     float* conv_out = cs.pool_k ? conv_scratch_ : pooled_[i];
     RN_CUDA(Conv3x3Relu6F32<float>(in, cw_[i], cb_[i], conv_out, n, cs.in_side, cs.in_side, cs.cin, cs.cout, st));
-    ++last_launches_;
+    Mark(("conv" + std::to_string(i) + "_f32").c_str(), st);
     if (cs.pool_k) {
       RN_CUDA(AvgPoolF32(conv_scratch_, pooled_[i], n, cs.conv_side, cs.conv_side, cs.cout, cs.pool_k, cs.pool_s, st));
-      ++last_launches_;
+      Mark(("pool" + std::to_string(i) + "_f32").c_str(), st);
     }
     if (cs.join_src >= 0) {
       RN_CUDA(JoinF32(pooled_[i], pooled_[cs.join_src], joined_[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
                       shape_.conv[cs.join_src].out_side, cs.cout, st));
-      ++last_launches_;
+      Mark(("join" + std::to_string(i) + "_f32").c_str(), st);
     }
   }
   return cudaSuccess;
@@ -194,41 +229,44 @@ cudaError_t Replica::TailF32(int first_layer, int n, cudaStream_t st) {
 cudaError_t Replica::ForwardF32(const void* d_in, InputKind kind, int n, cudaStream_t st) {
   const ConvShape& c0 = shape_.conv[0];
   const int k = static_cast<int>(kind);
+  Mark(nullptr, st);
   if (kind == InputKind::kF32Rgb)
     RN_CUDA(Conv3x3Relu6F32<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], conv_scratch_, n, c0.in_side,
                                    c0.in_side, 3, c0.cout, st));
   else
     RN_CUDA(Conv3x3Relu6F32<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], conv_scratch_, n, c0.in_side,
                                      c0.in_side, 3, c0.cout, st));
+  Mark("conv0_f32", st);
   RN_CUDA(AvgPoolF32(conv_scratch_, pooled_[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
-  last_launches_ += 2;
+  Mark("pool0_f32", st);
   return TailF32(1, n, st);
 }
 
 cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, cudaStream_t st) {
   const ConvShape& c0 = shape_.conv[0];
   const int k = static_cast<int>(kind);
+  Mark(nullptr, st);
   if (kind == InputKind::kF32Rgb)
     RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side, half_kind_, st));
   else
     RN_CUDA(Conv0PoolH<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side,
                                 half_kind_, st));
-  ++last_launches_;
+  Mark("conv0_pool_h", st);
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const void* in = shape_.conv[i - 1].join_src >= 0 ? join_h_[i - 1] : act_h_[i - 1];
     RN_CUDA(ConvTc(tc_[i], in, act_h_[i], n, half_kind_, st));
-    ++last_launches_;
+    Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
     if (cs.join_src >= 0) {
       RN_CUDA(JoinH(act_h_[i], act_h_[cs.join_src], join_h_[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
                     shape_.conv[cs.join_src].out_side, cs.cout, half_kind_, st));
-      ++last_launches_;
+      Mark(("join" + std::to_string(i) + "_h").c_str(), st);
     }
   }
   const int last = first_f32_layer_ - 1;
   const ConvShape& cl = shape_.conv[last];
   RN_CUDA(ChunkedToF32(act_h_[last], pooled_[last], n, cl.out_side, cl.cout, half_kind_, st));
-  ++last_launches_;
+  Mark("chunked_to_f32", st);
   return TailF32(first_f32_layer_, n, st);
 }
 
@@ -243,7 +281,7 @@ cudaError_t Replica::ForwardDevice(const void* d_in, InputKind kind, int n, long
   const ConvShape& cl = shape_.conv[kNumConvs - 1];
   const float* flat = cl.join_src >= 0 ? joined_[kNumConvs - 1] : pooled_[kNumConvs - 1];
   RN_CUDA(DenseTailF32(flat, n, shape_.flat_len, dense_, d_top1, d_probs, d_logits, d_pre_, st));
-  ++last_launches_;
+  Mark("dense_tail", st);
   last_n_ = n;
   return cudaSuccess;
 }

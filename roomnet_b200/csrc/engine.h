@@ -38,6 +38,14 @@ class Replica {
                           float* d_logits, cudaStream_t st);
 
   int last_launches() const { return last_launches_; }
+  // Per-kernel device timing (CUDA events on the launching stream, recorded between launches).
+  void set_profiling(bool on) { profiling_ = on; }
+  struct KernelTime {
+    std::string name;
+    double ms = 0;
+    int launches = 0;
+  };
+  cudaError_t ProfileResults(std::vector<KernelTime>* out);
   // Debug: copies the output of conv layer `layer` (pooled, after the residual join where there is
   // one) of the last micro-batch to host as NHWC fp32.
   cudaError_t DebugActivation(int layer, std::vector<float>* out, int dims[4]);
@@ -56,6 +64,11 @@ class Replica {
   std::string err_;
   int last_launches_ = 0;
   int last_n_ = 0;
+  bool profiling_ = false;
+  std::vector<cudaEvent_t> prof_events_;
+  std::vector<std::string> prof_names_;  // prof_names_[i] = kernel between event i and i+1 ("" = gap)
+  size_t prof_used_ = 0;
+  void Mark(const char* name, cudaStream_t st);
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
   cudaEvent_t ev_h2d_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};

@@ -1,0 +1,147 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle — needs a B200.
+
+Budgets (BASELINE.json north_star): identical top-1 on every image; max |dlogit| <= 1e-3 on the
+FP32 path and <= 2e-2 on the 16-bit tensor-core path, logit = post-ReLU6 out_op (network.py:43).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-3, "fp16": 2e-2}
+
+
+@pytest.fixture(scope="module")
+def oracle32():
+    from oracle.roomnet_oracle import RoomNetOracle
+    return RoomNetOracle(dtype=np.float32, conv_backend="torch").load()
+
+
+def _handle(capi, ckpt_prefix, precision, **kw):
+    h = capi.Handle(precision=precision, **kw)
+    h.load_tf_checkpoint(ckpt_prefix)
+    return h
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_suite64_matches_golden(capi, ckpt_prefix, suite64, golden, precision):
+    h = _handle(capi, ckpt_prefix, precision)
+    top1, probs, logits = h.infer_u8_bgr(suite64, want_logits=True)
+    assert h.kernel_launches > 0
+    err = np.abs(logits - golden["logits"]).max()
+    print("%s: max|dlogit| vs golden = %.3e, max|dsoftmax| = %.3e" % (precision, err, np.abs(probs - golden["softmax"]).max()))
+    assert np.array_equal(top1, golden["argmax"])
+    assert err <= TOL[precision]
+    np.testing.assert_allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_per_layer_activations(capi, ckpt_prefix, suite64, weights, precision):
+    """Every conv block output (pooled, after the residual join) against the folded fp64 oracle."""
+    from oracle.fold import fold, folded_forward
+    imgs = suite64[:4]
+    ref = folded_forward(fold(weights), imgs, dtype=np.float64, conv_backend="torch", collect=True)["tensors"]
+    h = _handle(capi, ckpt_prefix, precision)
+    h.infer_u8_bgr(imgs)
+    for layer in range(10):
+        got = h.debug_activation(layer)
+        want = ref[layer]
+        assert got.shape == want.shape, layer
+        scale = np.abs(want).max() + 1e-6
+        rel = np.abs(got - want).max() / scale
+        print("layer %d %s max rel err %.3e (absmax %.3f)" % (layer, got.shape, rel, scale))
+        assert rel <= (2e-5 if precision == "fp32" else 6e-3), "layer %d" % layer
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_feed_variants_agree(capi, ckpt_prefix, suite64, oracle32, precision):
+    """u8 BGR (RoomNet.infer), u8 RGB (quantised Java path) and float RGB (raw sess.run feed)."""
+    h = _handle(capi, ckpt_prefix, precision)
+    imgs = suite64[:8]
+    t0, p0, l0 = h.infer_u8_bgr(imgs, want_logits=True)
+    t1, p1, l1 = h.infer_u8_rgb(np.ascontiguousarray(imgs[..., ::-1]), want_logits=True)
+    x = oracle32.normalise(imgs).astype(np.float32)
+    t2, p2, l2 = h.infer_f32_rgb(x, want_logits=True)
+    assert np.array_equal(t0, t1) and np.array_equal(t0, t2)
+    # same arithmetic with the input-channel axis permuted: only the fp32 summation order differs
+    assert np.abs(l0 - l1).max() <= (1e-4 if precision == "fp32" else 2e-3)
+    assert np.abs(l0 - l2).max() <= TOL[precision]
+    ref = oracle32.forward(x)
+    assert np.abs(l2 - ref["logits"]).max() <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_batch_position_independence(capi, ckpt_prefix, suite64, precision):
+    """Bit-identical results whatever the batch size / micro-batch split (SURVEY §8e determinism)."""
+    h_big = _handle(capi, ckpt_prefix, precision, max_batch=64)
+    h_small = _handle(capi, ckpt_prefix, precision, max_batch=5)
+    _, _, full = h_big.infer_u8_bgr(suite64[:23], want_logits=True)
+    _, _, split = h_small.infer_u8_bgr(suite64[:23], want_logits=True)
+    assert np.array_equal(full, split)
+    for i in (0, 7, 22):
+        _, _, one = h_big.infer_u8_bgr(suite64[i:i + 1], want_logits=True)
+        assert np.array_equal(one[0], full[i])
+    perm = np.random.default_rng(0).permutation(23)
+    _, _, shuffled = h_big.infer_u8_bgr(suite64[:23][perm], want_logits=True)
+    assert np.array_equal(shuffled, full[perm])
+
+
+def test_ties_resolve_to_first_index(capi, ckpt_prefix):
+    """All-zero image: four logits clip to 0 — argmax must still be class 2, probs tie exactly."""
+    h = _handle(capi, ckpt_prefix, "fp32")
+    top1, probs, logits = h.infer_u8_bgr(np.zeros((1, 224, 224, 3), np.uint8), want_logits=True)
+    assert top1[0] == 2
+    np.testing.assert_allclose(probs[0], [0.047912, 0.087261, 0.721090, 0.047912, 0.047912, 0.047912], atol=2e-5)
+    assert logits[0][0] == 0 and logits[0][3] == 0 and logits[0][4] == 0 and logits[0][5] == 0
+
+
+def test_error_behaviour(capi, ckpt_prefix):
+    h = capi.Handle(precision="fp32")
+    with pytest.raises(capi.RoomNetError) as e:  # FailedPrecondition analogue: variables not restored
+        h.infer_u8_bgr(np.zeros((1, 224, 224, 3), np.uint8))
+    assert e.value.code == capi.RN_ERR_NOT_LOADED
+    h.load_tf_checkpoint(ckpt_prefix)
+    with pytest.raises(capi.RoomNetError) as e:  # InvalidArgumentError analogue: feed shape mismatch
+        h.infer_u8_bgr(np.zeros((1, 200, 200, 3), np.uint8))
+    assert e.value.code == capi.RN_ERR_INVALID_ARG
+    top1, probs = h.infer_u8_bgr(np.zeros((0, 224, 224, 3), np.uint8))
+    assert top1.shape == (0,) and probs.shape == (0, 6)
+    with pytest.raises(capi.RoomNetError) as e:
+        capi.Handle(devices=(99,))
+    assert e.value.code == capi.RN_ERR_CUDA
+
+
+@pytest.mark.parametrize("side", [300])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_other_resolutions(capi, ckpt_prefix, weights, precision, side):
+    """README's alternate resolutions with a synthesised dense/kernel (BASELINE config 4)."""
+    from oracle.roomnet_oracle import RoomNetOracle, synthetic_dense0, synthetic_suite
+    d0 = synthetic_dense0(side)
+    imgs = synthetic_suite(4, side)
+    orc = RoomNetOracle(im_side=side, dtype=np.float32, weights=weights, dense0_kernel=d0, conv_backend="torch")
+    ref = orc.forward(orc.normalise(imgs))
+    h = capi.Handle(im_side=side, precision=precision)
+    h.set_dense0(d0)
+    h.load_tf_checkpoint(ckpt_prefix)
+    top1, probs, logits = h.infer_u8_bgr(imgs, want_logits=True)
+    err = np.abs(logits - ref["logits"]).max()
+    print("side %d %s: max|dlogit| %.3e" % (side, precision, err))
+    assert np.array_equal(top1, ref["argmax"])
+    assert err <= TOL[precision]
+
+
+def test_drop_in_roomnet_class(ckpt_prefix, suite64, golden):
+    """The reference's call shape: RoomNet(...).load(path); infer_optimized(im) -> (int64[1], f32[1,6])."""
+    from roomnet_b200 import RoomNet
+    nn = RoomNet(num_classes=6, im_side=224, compute_bn_mean_var=False, optimized_inference=True)
+    nn.load(ckpt_prefix)
+    for i in (0, 1, 2, 3):
+        idx, conf = nn.infer_optimized(suite64[i])
+        assert idx.dtype == np.int64 and idx.shape == (1,) and conf.shape == (1, 6) and conf.dtype == np.float32
+        assert idx[0] == golden["argmax"][i]
+    idx, conf = nn.infer(suite64[:16])
+    assert np.array_equal(idx, golden["argmax"][:16])
+    nn2 = RoomNet(num_classes=6, im_side=224, compute_bn_mean_var=False, precision="fp32")
+    nn2.load(ckpt_prefix)
+    out = nn2.infer(suite64[:16])  # non-optimized graph returns argmax only (network.py:72)
+    assert isinstance(out, np.ndarray) and np.array_equal(out, golden["argmax"][:16])
