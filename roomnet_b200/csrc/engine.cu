@@ -96,6 +96,7 @@ cudaError_t Replica::Init() {
       }
     }
   }
+  if (first_f32_layer_ > 0) RN_CUDA(Alloc(&in_h_, ChunkedBytes(max_batch_, shape_.im_side, 8)));
   const size_t in_bytes = InputBytesPerImage(shape_, InputKind::kF32Rgb) * B;
   for (int i = 0; i < 2; ++i) {
     RN_CUDA(Alloc(&d_in_[i], in_bytes));
@@ -147,8 +148,40 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
     dense_.out[i] = shape_.dense_out[i];
   }
   if (precision_ != RN_PREC_FP32) {
+    // conv0: both the tensor-core kernel (uint8 feeds) and the CUDA-core kernel (float feed) store
+    // sum_3x3(relu6)/6 = 1.5 x the pooled mean
+    act_scale_[0] = 9.0 / 6.0;
+    {
+      const ConvShape& c0 = shape_.conv[0];
+      TcConvLayer& L = tc_[0];
+      L.cin = 8;
+      L.cout = 16;
+      L.in_side = c0.in_side;
+      L.pool_k = c0.pool_k;
+      L.pool_s = c0.pool_s;
+      L.out_side = c0.out_side;
+      L.cout_parts = 1;
+      L.amode = 2;
+      std::vector<double> b6(16, 0.0);
+      for (int k = 0; k < 8; ++k) b6[k] = f.conv0_u8bgr.b[k] / 6.0;  // identical for BGR and RGB byte order
+      RN_CUDA(UploadF32(b6, &tc_bias_[0]));
+      L.bias = tc_bias_[0];
+      L.w_bytes = PackTcConv0Weights(nullptr, half_kind_, 1.0, nullptr);
+      const FoldedConv* src[2] = {&f.conv0_u8bgr, &f.conv0_u8rgb};
+      for (int k = 0; k < 2; ++k) {
+        std::vector<uint8_t> host(L.w_bytes);
+        // activations are fed as pixel/256 (exact), so the weights carry 256/6
+        PackTcConv0Weights(src[k]->w.data(), half_kind_, 256.0 / 6.0, host.data());
+        if (!tc0_w_[k]) RN_CUDA(Alloc(&tc0_w_[k], host.size()));
+        RN_CUDA(cudaMemcpy(tc0_w_[k], host.data(), host.size(), cudaMemcpyHostToDevice));
+      }
+    }
     for (int i = 1; i < first_f32_layer_; ++i) {
       const ConvShape& cs = shape_.conv[i];
+      const bool in_is_join = shape_.conv[i - 1].join_src >= 0;
+      const double g_in = in_is_join ? 1.0 : act_scale_[i - 1];
+      // the kernel computes saturate(conv(stored_in, W') + b') == relu6(z)/6 and stores the pool-window SUM
+      act_scale_[i] = (cs.pool_k ? cs.pool_k * cs.pool_k : 1) / 6.0;
       TcConvLayer& L = tc_[i];
       L.cin = cs.cin;
       L.cout = cs.cout;
@@ -157,15 +190,25 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
       L.pool_s = cs.pool_s;
       L.out_side = cs.out_side;
       L.cout_parts = cs.cout > 64 ? cs.cout / 64 : 1;
-      L.bias = cb_[i];
-      size_t part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, nullptr);
+      std::vector<double> b6(f.conv[i].b.size());
+      for (size_t k = 0; k < b6.size(); ++k) b6[k] = f.conv[i].b[k] / 6.0;
+      RN_CUDA(UploadF32(b6, &tc_bias_[i]));
+      L.bias = tc_bias_[i];
+      size_t part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0, nullptr);
       std::vector<uint8_t> host(part_bytes * L.cout_parts);
-      PackTcWeights(f.conv[i].w.data(), cs.cin, cs.cout, L.cout_parts, half_kind_, host.data());
+      PackTcWeights(f.conv[i].w.data(), cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0 / (6.0 * g_in), host.data());
       void* d = const_cast<void*>(L.w_packed);
       if (!d) RN_CUDA(Alloc(&d, host.size()));
       RN_CUDA(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
       L.w_packed = d;
       L.w_bytes = part_bytes;
+      if (cs.join_src >= 0) {  // out = (A/g_k) * stored_k + (B/g_0) * resize(stored_0) + C  -> true scale
+        std::vector<double> a(f.join[i].a), b(f.join[i].b);
+        for (auto& v : a) v /= act_scale_[i];
+        for (auto& v : b) v /= act_scale_[cs.join_src];
+        RN_CUDA(UploadF32(a, &tc_ja_[i]));
+        RN_CUDA(UploadF32(b, &tc_jb_[i]));
+      }
     }
   }
   loaded_ = true;
@@ -246,26 +289,33 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, cudaStre
   const ConvShape& c0 = shape_.conv[0];
   const int k = static_cast<int>(kind);
   Mark(nullptr, st);
-  if (kind == InputKind::kF32Rgb)
+  if (kind == InputKind::kF32Rgb) {
+    // raw float feed: operands need more than 11 bits, keep conv0 in fp32 on the CUDA cores
     RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side, half_kind_, st));
-  else
-    RN_CUDA(Conv0PoolH<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side,
-                                half_kind_, st));
-  Mark("conv0_pool_h", st);
+    Mark("conv0_pool_h", st);
+  } else {
+    RN_CUDA(PrepU8(static_cast<const uint8_t*>(d_in), in_h_, n, c0.in_side, half_kind_, st));
+    Mark("prep_u8", st);
+    TcConvLayer L0 = tc_[0];
+    L0.w_packed = tc0_w_[k];
+    RN_CUDA(ConvTc(L0, in_h_, act_h_[0], n, half_kind_, st));
+    Mark("conv0_tc", st);
+  }
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const void* in = shape_.conv[i - 1].join_src >= 0 ? join_h_[i - 1] : act_h_[i - 1];
     RN_CUDA(ConvTc(tc_[i], in, act_h_[i], n, half_kind_, st));
     Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
     if (cs.join_src >= 0) {
-      RN_CUDA(JoinH(act_h_[i], act_h_[cs.join_src], join_h_[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
+      RN_CUDA(JoinH(act_h_[i], act_h_[cs.join_src], join_h_[i], tc_ja_[i], tc_jb_[i], jc_[i], n, cs.out_side,
                     shape_.conv[cs.join_src].out_side, cs.cout, half_kind_, st));
       Mark(("join" + std::to_string(i) + "_h").c_str(), st);
     }
   }
   const int last = first_f32_layer_ - 1;
   const ConvShape& cl = shape_.conv[last];
-  RN_CUDA(ChunkedToF32(act_h_[last], pooled_[last], n, cl.out_side, cl.cout, half_kind_, st));
+  RN_CUDA(ChunkedToF32(act_h_[last], pooled_[last], n, cl.out_side, cl.cout, half_kind_,
+                       static_cast<float>(1.0 / act_scale_[last]), st));
   Mark("chunked_to_f32", st);
   return TailF32(first_f32_layer_, n, st);
 }
@@ -385,7 +435,8 @@ cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dim
   } else {
     RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), elems * sizeof(float)));
     const void* h = cs.join_src >= 0 ? join_h_[layer] : act_h_[layer];
-    cudaError_t e = ChunkedToF32(h, tmp, last_n_, cs.out_side, cs.cout, half_kind_, compute_);
+    const float sc = cs.join_src >= 0 ? 1.f : static_cast<float>(1.0 / act_scale_[layer]);
+    cudaError_t e = ChunkedToF32(h, tmp, last_n_, cs.out_side, cs.cout, half_kind_, sc, compute_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(compute_);
     if (e != cudaSuccess) {
       cudaFree(tmp);

@@ -85,6 +85,14 @@ class Replica {
   DenseParams dense_{};
   // 16-bit packed weights
   TcConvLayer tc_[kNumConvs] = {};
+  // 16-bit path bookkeeping: stored activation = true value * act_scale_[i]  (k*k/6 after a pooled
+  // tensor-core layer, 1 for conv0 and for residual-join outputs)
+  double act_scale_[kNumConvs] = {};
+  float* tc_bias_[kNumConvs] = {};
+  void* tc0_w_[2] = {nullptr, nullptr};  // conv0 packed weights for uint8 BGR / RGB byte order
+  void* in_h_ = nullptr;                // uint8 image expanded to pixel-pair chunks (PrepU8)
+  float* tc_ja_[kNumConvs] = {};
+  float* tc_jb_[kNumConvs] = {};
   HalfKind half_kind_ = HalfKind::kF16;
 
   // activations

@@ -40,14 +40,22 @@ struct TcConvLayer {
   const void* w_packed;   // device, packed by PackTcWeights
   size_t w_bytes;         // bytes per cout-part
   int cout_parts;         // cout is processed in `cout_parts` passes of cout/cout_parts channels
-  const float* bias;      // device [cout]
+  const float* bias;      // device [cout], already divided by 6 (the kernel clips with saturate)
+  int amode = 0;          // 2 = conv0 (uint8 image pre-expanded by PrepU8)
 };
 
 // Size in bytes of an activation tensor in chunked layout, incl. over-read slack.
 size_t ChunkedBytes(int n, int side, int channels);
 
 // Host-side weight packer: HWIO fp64 -> per-part shared-memory image of the conv_tc kernel.
-size_t PackTcWeights(const double* w_hwio, int cin, int cout, int cout_parts, HalfKind kind, void* out_host);
+// `scale` multiplies every weight before rounding (stored-activation scale bookkeeping, see engine.cu).
+size_t PackTcWeights(const double* w_hwio, int cin, int cout, int cout_parts, HalfKind kind, double scale,
+                     void* out_host);
+
+// conv0 on the tensor cores: weights [3][3][3][8] (uint8-folded) split into fp16 hi + lo halves.
+size_t PackTcConv0Weights(const double* w_hwio, HalfKind kind, double scale, void* out_host);
+// uint8 NHWC image -> pixel-pair chunks (values / 256, exact) consumed by conv0's A descriptor.
+cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st);
 
 cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st);
 
@@ -59,6 +67,6 @@ cudaError_t Conv0PoolH(const TIn* in, const float* w, const float* b, void* out,
 cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, const float* B, const float* C, int N,
                   int S, int SS, int Ch, HalfKind kind, cudaStream_t st);
 // chunked 16-bit -> NHWC fp32
-cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, cudaStream_t st);
+cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale, cudaStream_t st);
 
 }  // namespace rn

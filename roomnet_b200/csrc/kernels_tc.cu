@@ -39,7 +39,7 @@ constexpr int kPlanePx = 136;         // pixels per channel-chunk plane in a sme
 constexpr int kPlaneBytes = kPlanePx * 16;
 constexpr int kLoadPx = 132;          // pixels fetched per plane row (128 + taps, 16B multiple)
 constexpr int kSlackBytes = 4096;     // over-read slack behind every chunked tensor
-constexpr int kThreads = 192;         // warp 0 TMA producer, warp 1 MMA issuer, warps 2..5 epilogue
+constexpr int kThreads = 192;         // (v1 layout, kept for the small helper kernels)
 constexpr int kSmemBudget = 227 * 1024;
 
 // ------------------------------------------------------------------ PTX ----
@@ -144,30 +144,48 @@ struct TcParams {
   int n_rowblocks;
   int n_items;
   int w_bytes;        // packed weight bytes per part
-  int bf16;
 };
 
-template <int CB, int COUT>
+// POOL modes: 0 = none, 31 = 3x3/1, 41 = 4x4/1, 42 = 4x4/2.  The kernel stores the window SUM of
+// saturate(conv/6): the factors k*k and 6 are folded into the consumer's weights by the host.
+// AMODE: 0 = channel-chunk planes (Cin >= 16), 1 = Cin 8: pixel pairs form a K=16 step (LBO = 16 B),
+//        2 = conv0: a 16-byte chunk holds pixels (x, x+1) x (c0,c1,c2,0); chunks x and x+2 (LBO = 32 B) form one
+//            K=16 step that covers all three dx taps; the two k-steps are the hi and lo halves of the weights
+template <int CB, int COUT, int AMODE>
 struct TcCfg {
-  static constexpr bool kPaired = (CB == 1);                 // Cin = 8: two adjacent pixels form one K=16 step
-  static constexpr int kPlanes = kPaired ? 4 : 3 * CB;       // weight planes (dx-major)
-  static constexpr int kKSteps = kPaired ? 2 : 3 * (CB / 2); // MMAs per input row (before ring splits)
+  static constexpr int kPlanes = AMODE == 0 ? 3 * CB : 4;       // weight planes
+  static constexpr int kKSteps = AMODE == 0 ? 3 * (CB / 2) : 2; // MMAs per input row
   static constexpr int kSlots = (512 / COUT) > 16 ? 16 : (512 / COUT);
+  static constexpr int kLogSlots = kSlots == 16 ? 4 : 3;
+  static_assert(kSlots == 16 || kSlots == 8, "ring size must be a power of two");
   static constexpr int kTmemCols = kSlots * COUT;
   static constexpr int kWBytes = kPlanes * 3 * COUT * 16;
   static constexpr int kStageBytes = CB * kPlaneBytes;
-  static constexpr int kFixedBytes = kWBytes + COUT * 4 + 2 * 4 * COUT * 16 + 1024;
+  static constexpr int kXgBytes = 2 * 2 * 4 * 2 * (COUT / 4) * 16;  // [grp][parity][quad][out row][pair] uint4
+  static constexpr int kFixedBytes = kWBytes + COUT * 4 + kXgBytes + 1024;
   static constexpr int kStagesFit = (kSmemBudget - kFixedBytes) / kStageBytes;
-  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
   static_assert(kStages >= 3, "not enough shared memory for a 3-stage input ring");
+  // descriptor offsets (in 16-byte units) of k-step ks relative to the stage / weight base
+  __host__ __device__ static constexpr uint32_t a_off16(int ks) {
+    return AMODE == 0 ? static_cast<uint32_t>((2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * kPlanePx + ks / (CB / 2 > 0 ? CB / 2 : 1))
+           : AMODE == 1 ? static_cast<uint32_t>(2 * ks)
+                        : 0u;
+  }
+  __host__ __device__ static constexpr uint32_t b_off16(int ks) {
+    return AMODE == 0 ? static_cast<uint32_t>(((ks / (CB / 2 > 0 ? CB / 2 : 1)) * CB + 2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * 3 * COUT)
+                      : static_cast<uint32_t>(2 * ks * 3 * COUT);
+  }
+  static constexpr uint32_t kALbo16 = AMODE == 0 ? kPlanePx : (AMODE == 1 ? 1 : 2);  // K-direction core-matrix stride / 16
+  static constexpr uint32_t kBLbo16 = 3 * COUT;
 };
 
 struct Item {
   int n0, x_in0, x_out0, po0, npo, c0, nconv;
 };
 
-template <int POOL_S, int SEG>
+template <int POOL, int SEG>
 __device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
   Item it;
   int rb = item % p.n_rowblocks;
@@ -179,44 +197,115 @@ __device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
   it.x_out0 = strip * p.strip_step_out;
   it.po0 = rb * p.rows_per_item;
   it.npo = min(p.rows_per_item, p.out_side - it.po0);
-  if (POOL_S == 0) {
+  if (POOL == 0) {
     it.c0 = it.po0;
     it.nconv = it.npo;
+  } else if (POOL == 42) {
+    it.c0 = it.po0 * 2;
+    it.nconv = (it.npo - 1) * 2 + 4;
   } else {
-    it.c0 = it.po0 * POOL_S;
-    it.nconv = (it.npo - 1) * POOL_S + 4;
+    it.c0 = it.po0;
+    it.nconv = it.npo + (POOL == 41 ? 3 : 2);
   }
   return it;
 }
 
+template <bool BF16>
+struct H2 {
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    if constexpr (BF16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    if constexpr (BF16) {
+      __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    } else {
+      __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  __device__ static __forceinline__ uint32_t sixteenth(uint32_t a) {  // exact: power-of-two scale
+    if constexpr (BF16) {
+      __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), __floats2bfloat162_rn(0.0625f, 0.0625f));
+      return *reinterpret_cast<uint32_t*>(&r);
+    } else {
+      __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), __floats2half2_rn(0.0625f, 0.0625f));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+};
+
+__device__ __forceinline__ void tc_mma_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                           uint32_t idesc) {
+  // D[tmem] += A[smem] * B[smem]; both descriptors share the high word (SBO = 128 B, version 1, no swizzle)
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+constexpr int kThreadsTc = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (2 channel groups x 4 quadrants)
+
 // ---------------------------------------------------------------------------
-// CB     : input channel chunks (Cin/8)           COUT : output channels of this pass
-// POOL_S : 0 = no pooling, 1 = 4x4/1, 2 = 4x4/2   SEG  : images side by side in one 128-pixel tile
+// CB   : input channel chunks (Cin/8)         COUT : output channels of this pass
+// POOL : 0 / 31 / 41 / 42                     SEG  : images side by side in one 128-pixel tile
 // ---------------------------------------------------------------------------
-template <int CB, int COUT, int POOL_S, int SEG>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams p) {
-  using Cfg = TcCfg<CB, COUT>;
+// CREAL: channels actually produced (<= COUT; conv0 pads 8 -> 16 to satisfy UMMA N % 16 == 0)
+template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT>
+__global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p) {
+  using Cfg = TcCfg<CB, COUT, AMODE>;
+  using HH = H2<BF16>;
   constexpr int R = Cfg::kSlots;
+  constexpr int LOGR = Cfg::kLogSlots;
   constexpr int NST = Cfg::kStages;
   constexpr int SEGW = kTileM / SEG;
+  constexpr int NG = CREAL >= 16 ? 2 : 1;  // epilogue channel groups (4 warps each)
+  constexpr int CG = CREAL / NG;           // channels per epilogue group
+  constexpr int NP = CG / 2;     // half2 pairs per thread
   constexpr uint32_t kStageTx = CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16);
+  constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_w = smem;                                            // packed weights
-  uint8_t* s_stage = smem + Cfg::kWBytes;                         // NST input-row stages
+  uint8_t* s_w = smem;
+  uint8_t* s_stage = smem + Cfg::kWBytes;
   float* s_bias = reinterpret_cast<float*>(s_stage + NST * Cfg::kStageBytes);
-  float4* s_xchg = reinterpret_cast<float4*>(s_bias + COUT);      // [2][4 quads][COUT] ghost columns
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_xchg + 2 * 4 * COUT);
-  // barrier map: [0,NST) full, [NST,2NST) empty, 2NST weights, then R acc_full, R acc_empty
+  uint4* s_xg = reinterpret_cast<uint4*>(s_bias + COUT);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_xg) + Cfg::kXgBytes);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1 + 2 * R);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(s_bar);
-  auto bar_full = [&](int s) { return bar0 + 8u * s; };
-  auto bar_empty = [&](int s) { return bar0 + 8u * (NST + s); };
-  const uint32_t bar_w = bar0 + 8u * (2 * NST);
-  auto bar_accf = [&](int s) { return bar0 + 8u * (2 * NST + 1 + s); };
-  auto bar_acce = [&](int s) { return bar0 + 8u * (2 * NST + 1 + R + s); };
+  const uint32_t bar_full0 = bar0, bar_empty0 = bar0 + 8u * NST, bar_w = bar0 + 8u * (2 * NST);
+  const uint32_t bar_accf0 = bar0 + 8u * (2 * NST + 1), bar_acce0 = bar_accf0 + 8u * R;
 
   const int part = blockIdx.y;
   const uint8_t* w_gmem = p.w + static_cast<size_t>(part) * p.w_bytes;
@@ -224,13 +313,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams p) 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(bar_full(s), 1);
-      mbar_init(bar_empty(s), 1);
+      mbar_init(bar_full0 + 8u * s, 1);
+      mbar_init(bar_empty0 + 8u * s, 1);
     }
     mbar_init(bar_w, 1);
     for (int s = 0; s < R; ++s) {
-      mbar_init(bar_accf(s), 1);
-      mbar_init(bar_acce(s), 4);
+      mbar_init(bar_accf0 + 8u * s, 1);
+      mbar_init(bar_acce0 + 8u * s, 4 * NG);
     }
     fence_barrier_init();
   }
@@ -240,13 +329,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams p) 
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = bias_g[i];
+  for (int i = threadIdx.x; i < COUT; i += kThreadsTc) s_bias[i] = bias_g[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  const size_t in_row_bytes = static_cast<size_t>(CB) * p.in_side * 16;  // all planes of one input row
+  const size_t in_row_bytes = static_cast<size_t>(CB) * p.in_side * 16;
   const size_t in_img_bytes = in_row_bytes * p.in_side;
 
   if (warp == 0) {
@@ -257,220 +346,307 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const TcParams p) 
         int sz = min(16384, Cfg::kWBytes - off);
         tma_bulk_g2s(smem_u32(s_w + off), w_gmem + off, sz, bar_w);
       }
-      uint32_t cnt = 0;
+      uint32_t st = 0, ph = 1;  // waiting parity 1 on a fresh "empty" barrier passes immediately
+      const uint32_t stage0 = smem_u32(s_stage);
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const Item it = decode_item<POOL_S, SEG>(p, item);
+        const Item it = decode_item<POOL, SEG>(p, item);
         const int nin = it.nconv + 2;
-        for (int r = 0; r < nin; ++r, ++cnt) {
-          const int st = cnt % NST;
-          mbar_wait(bar_empty(st), ((cnt / NST) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar_full(st), kStageTx);
-          const uint32_t dst = smem_u32(s_stage + st * Cfg::kStageBytes);
+        const uint8_t* src0 = p.in + it.n0 * in_img_bytes + it.c0 * in_row_bytes + static_cast<size_t>(it.x_in0) * 16;
+        const uint8_t* src1 = p.in + min(it.n0 + 1, p.N - 1) * in_img_bytes + it.c0 * in_row_bytes;
+        for (int r = 0; r < nin; ++r) {
+          mbar_wait(bar_empty0 + 8u * st, ph);
+          const uint32_t full = bar_full0 + 8u * st;
+          mbar_arrive_expect_tx(full, kStageTx);
+          const uint32_t dst = stage0 + st * Cfg::kStageBytes;
 #pragma unroll
-          for (int sg = 0; sg < SEG; ++sg) {
-            const int n = min(it.n0 + sg, p.N - 1);
-            const uint8_t* src = p.in + n * in_img_bytes + (it.c0 + r) * in_row_bytes +
-                                 static_cast<size_t>(it.x_in0) * 16;
-            for (int c = 0; c < CB; ++c)
-              tma_bulk_g2s(dst + c * kPlaneBytes + sg * SEGW * 16, src + static_cast<size_t>(c) * p.in_side * 16,
-                           SEG == 1 ? kLoadPx * 16 : SEGW * 16, bar_full(st));
+          for (int c = 0; c < CB; ++c) {
+            if (SEG == 1) {
+              tma_bulk_g2s(dst + c * kPlaneBytes, src0 + static_cast<size_t>(c) * p.in_side * 16, kLoadPx * 16, full);
+            } else {
+              tma_bulk_g2s(dst + c * kPlaneBytes, src0 + static_cast<size_t>(c) * p.in_side * 16, SEGW * 16, full);
+              tma_bulk_g2s(dst + c * kPlaneBytes + SEGW * 16, src1 + static_cast<size_t>(c) * p.in_side * 16, SEGW * 16,
+                           full);
+            }
+          }
+          src0 += in_row_bytes;
+          src1 += in_row_bytes;
+          if (++st == NST) {
+            st = 0;
+            ph ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
+    // Everything here is warp-uniform; only the tcgen05 instructions themselves are issued by lane 0.
     mbar_wait(bar_w, 0);
-    const uint32_t w_base = smem_u32(s_w);
-    const uint32_t idesc0 = make_idesc(0, p.bf16);
-    uint32_t cnt = 0, G = 0;
+    const uint32_t a_lo0 = (smem_u32(s_stage) >> 4) | (Cfg::kALbo16 << 16);
+    const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | (Cfg::kBLbo16 << 16);
+    const uint32_t idesc0 = make_idesc(0, BF16 ? 1 : 0);
+    uint32_t st = 0, ph = 0, G = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item<POOL_S, SEG>(p, item);
+      const Item it = decode_item<POOL, SEG>(p, item);
       const int nin = it.nconv + 2;
-      for (int r = 0; r < nin; ++r, ++cnt) {
-        const int st = cnt % NST;
-        if (r < it.nconv) {  // the accumulator of conv row r is (re)started by this input row
+      for (int r = 0; r < nin; ++r) {
+        if (r < it.nconv) {  // accumulator of conv row r must have been drained and re-initialised with the bias
           const uint32_t gy = G + r;
-          mbar_wait(bar_acce(gy % R), ((gy / R) & 1) ^ 1);
+          mbar_wait(bar_acce0 + 8u * (gy & (R - 1)), (gy >> LOGR) & 1);
         }
-        mbar_wait(bar_full(st), (cnt / NST) & 1);
+        mbar_wait(bar_full0 + 8u * st, ph);
         tc_fence_after();
+        const int jlo = max(0, 2 - r);  // j = 2 - dy ; conv row y = r - 2 + j
+        const int jhi = min(2, it.nconv + 1 - r);
+        const uint32_t sb = (G + r - 2 + jlo) & (R - 1);
+        const int nj = jhi - jlo + 1;
+        const int len1 = min(nj, R - static_cast<int>(sb));  // slots before the ring wraps
+        const uint32_t a_lo = a_lo0 + st * (Cfg::kStageBytes >> 4);
         if (lane == 0) {
-          const uint32_t a_base = smem_u32(s_stage + st * Cfg::kStageBytes);
-          const int jlo = max(0, 2 - r);                       // j = 2 - dy ; conv row y = r - 2 + j
-          const int jhi = min(2, it.nconv + 1 - r);
-#pragma unroll 1
-          for (int ks = 0; ks < Cfg::kKSteps; ++ks) {
-            uint64_t a_desc;
-            int plane;
-            if constexpr (Cfg::kPaired) {
-              a_desc = make_desc(a_base + (2 * ks) * 16, 16, 128);
-              plane = 2 * ks;
-            } else {
-              constexpr int kHalfCb = CB / 2;
-              const int dx = ks / kHalfCb, kk = ks % kHalfCb;
-              a_desc = make_desc(a_base + (2 * kk) * kPlaneBytes + dx * 16, kPlaneBytes, 128);
-              plane = dx * CB + 2 * kk;
-            }
-            const bool first = (ks == 0);
-            int j = jlo;
-            while (j <= jhi) {
-              const int s0 = (G + r - 2 + j) % R;
-              const bool fresh = (j == 2) && first;
-              int len = 1;
-              if (!fresh)
-                while (j + len <= jhi && s0 + len < R && !((j + len) == 2 && first)) ++len;
-              const uint64_t b_desc =
-                  make_desc(w_base + (plane * 3 * COUT + j * COUT) * 16, 3 * COUT * 16, 128);
-              tc_mma_f16(tmem_base + s0 * COUT, a_desc, b_desc, idesc0 | (static_cast<uint32_t>((len * COUT) >> 3) << 17),
-                         fresh ? 0u : 1u);
-              j += len;
-            }
+          {
+            const uint32_t d = tmem_base + sb * COUT;
+            const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
+            const uint32_t b_lo = b_lo0 + jlo * COUT;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+              tc_mma_acc(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
           }
-          tc_commit(bar_empty(st));
-          if (r >= 2) tc_commit(bar_accf((G + r - 2) % R));
+          if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
+            const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
+            const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+              tc_mma_acc(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+          }
+          tc_commit(bar_empty0 + 8u * st);
+          if (r >= 2) tc_commit(bar_accf0 + 8u * ((G + r - 2) & (R - 1)));
         }
         __syncwarp();
+        if (++st == NST) {
+          st = 0;
+          ph ^= 1;
+        }
       }
       G += it.nconv;
     }
-  } else {
+  } else if (warp < 2 + 4 * NG) {
     // ============================= epilogue =============================
-    const int quad = warp & 3;                    // TMEM lane quadrant this warp may read
+    const int ew = warp - 2;
+    const int grp = ew >> 2;                      // channel group: channels [grp*CG, grp*CG + CG)
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
     const int pix = quad * 32 + lane;             // pixel (UMMA row) owned by this thread
     const int seg = pix / SEGW, xs = pix % SEGW;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int bf16 = p.bf16;
+    const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * CG;
     const size_t out_row_bytes = static_cast<size_t>(p.cb_out_total) * p.out_side * 16;
     const size_t out_img_bytes = out_row_bytes * p.out_side;
-    uint32_t G = 0;
-    uint32_t xrow = 0;  // output rows emitted (ghost buffer parity)
+    const uint32_t bar_id = 1 + grp;
 
+    float bias_r[CG];
+#pragma unroll
+    for (int c = 0; c < CG; ++c) bias_r[c] = s_bias[grp * CG + c];
+    // every accumulator slot starts out holding the bias: the MMAs then always accumulate
+    for (int s = 0; s < R; ++s) {
+#pragma unroll
+      for (int g8 = 0; g8 < CG / 8; ++g8) tc_st8(t_base + s * COUT + g8 * 8, bias_r + g8 * 8);
+    }
+    tc_wait_st();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0)
+      for (int s = 0; s < R; ++s) mbar_arrive(bar_acce0 + 8u * s);
+
+    uint32_t G = 0, iter = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item<POOL_S, SEG>(p, item);
+      const Item it = decode_item<POOL, SEG>(p, item);
       const int n_img = it.n0 + seg;
       bool col_ok;
       int col;
-      if (POOL_S == 0) {
+      if (POOL == 0) {
         col = it.x_in0 + xs;
         col_ok = col < p.conv_side;
-      } else if (POOL_S == 1) {
-        col = it.x_out0 + xs;
-        col_ok = (xs + 3 < SEGW) && (xs < p.strip_step_out || p.n_strips == 1) && col < p.out_side;
-      } else {
+      } else if (POOL == 42) {
         col = it.x_out0 + (xs >> 1);
-        col_ok = !(xs & 1) && (xs + 3 < SEGW) && ((xs >> 1) < p.strip_step_out || p.n_strips == 1) && col < p.out_side;
+        col_ok = !(xs & 1) && (xs + 3 < SEGW) && col < p.out_side;
+      } else {
+        col = it.x_out0 + xs;
+        col_ok = (xs + (POOL == 41 ? 3 : 2) < SEGW) && col < p.out_side;
       }
       col_ok = col_ok && n_img < p.N;
-      uint8_t* out_px = p.out + n_img * out_img_bytes + (static_cast<size_t>(part) * (COUT / 8) * p.out_side + col) * 16;
+      uint8_t* out_px = p.out + n_img * out_img_bytes +
+                        ((static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.out_side + col) * 16;
 
-      // vertical pooling window (registers).  POOL_S==1: r1 = previous row, q1/q2 = pair sums ending 1/2 rows back.
-      float r1[POOL_S == 1 ? COUT : 1], q1[POOL_S != 0 ? COUT : 1], q2[POOL_S == 1 ? COUT : 1];
+      // vertical pooling window, fp32 registers
+      float r1[(POOL == 41 || POOL == 31) ? CG : 1], q1[POOL != 0 ? CG : 1], q2[POOL == 41 ? CG : 1];
 #pragma unroll
-      for (int c = 0; c < (POOL_S != 0 ? COUT : 1); ++c) q1[c] = 0.f;
+      for (int c = 0; c < (POOL != 0 ? CG : 1); ++c) q1[c] = 0.f;
 #pragma unroll
-      for (int c = 0; c < (POOL_S == 1 ? COUT : 1); ++c) r1[c] = q2[c] = 0.f;
+      for (int c = 0; c < ((POOL == 41 || POOL == 31) ? CG : 1); ++c) r1[c] = 0.f;
+#pragma unroll
+      for (int c = 0; c < (POOL == 41 ? CG : 1); ++c) q2[c] = 0.f;
 
-      constexpr int kRowStep = POOL_S == 2 ? 2 : 1;
-      for (int y = 0; y < it.nconv; y += kRowStep) {
+      for (int y = 0; y < it.nconv; y += 2, ++iter) {
+        const bool has2 = y + 1 < it.nconv;
         const uint32_t gy = G + y;
-        const int slot0 = gy % R;
-        mbar_wait(bar_accf(slot0), (gy / R) & 1);
-        int slot1 = 0;
-        if (POOL_S == 2) {
-          slot1 = (gy + 1) % R;
-          mbar_wait(bar_accf(slot1), ((gy + 1) / R) & 1);
-        }
+        const uint32_t slot0 = gy & (R - 1), slot1 = (gy + 1) & (R - 1);
+        mbar_wait(bar_accf0 + 8u * slot0, (gy >> LOGR) & 1);
+        if (has2) mbar_wait(bar_accf0 + 8u * slot1, ((gy + 1) >> LOGR) & 1);
         tc_fence_after();
-        bool emit;
-        int yo;
-        if (POOL_S == 0) {
-          emit = true;
-          yo = it.c0 + y;
-        } else if (POOL_S == 1) {
-          emit = y >= 3;
-          yo = it.po0 + y - 3;
+        float a[CG], b[CG];
+#pragma unroll
+        for (int g8 = 0; g8 < CG / 8; ++g8) tc_ld8(t_base + slot0 * COUT + g8 * 8, a + g8 * 8);
+        if (has2) {
+#pragma unroll
+          for (int g8 = 0; g8 < CG / 8; ++g8) tc_ld8(t_base + slot1 * COUT + g8 * 8, b + g8 * 8);
         } else {
-          emit = y >= 2;
-          yo = it.po0 + (y - 2) / 2;
-        }
-        float4* xw = s_xchg + ((xrow & 1) * 4 + quad) * COUT;
-        const float4* xr = s_xchg + ((xrow & 1) * 4 + ((quad + 1) & 3)) * COUT;
-
-        // pass 1: TMEM -> registers, bias + ReLU6, vertical window; keeps the vertical sums in v[]
-        float v[COUT];
 #pragma unroll
-        for (int g = 0; g < COUT / 16; ++g) {
-          uint32_t a[16], b[16];
-          tc_ld16(t_lane + slot0 * COUT + g * 16, a);
-          if (POOL_S == 2) tc_ld16(t_lane + slot1 * COUT + g * 16, b);
-          tc_wait_ld();
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const int c = g * 16 + e;
-            const float bia = s_bias[c];
-            float x = relu6f(__uint_as_float(a[e]) + bia);
-            if (POOL_S == 0) {
-              v[c] = x;
-            } else if (POOL_S == 1) {
-              const float q0 = x + r1[c];
-              v[c] = q0 + q2[c];
-              q2[c] = q1[c];
-              q1[c] = q0;
-              r1[c] = x;
-            } else {
-              const float q0 = x + relu6f(__uint_as_float(b[e]) + bia);
-              v[c] = q0 + q1[c];
-              q1[c] = q0;
-            }
-          }
+          for (int c = 0; c < CG; ++c) b[c] = 0.f;
         }
-        // accumulator slots are free again
+        tc_wait_ld();
+        // hand the slots back, pre-loaded with the bias
+#pragma unroll
+        for (int g8 = 0; g8 < CG / 8; ++g8) tc_st8(t_base + slot0 * COUT + g8 * 8, bias_r + g8 * 8);
+        if (has2) {
+#pragma unroll
+          for (int g8 = 0; g8 < CG / 8; ++g8) tc_st8(t_base + slot1 * COUT + g8 * 8, bias_r + g8 * 8);
+        }
+        tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(bar_acce(slot0));
-          if (POOL_S == 2) mbar_arrive(bar_acce(slot1));
+          mbar_arrive(bar_acce0 + 8u * slot0);
+          if (has2) mbar_arrive(bar_acce0 + 8u * slot1);
         }
-        if (!emit) continue;
-        if (POOL_S != 0) {
-          // ghost columns: the first three pixels of the next quadrant
-          if (lane < 3) {
-#pragma unroll
-            for (int c = 0; c < COUT; ++c) reinterpret_cast<float*>(&xw[c])[lane] = v[c];
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+
+        // ---- ReLU6 + vertical window -> packed 16-bit pairs vp[k][i] for output row k of this iteration
+        uint32_t vp[2][NP];
+        bool emit0, emit1;
+        int yo0, yo1;
+        if (POOL == 0) {
+          emit0 = true;
+          emit1 = has2;
+          yo0 = it.c0 + y;
+          yo1 = yo0 + 1;
+        } else if (POOL == 42) {
+          emit0 = y >= 2;
+          emit1 = false;
+          yo0 = it.po0 + (y - 2) / 2;
+          yo1 = 0;
+        } else if (POOL == 41) {
+          emit0 = y >= 3;
+          emit1 = has2 && y >= 2;
+          yo0 = it.po0 + y - 3;
+          yo1 = yo0 + 1;
+        } else {
+          emit0 = y >= 2;
+          emit1 = has2 && y >= 1;
+          yo0 = it.po0 + y - 2;
+          yo1 = yo0 + 1;
         }
-        uint8_t* orow = out_px + yo * out_row_bytes;
 #pragma unroll
-        for (int cb = 0; cb < COUT / 8; ++cb) {
-          float h[8];
+        for (int i = 0; i < NP; ++i) {
+          float o0[2], o1[2];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = cb * 8 + e;
-            if (POOL_S == 0) {
-              h[e] = v[c];
-            } else {
-              const float4 gh = xr[c];
-              float a1 = __shfl_down_sync(0xffffffffu, v[c], 1);
-              if (lane == 31) a1 = gh.x;
-              const float t = v[c] + a1;
-              float b2 = __shfl_down_sync(0xffffffffu, t, 2);
-              if (lane == 30) b2 = gh.x + gh.y;
-              if (lane == 31) b2 = gh.y + gh.z;
-              h[e] = (t + b2) * 0.0625f;
+          for (int e = 0; e < 2; ++e) {
+            const int c = 2 * i + e;
+            // weights and bias carry a factor 1/6: relu6(z)/6 == saturate(z/6), one FADD.SAT
+            const float x0 = __saturatef(a[c]), x1 = __saturatef(b[c]);
+            if (POOL == 0) {
+              o0[e] = x0;
+              o1[e] = x1;
+            } else if (POOL == 42) {
+              const float q0 = x0 + x1;
+              o0[e] = q0 + q1[c];
+              o1[e] = 0.f;
+              q1[c] = q0;
+            } else if (POOL == 41) {
+              const float qa = x0 + r1[c], qb = x1 + x0;
+              o0[e] = qa + q2[c];
+              o1[e] = qb + q1[c];
+              q2[c] = qa;
+              q1[c] = qb;
+              r1[c] = x1;
+            } else {  // 31: q1 = r(y-1) + r(y-2), r1 = r(y-1)
+              o0[e] = x0 + q1[c];
+              o1[e] = x1 + (x0 + r1[c]);
+              q1[c] = x1 + x0;
+              r1[c] = x1;
             }
           }
-          if (col_ok) {
-            uint4 o;
-            o.x = pack2(h[0], h[1], bf16);
-            o.y = pack2(h[2], h[3], bf16);
-            o.z = pack2(h[4], h[5], bf16);
-            o.w = pack2(h[6], h[7], bf16);
-            *reinterpret_cast<uint4*>(orow + static_cast<size_t>(cb) * p.out_side * 16) = o;
+          vp[0][i] = HH::pack(o0[0], o0[1]);
+          vp[1][i] = HH::pack(o1[0], o1[1]);
+        }
+        if (!emit0 && !emit1) continue;
+
+        // ---- horizontal window with warp shuffles; the columns owned by the next quadrant come through smem
+        uint32_t hp[2][NP];
+        if (POOL == 0) {
+#pragma unroll
+          for (int i = 0; i < NP; ++i) {
+            hp[0][i] = vp[0][i];
+            hp[1][i] = vp[1][i];
+          }
+        } else {
+          // ghost record per (output row k, pair i): {v0, t0 | v1, t1} written by lanes 0 and 1 of the NEXT quadrant
+          uint2* xw = reinterpret_cast<uint2*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + quad) * 2) * NP));
+          const uint32_t* xr =
+              reinterpret_cast<const uint32_t*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + ((quad + 1) & 3)) * 2) * NP));
+          uint32_t tt[2][NP];
+          constexpr int NK = (POOL == 42) ? 1 : 2;
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+              const uint32_t v = vp[k][i];
+              if (POOL == 42) {
+                const uint32_t u = HH::add(v, __shfl_xor_sync(0xffffffffu, v, 1));
+                tt[k][i] = u;
+                if (lane == 0) xw[(k * NP + i) * 2].x = u;
+              } else {
+                const uint32_t t = HH::add(v, __shfl_down_sync(0xffffffffu, v, 1));
+                tt[k][i] = t;
+                if (lane < 2) xw[(k * NP + i) * 2 + lane] = make_uint2(v, t);
+              }
+            }
+          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+#pragma unroll
+          for (int k = 0; k < NK; ++k)
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+              const uint32_t* g = xr + (k * NP + i) * 4;  // g[0]=v0 g[1]=t0 g[2]=v1 g[3]=t1 of the next quadrant
+              if (POOL == 42) {
+                uint32_t nb = __shfl_down_sync(0xffffffffu, tt[k][i], 2);
+                if (lane == 30) nb = g[0];
+                hp[k][i] = HH::add(tt[k][i], nb);
+              } else if (POOL == 41) {
+                uint32_t t = tt[k][i];
+                if (lane == 31) t = HH::add(vp[k][i], g[0]);
+                uint32_t nb = __shfl_down_sync(0xffffffffu, t, 2);
+                if (lane >= 30) nb = g[2 * (lane - 30) + 1];
+                hp[k][i] = HH::add(t, nb);
+              } else {
+                uint32_t t = tt[k][i];
+                if (lane == 31) t = HH::add(vp[k][i], g[0]);
+                uint32_t nb = __shfl_down_sync(0xffffffffu, vp[k][i], 2);
+                if (lane >= 30) nb = g[2 * (lane - 30)];
+                hp[k][i] = HH::add(t, nb);
+              }
+            }
+        }
+        if (col_ok) {
+          if (emit0) {
+            uint8_t* orow = out_px + yo0 * out_row_bytes;
+#pragma unroll
+            for (int cb = 0; cb < CG / 8; ++cb)
+              *reinterpret_cast<uint4*>(orow + static_cast<size_t>(cb) * p.out_side * 16) =
+                  make_uint4(hp[0][4 * cb], hp[0][4 * cb + 1], hp[0][4 * cb + 2], hp[0][4 * cb + 3]);
+          }
+          if (emit1) {
+            uint8_t* orow = out_px + yo1 * out_row_bytes;
+#pragma unroll
+            for (int cb = 0; cb < CG / 8; ++cb)
+              *reinterpret_cast<uint4*>(orow + static_cast<size_t>(cb) * p.out_side * 16) =
+                  make_uint4(hp[1][4 * cb], hp[1][4 * cb + 1], hp[1][4 * cb + 2], hp[1][4 * cb + 3]);
           }
         }
-        ++xrow;
       }
       G += it.nconv;
     }
@@ -540,7 +716,7 @@ __global__ void __launch_bounds__(256) conv0_pool_kernel(const TIn* __restrict__
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) s += s_conv[py + dy][px + dx][o];
-      h[o] = s / 9.f;
+      h[o] = s * (1.f / 6.f);  // stored scale 9/6 of the pooled mean, as the tensor-core layers (engine.cu)
     }
     uint4 o4;
     o4.x = pack2(h[0], h[1], bf16);
@@ -600,7 +776,7 @@ __global__ void join_h_kernel(const uint4* __restrict__ p, const uint4* __restri
 }
 
 __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int N, int S, int C,
-                                      int bf16) {
+                                      int bf16, float scale) {
   const size_t total = static_cast<size_t>(N) * S * S * C;
   const int CBn = C / 8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -619,13 +795,38 @@ __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __
       __half h = *reinterpret_cast<__half*>(&raw);
       f = __half2float(h);
     }
-    out[i] = f;
+    out[i] = f * scale;
   }
 }
 
-template <int CB, int COUT, int POOL_S, int SEG>
-cudaError_t launch_tc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
-  using Cfg = TcCfg<CB, COUT>;
+// uint8 NHWC (3 channels) -> conv0 tensor-core input: out[n][y][x] = 16 bytes {p(x).c0,c1,c2,0, p(x+1).c0,c1,c2,0}
+// with p = pixel/256 (exact in fp16 and bf16).  One thread per output chunk.
+__global__ void prep_u8_kernel(const uint8_t* __restrict__ in, uint4* __restrict__ out, int N, int S, int bf16) {
+  const size_t total = static_cast<size_t>(N) * S * S;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % S);
+    const uint8_t* px = in + i * 3;
+    float a0 = px[0], a1 = px[1], a2 = px[2];
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    if (x + 1 < S) {
+      b0 = px[3];
+      b1 = px[4];
+      b2 = px[5];
+    }
+    const float sc = 1.f / 256.f;
+    uint4 o;
+    o.x = pack2(a0 * sc, a1 * sc, bf16);
+    o.y = pack2(a2 * sc, 0.f, bf16);
+    o.z = pack2(b0 * sc, b1 * sc, bf16);
+    o.w = pack2(b2 * sc, 0.f, bf16);
+    out[i] = o;
+  }
+}
+
+template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT>
+cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
+  using Cfg = TcCfg<CB, COUT, AMODE>;
   TcParams p{};
   p.in = static_cast<const uint8_t*>(in);
   p.out = static_cast<uint8_t*>(out);
@@ -635,37 +836,43 @@ cudaError_t launch_tc(const TcConvLayer& L, const void* in, void* out, int N, Ha
   p.in_side = L.in_side;
   p.conv_side = L.in_side - 2;
   p.out_side = L.out_side;
-  p.cb_out_total = L.cout / 8;
+  p.cb_out_total = (CREAL * L.cout_parts) / 8;
   p.w_bytes = static_cast<int>(L.w_bytes);
-  p.bf16 = kind == HalfKind::kBF16;
   constexpr int SEGW = kTileM / SEG;
   if (SEG == 2 && L.in_side > SEGW) return cudaErrorInvalidValue;
-  if (POOL_S == 0) {
+  if (POOL == 0) {
     p.strip_step_in = p.strip_step_out = kTileM;
     p.n_strips = SEG == 2 ? 1 : (p.conv_side + kTileM - 1) / kTileM;
-  } else if (POOL_S == 1) {
-    p.strip_step_in = p.strip_step_out = kTileM - 3;
-    p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
-  } else {
+  } else if (POOL == 42) {
     p.strip_step_out = (kTileM - 4) / 2 + 1;  // 63 pooled columns per strip
     p.strip_step_in = 2 * p.strip_step_out;
     p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
+  } else {
+    p.strip_step_in = p.strip_step_out = kTileM - (POOL == 41 ? 3 : 2);
+    p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
   }
   const int groups = (N + SEG - 1) / SEG;
-  const int base_items = groups * p.n_strips;
-  // split rows so that the persistent grid sees >= ~4 waves, but keep >= 16 pooled rows per item
+  const int base_items = groups * p.n_strips * L.cout_parts;
+  // split rows so that the persistent grid sees >= ~4 waves, but keep >= 8 pooled rows per item
   int nrb = (4 * 148 + base_items - 1) / base_items;
-  nrb = std::max(1, std::min(nrb, std::max(1, p.out_side / 16)));
+  nrb = std::max(1, std::min(nrb, std::max(1, p.out_side / 8)));
   p.rows_per_item = (p.out_side + nrb - 1) / nrb;
   p.n_rowblocks = (p.out_side + p.rows_per_item - 1) / p.rows_per_item;
-  p.n_items = base_items * p.n_rowblocks;
-  auto kern = conv_tc_kernel<CB, COUT, POOL_S, SEG>;
+  p.n_items = groups * p.n_strips * p.n_rowblocks;
+  auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL>;
   // per device (replicas of several GPUs share the process), and cheap enough to repeat
   cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return ea;
-  dim3 grid(std::min(p.n_items, 148), L.cout_parts);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(p);
+  const int gx = std::max(1, std::min(p.n_items, 148 / L.cout_parts));
+  dim3 grid(gx, L.cout_parts);
+  kern<<<grid, kThreadsTc, Cfg::kSmemBytes, st>>>(p);
   return cudaGetLastError();
+}
+
+template <int CB, int COUT, int POOL, int SEG, int AMODE, int CREAL = COUT>
+cudaError_t launch_tc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
+  return kind == HalfKind::kBF16 ? launch_tc_impl<CB, COUT, POOL, SEG, AMODE, true, CREAL>(L, in, out, N, st)
+                                 : launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL>(L, in, out, N, st);
 }
 
 uint16_t to_half_bits(double v, HalfKind kind) {
@@ -688,7 +895,7 @@ size_t ChunkedBytes(int n, int side, int channels) {
   return static_cast<size_t>(n) * side * side * channels * 2 + kSlackBytes;
 }
 
-size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKind kind, void* out_host) {
+size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKind kind, double scale, void* out_host) {
   const int cb = cin / 8;
   const bool paired = cb == 1;
   const int planes = paired ? 4 : 3 * cb;
@@ -706,7 +913,7 @@ size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKin
         const int dy = 2 - j;
         for (int oc = 0; oc < cp; ++oc)
           for (int e = 0; e < 8; ++e) {
-            double v = w[(((dy * 3 + dx) * cin) + c0 + e) * cout + part * cp + oc];
+            double v = scale * w[(((dy * 3 + dx) * cin) + c0 + e) * cout + part * cp + oc];
             o[part * (part_bytes / 2) + ((static_cast<size_t>(pl) * 3 * cp + j * cp + oc) * 8) + e] =
                 to_half_bits(v, kind);
           }
@@ -715,17 +922,64 @@ size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKin
   return part_bytes;
 }
 
+size_t PackTcConv0Weights(const double* w, HalfKind kind, double scale, void* out_host) {
+  // planes: 0/1 = hi halves for pixel pairs (x,x+1)/(x+2,x+3), 2/3 = lo halves; rows [dy=2|dy=1|dy=0] x 16 (8 real)
+  constexpr int kCout = 16, kReal = 8;
+  const size_t bytes = static_cast<size_t>(4) * 3 * kCout * 16;
+  if (!out_host) return bytes;
+  uint16_t* o = static_cast<uint16_t*>(out_host);
+  std::memset(o, 0, bytes);
+  auto to_f = [&](uint16_t bits) {
+    if (kind == HalfKind::kBF16) {
+      uint32_t u = static_cast<uint32_t>(bits) << 16;
+      float f;
+      std::memcpy(&f, &u, 4);
+      return static_cast<double>(f);
+    }
+    __half h;
+    std::memcpy(&h, &bits, 2);
+    return static_cast<double>(__half2float(h));
+  };
+  for (int half = 0; half < 2; ++half)
+    for (int j = 0; j < 3; ++j)
+      for (int oc = 0; oc < kReal; ++oc)
+        for (int e = 0; e < 8; ++e) {
+          const int ch = e % 4;
+          if (ch == 3) continue;
+          for (int hi_lo = 0; hi_lo < 2; ++hi_lo) {
+            const int dx = half * 2 + e / 4;
+            if (dx > 2) continue;
+            const int dy = 2 - j;
+            const double v = scale * w[((dy * 3 + dx) * 3 + ch) * kReal + oc];
+            const uint16_t hi = to_half_bits(v, kind);
+            const uint16_t bits = hi_lo == 0 ? hi : to_half_bits(v - to_f(hi), kind);
+            const int pl = hi_lo * 2 + half;
+            o[(static_cast<size_t>(pl) * 3 * kCout + j * kCout + oc) * 8 + e] = bits;
+          }
+        }
+  return bytes;
+}
+
+cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st) {
+  size_t total = static_cast<size_t>(N) * S * S;
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  prep_u8_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint4*>(out), N, S, kind == HalfKind::kBF16);
+  return cudaGetLastError();
+}
+
 cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
   const int cb = L.cin / 8, cp = L.cout / L.cout_parts;
   const bool seg2 = L.in_side <= 64;
-  if (cb == 1 && cp == 32 && L.pool_s == 1) return launch_tc<1, 32, 1, 1>(L, in, out, N, kind, st);
-  if (cb == 4 && cp == 32 && L.pool_s == 1) return launch_tc<4, 32, 1, 1>(L, in, out, N, kind, st);
-  if (cb == 4 && cp == 64 && L.pool_s == 2) return launch_tc<4, 64, 2, 1>(L, in, out, N, kind, st);
-  if (cb == 8 && cp == 64 && L.pool_s == 2) return launch_tc<8, 64, 2, 1>(L, in, out, N, kind, st);
-  if (cb == 8 && cp == 64 && L.pool_k == 0)
-    return seg2 ? launch_tc<8, 64, 0, 2>(L, in, out, N, kind, st) : launch_tc<8, 64, 0, 1>(L, in, out, N, kind, st);
-  if (cb == 16 && cp == 16 && L.pool_s == 2)
-    return seg2 ? launch_tc<16, 16, 2, 2>(L, in, out, N, kind, st) : launch_tc<16, 16, 2, 1>(L, in, out, N, kind, st);
+  const int pool = L.pool_k * 10 + L.pool_s;
+  if (L.amode == 2) return launch_tc<1, 16, 31, 1, 2, 8>(L, in, out, N, kind, st);
+  if (cb == 1 && cp == 32 && pool == 41) return launch_tc<1, 32, 41, 1, 1>(L, in, out, N, kind, st);
+  if (cb == 4 && cp == 32 && pool == 41) return launch_tc<4, 32, 41, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 4 && cp == 64 && pool == 42) return launch_tc<4, 64, 42, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 8 && cp == 64 && pool == 42) return launch_tc<8, 64, 42, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 8 && cp == 64 && pool == 0)
+    return seg2 ? launch_tc<8, 64, 0, 2, 0>(L, in, out, N, kind, st) : launch_tc<8, 64, 0, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 16 && cp == 16 && pool == 42)
+    return seg2 ? launch_tc<16, 16, 42, 2, 0>(L, in, out, N, kind, st) : launch_tc<16, 16, 42, 1, 0>(L, in, out, N, kind, st);
   return cudaErrorInvalidValue;
 }
 
@@ -750,11 +1004,12 @@ cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, con
   return cudaGetLastError();
 }
 
-cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, cudaStream_t st) {
+cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale,
+                         cudaStream_t st) {
   size_t total = static_cast<size_t>(N) * S * S * Ch;
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
   chunked_to_f32_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(in), out, N, S, Ch,
-                                                kind == HalfKind::kBF16);
+                                                kind == HalfKind::kBF16, scale);
   return cudaGetLastError();
 }
 
