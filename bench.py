@@ -253,7 +253,8 @@ def main():
         roofline = None
         if prof:
             total_ms = sum(p["ms"] for p in prof)
-            top = max(prof, key=lambda p: p["ms"])
+            convs = [p for p in prof if p["name"].startswith("conv") and p["name"].endswith("_tc")] or prof
+            top = max(convs, key=lambda p: p["ms"])  # dominant tensor-core kernel
             layer = int("".join(ch for ch in top["name"] if ch.isdigit()) or 0) if top["name"].startswith("conv") else None
             if layer is not None:
                 flops_per_launch = conv_flops(layer) * B * args.steps / top["launches"]

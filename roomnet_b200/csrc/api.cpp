@@ -137,7 +137,7 @@ int rn_create(const rn_config* cfg, rn_handle** out) {
   if (mb <= 0) {
     // resident micro-batch: bounded by activation memory, which grows with im_side^2
     double scale = (224.0 * 224.0) / (static_cast<double>(cfg->im_side) * cfg->im_side);
-    mb = std::max(1, std::min(256, static_cast<int>(64 * scale)));
+    mb = std::max(1, std::min(256, static_cast<int>(256 * scale)));
   }
   h->cfg.max_batch = mb;
   for (int i = 0; i < cfg->n_devices; ++i) {

@@ -285,7 +285,8 @@ cudaError_t Replica::ForwardF32(const void* d_in, InputKind kind, int n, cudaStr
   return TailF32(1, n, st);
 }
 
-cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, cudaStream_t st) {
+cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
+                               float* d_logits, cudaStream_t st) {
   const ConvShape& c0 = shape_.conv[0];
   const int k = static_cast<int>(kind);
   Mark(nullptr, st);
@@ -314,10 +315,28 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, cudaStre
   }
   const int last = first_f32_layer_ - 1;
   const ConvShape& cl = shape_.conv[last];
+  if (last == 7 && TailFusedSupported(cl.out_side, cl.cout) && shape_.conv[8].pool_k == 4 && shape_.conv[8].pool_s == 2 &&
+      shape_.conv[9].pool_k == 4 && shape_.conv[9].pool_s == 2 && shape_.conv[9].join_src == 7) {
+    RN_CUDA(TailFused(act_h_[7], n, cl.out_side, static_cast<float>(1.0 / act_scale_[7]), cw_[8], cb_[8], cw_[9], cb_[9],
+                      ja_[9], jb_[9], jc_[9], dense_, shape_.flat_len, half_kind_, d_top1, d_probs, d_logits, pooled_[8],
+                      joined_[9], st));
+    Mark("tail_fused", st);
+    return cudaSuccess;
+  }
   RN_CUDA(ChunkedToF32(act_h_[last], pooled_[last], n, cl.out_side, cl.cout, half_kind_,
                        static_cast<float>(1.0 / act_scale_[last]), st));
   Mark("chunked_to_f32", st);
-  return TailF32(first_f32_layer_, n, st);
+  cudaError_t e = TailF32(first_f32_layer_, n, st);
+  if (e != cudaSuccess) return e;
+  return DenseTail(n, d_top1, d_probs, d_logits, st);
+}
+
+cudaError_t Replica::DenseTail(int n, long long* d_top1, float* d_probs, float* d_logits, cudaStream_t st) {
+  const ConvShape& cl = shape_.conv[kNumConvs - 1];
+  const float* flat = cl.join_src >= 0 ? joined_[kNumConvs - 1] : pooled_[kNumConvs - 1];
+  RN_CUDA(DenseTailF32(flat, n, shape_.flat_len, dense_, d_top1, d_probs, d_logits, d_pre_, st));
+  Mark("dense_tail", st);
+  return cudaSuccess;
 }
 
 cudaError_t Replica::ForwardDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
@@ -326,12 +345,14 @@ cudaError_t Replica::ForwardDevice(const void* d_in, InputKind kind, int n, long
     err_ = "micro-batch size out of range";
     return cudaErrorInvalidValue;
   }
-  cudaError_t e = precision_ == RN_PREC_FP32 ? ForwardF32(d_in, kind, n, st) : ForwardTc(d_in, kind, n, st);
+  cudaError_t e;
+  if (precision_ == RN_PREC_FP32) {
+    e = ForwardF32(d_in, kind, n, st);
+    if (e == cudaSuccess) e = DenseTail(n, d_top1, d_probs, d_logits, st);
+  } else {
+    e = ForwardTc(d_in, kind, n, d_top1, d_probs, d_logits, st);
+  }
   if (e != cudaSuccess) return e;
-  const ConvShape& cl = shape_.conv[kNumConvs - 1];
-  const float* flat = cl.join_src >= 0 ? joined_[kNumConvs - 1] : pooled_[kNumConvs - 1];
-  RN_CUDA(DenseTailF32(flat, n, shape_.flat_len, dense_, d_top1, d_probs, d_logits, d_pre_, st));
-  Mark("dense_tail", st);
   last_n_ = n;
   return cudaSuccess;
 }
@@ -430,7 +451,7 @@ cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dim
   RN_CUDA(cudaStreamSynchronize(compute_));
   const float* src = nullptr;
   float* tmp = nullptr;
-  if (layer >= first_f32_layer_ || (layer == first_f32_layer_ - 1 && cs.join_src < 0)) {
+  if (layer >= first_f32_layer_) {
     src = cs.join_src >= 0 ? joined_[layer] : pooled_[layer];
   } else {
     RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), elems * sizeof(float)));

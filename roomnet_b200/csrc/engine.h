@@ -53,7 +53,9 @@ class Replica {
 
  private:
   cudaError_t ForwardF32(const void* d_in, InputKind kind, int n, cudaStream_t st);
-  cudaError_t ForwardTc(const void* d_in, InputKind kind, int n, cudaStream_t st);
+  cudaError_t ForwardTc(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs, float* d_logits,
+                        cudaStream_t st);
+  cudaError_t DenseTail(int n, long long* d_top1, float* d_probs, float* d_logits, cudaStream_t st);
   cudaError_t TailF32(int first_layer, int n, cudaStream_t st);
   cudaError_t Alloc(void** p, size_t bytes);
   cudaError_t UploadF32(const std::vector<double>& v, float** dptr);

@@ -66,6 +66,12 @@ cudaError_t Conv0PoolH(const TIn* in, const float* w, const float* b, void* out,
 // out = A*p + B*resize(src) + C on chunked 16-bit tensors.
 cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, const float* B, const float* C, int N,
                   int S, int SS, int Ch, HalfKind kind, cudaStream_t st);
+// Fused tail (conv8 .. softmax) for small maps; dbg8/dbg9 (optional) receive the NHWC outputs of conv blocks 8/9.
+bool TailFusedSupported(int s7, int channels);
+cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float* w8, const float* b8, const float* w9,
+                      const float* b9, const float* ja, const float* jb, const float* jc, const DenseParams& dp,
+                      int flat_len, HalfKind kind, long long* top1, float* probs, float* logits, float* dbg8,
+                      float* dbg9, cudaStream_t st);
 // chunked 16-bit -> NHWC fp32
 cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale, cudaStream_t st);
 

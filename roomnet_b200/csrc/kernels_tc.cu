@@ -38,7 +38,7 @@ constexpr int kTileM = 128;           // pixels per row tile (UMMA M)
 constexpr int kPlanePx = 136;         // pixels per channel-chunk plane in a smem stage
 constexpr int kPlaneBytes = kPlanePx * 16;
 constexpr int kLoadPx = 132;          // pixels fetched per plane row (128 + taps, 16B multiple)
-constexpr int kSlackBytes = 4096;     // over-read slack behind every chunked tensor
+constexpr int kSlackBytes = 128 * 1024;  // over-read slack behind every chunked tensor (row tails + one padding row)
 constexpr int kThreads = 192;         // (v1 layout, kept for the small helper kernels)
 constexpr int kSmemBudget = 227 * 1024;
 
@@ -207,6 +207,9 @@ __device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
     it.c0 = it.po0;
     it.nconv = it.npo + (POOL == 41 ? 3 : 2);
   }
+  // the epilogue consumes two conv rows per iteration: an odd count gets one extra (never stored) row, whose
+  // input rows may lie past the image (next image or the slack behind the tensor) - harmless garbage
+  it.nconv = (it.nconv + 1) & ~1;
   return it;
 }
 
@@ -271,6 +274,67 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const float* v) {
                "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
 }
+template <int N>
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
+  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM load width");
+  uint32_t r[N];
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  } else if constexpr (N == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N>
+__device__ __forceinline__ void tc_st(uint32_t taddr, const float* v) {
+  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM store width");
+#define RN_U(i) "r"(__float_as_uint(v[i]))
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), RN_U(0), RN_U(1), RN_U(2),
+                 RN_U(3)
+                 : "memory");
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), RN_U(0),
+                 RN_U(1), RN_U(2), RN_U(3), RN_U(4), RN_U(5), RN_U(6), RN_U(7)
+                 : "memory");
+  } else if constexpr (N == 16) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+            taddr),
+        RN_U(0), RN_U(1), RN_U(2), RN_U(3), RN_U(4), RN_U(5), RN_U(6), RN_U(7), RN_U(8), RN_U(9), RN_U(10), RN_U(11),
+        RN_U(12), RN_U(13), RN_U(14), RN_U(15)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        RN_U(0), RN_U(1), RN_U(2), RN_U(3), RN_U(4), RN_U(5), RN_U(6), RN_U(7), RN_U(8), RN_U(9), RN_U(10), RN_U(11),
+        RN_U(12), RN_U(13), RN_U(14), RN_U(15), RN_U(16), RN_U(17), RN_U(18), RN_U(19), RN_U(20), RN_U(21), RN_U(22),
+        RN_U(23), RN_U(24), RN_U(25), RN_U(26), RN_U(27), RN_U(28), RN_U(29), RN_U(30), RN_U(31)
+        : "memory");
+  }
+#undef RN_U
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr int kThreadsTc = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (2 channel groups x 4 quadrants)
@@ -288,7 +352,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
   constexpr int LOGR = Cfg::kLogSlots;
   constexpr int NST = Cfg::kStages;
   constexpr int SEGW = kTileM / SEG;
-  constexpr int NG = CREAL >= 16 ? 2 : 1;  // epilogue channel groups (4 warps each)
+  constexpr int NG = 2;                    // epilogue channel groups (4 warps each)
   constexpr int CG = CREAL / NG;           // channels per epilogue group
   constexpr int NP = CG / 2;     // half2 pairs per thread
   constexpr uint32_t kStageTx = CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16);
@@ -438,16 +502,16 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * CG;
     const size_t out_row_bytes = static_cast<size_t>(p.cb_out_total) * p.out_side * 16;
     const size_t out_img_bytes = out_row_bytes * p.out_side;
+    const size_t out_plane_bytes = static_cast<size_t>(p.out_side) * 16;
     const uint32_t bar_id = 1 + grp;
+    constexpr int KW = POOL == 31 ? 3 : 4;        // pooling window
+    constexpr int LAG = POOL == 42 ? 2 : KW - 1;  // conv rows between an output row's first row and its last
 
     float bias_r[CG];
 #pragma unroll
     for (int c = 0; c < CG; ++c) bias_r[c] = s_bias[grp * CG + c];
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
-    for (int s = 0; s < R; ++s) {
-#pragma unroll
-      for (int g8 = 0; g8 < CG / 8; ++g8) tc_st8(t_base + s * COUT + g8 * 8, bias_r + g8 * 8);
-    }
+    for (int s = 0; s < R; ++s) tc_st<CG>(t_base + s * COUT, bias_r);
     tc_wait_st();
     tc_fence_before();
     __syncwarp();
@@ -468,11 +532,15 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
         col_ok = !(xs & 1) && (xs + 3 < SEGW) && col < p.out_side;
       } else {
         col = it.x_out0 + xs;
-        col_ok = (xs + (POOL == 41 ? 3 : 2) < SEGW) && col < p.out_side;
+        col_ok = (xs + KW - 1 < SEGW) && col < p.out_side;
       }
       col_ok = col_ok && n_img < p.N;
-      uint8_t* out_px = p.out + n_img * out_img_bytes +
-                        ((static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.out_side + col) * 16;
+      // output row pointer of the row produced by output slot 0 of the current iteration (may start "before" po0)
+      uint8_t* optr = p.out + n_img * out_img_bytes +
+                      ((static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.out_side + col) * 16 +
+                      static_cast<ptrdiff_t>(it.po0) * out_row_bytes + (CG == 4 ? grp * 8 : 0);
+      if (POOL == 41 || POOL == 31) optr -= static_cast<ptrdiff_t>(LAG) * out_row_bytes;
+      if (POOL == 42) optr -= out_row_bytes;
 
       // vertical pooling window, fp32 registers
       float r1[(POOL == 41 || POOL == 31) ? CG : 1], q1[POOL != 0 ? CG : 1], q2[POOL == 41 ? CG : 1];
@@ -483,64 +551,32 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
 #pragma unroll
       for (int c = 0; c < (POOL == 41 ? CG : 1); ++c) q2[c] = 0.f;
 
+      // it.nconv is even: two conv rows per iteration (row slots gy, gy+1)
+#pragma unroll 2
       for (int y = 0; y < it.nconv; y += 2, ++iter) {
-        const bool has2 = y + 1 < it.nconv;
         const uint32_t gy = G + y;
         const uint32_t slot0 = gy & (R - 1), slot1 = (gy + 1) & (R - 1);
         mbar_wait(bar_accf0 + 8u * slot0, (gy >> LOGR) & 1);
-        if (has2) mbar_wait(bar_accf0 + 8u * slot1, ((gy + 1) >> LOGR) & 1);
+        mbar_wait(bar_accf0 + 8u * slot1, ((gy + 1) >> LOGR) & 1);
         tc_fence_after();
         float a[CG], b[CG];
-#pragma unroll
-        for (int g8 = 0; g8 < CG / 8; ++g8) tc_ld8(t_base + slot0 * COUT + g8 * 8, a + g8 * 8);
-        if (has2) {
-#pragma unroll
-          for (int g8 = 0; g8 < CG / 8; ++g8) tc_ld8(t_base + slot1 * COUT + g8 * 8, b + g8 * 8);
-        } else {
-#pragma unroll
-          for (int c = 0; c < CG; ++c) b[c] = 0.f;
-        }
+        tc_ld<CG>(t_base + slot0 * COUT, a);
+        tc_ld<CG>(t_base + slot1 * COUT, b);
         tc_wait_ld();
         // hand the slots back, pre-loaded with the bias
-#pragma unroll
-        for (int g8 = 0; g8 < CG / 8; ++g8) tc_st8(t_base + slot0 * COUT + g8 * 8, bias_r + g8 * 8);
-        if (has2) {
-#pragma unroll
-          for (int g8 = 0; g8 < CG / 8; ++g8) tc_st8(t_base + slot1 * COUT + g8 * 8, bias_r + g8 * 8);
-        }
+        tc_st<CG>(t_base + slot0 * COUT, bias_r);
+        tc_st<CG>(t_base + slot1 * COUT, bias_r);
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar_acce0 + 8u * slot0);
-          if (has2) mbar_arrive(bar_acce0 + 8u * slot1);
+          mbar_arrive(bar_acce0 + 8u * slot1);
         }
 
-        // ---- ReLU6 + vertical window -> packed 16-bit pairs vp[k][i] for output row k of this iteration
+        // ---- saturate (= ReLU6/6) + vertical window -> packed 16-bit pairs vp[k][i] for output slot k
+        // output slot 0 is pooled row (y - LAG) [41/31] or (y - 2)/2 [42] or conv row y [0]; slot 1 the next one
         uint32_t vp[2][NP];
-        bool emit0, emit1;
-        int yo0, yo1;
-        if (POOL == 0) {
-          emit0 = true;
-          emit1 = has2;
-          yo0 = it.c0 + y;
-          yo1 = yo0 + 1;
-        } else if (POOL == 42) {
-          emit0 = y >= 2;
-          emit1 = false;
-          yo0 = it.po0 + (y - 2) / 2;
-          yo1 = 0;
-        } else if (POOL == 41) {
-          emit0 = y >= 3;
-          emit1 = has2 && y >= 2;
-          yo0 = it.po0 + y - 3;
-          yo1 = yo0 + 1;
-        } else {
-          emit0 = y >= 2;
-          emit1 = has2 && y >= 1;
-          yo0 = it.po0 + y - 2;
-          yo1 = yo0 + 1;
-        }
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           float o0[2], o1[2];
@@ -572,12 +608,12 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
             }
           }
           vp[0][i] = HH::pack(o0[0], o0[1]);
-          vp[1][i] = HH::pack(o1[0], o1[1]);
+          if (POOL != 42) vp[1][i] = HH::pack(o1[0], o1[1]);
         }
-        if (!emit0 && !emit1) continue;
 
         // ---- horizontal window with warp shuffles; the columns owned by the next quadrant come through smem
         uint32_t hp[2][NP];
+        constexpr int NK = (POOL == 42) ? 1 : 2;
         if (POOL == 0) {
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
@@ -585,25 +621,28 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
             hp[1][i] = vp[1][i];
           }
         } else {
-          // ghost record per (output row k, pair i): {v0, t0 | v1, t1} written by lanes 0 and 1 of the NEXT quadrant
-          uint2* xw = reinterpret_cast<uint2*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + quad) * 2) * NP));
+          // ghost record per (output slot k, pair i): 16 bytes, see the readers below
+          uint32_t* xw = reinterpret_cast<uint32_t*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + quad) * 2) * NP));
           const uint32_t* xr =
               reinterpret_cast<const uint32_t*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + ((quad + 1) & 3)) * 2) * NP));
           uint32_t tt[2][NP];
-          constexpr int NK = (POOL == 42) ? 1 : 2;
 #pragma unroll
           for (int k = 0; k < NK; ++k)
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
               const uint32_t v = vp[k][i];
+              uint32_t* rec = xw + (k * NP + i) * 4;
               if (POOL == 42) {
                 const uint32_t u = HH::add(v, __shfl_xor_sync(0xffffffffu, v, 1));
                 tt[k][i] = u;
-                if (lane == 0) xw[(k * NP + i) * 2].x = u;
+                if (lane == 0) rec[0] = u;
               } else {
                 const uint32_t t = HH::add(v, __shfl_down_sync(0xffffffffu, v, 1));
                 tt[k][i] = t;
-                if (lane < 2) xw[(k * NP + i) * 2 + lane] = make_uint2(v, t);
+                // record = {x, A | v0, B}: lane 30 of the previous quadrant reads (x, A), lane 31 reads (v0, B)
+                //   41: A = t0, B = t1        31: A = v0, B = v1
+                if (lane < 2) rec[2 * lane + 1] = (POOL == 41) ? t : v;
+                if (lane == 0) rec[2] = v;
               }
             }
           asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -611,41 +650,43 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
           for (int k = 0; k < NK; ++k)
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
-              const uint32_t* g = xr + (k * NP + i) * 4;  // g[0]=v0 g[1]=t0 g[2]=v1 g[3]=t1 of the next quadrant
+              const uint32_t* rec = xr + (k * NP + i) * 4;
               if (POOL == 42) {
                 uint32_t nb = __shfl_down_sync(0xffffffffu, tt[k][i], 2);
-                if (lane == 30) nb = g[0];
+                if (lane == 30) nb = rec[0];
                 hp[k][i] = HH::add(tt[k][i], nb);
-              } else if (POOL == 41) {
-                uint32_t t = tt[k][i];
-                if (lane == 31) t = HH::add(vp[k][i], g[0]);
-                uint32_t nb = __shfl_down_sync(0xffffffffu, t, 2);
-                if (lane >= 30) nb = g[2 * (lane - 30) + 1];
-                hp[k][i] = HH::add(t, nb);
               } else {
+                uint2 gg = make_uint2(0u, 0u);
+                if (lane >= 30) gg = *reinterpret_cast<const uint2*>(rec + 2 * (lane - 30));
                 uint32_t t = tt[k][i];
-                if (lane == 31) t = HH::add(vp[k][i], g[0]);
-                uint32_t nb = __shfl_down_sync(0xffffffffu, vp[k][i], 2);
-                if (lane >= 30) nb = g[2 * (lane - 30)];
+                if (lane == 31) t = HH::add(vp[k][i], gg.x);
+                uint32_t nb = __shfl_down_sync(0xffffffffu, POOL == 41 ? t : vp[k][i], 2);
+                if (lane >= 30) nb = gg.y;
                 hp[k][i] = HH::add(t, nb);
               }
             }
         }
-        if (col_ok) {
-          if (emit0) {
-            uint8_t* orow = out_px + yo0 * out_row_bytes;
+        // ---- stores: output slot k of this iteration is row (first + k) relative to the item
+        {
+          int first;  // index (relative to po0 / c0) of output slot 0
+          if (POOL == 0) first = y;
+          else if (POOL == 42) first = (y >> 1) - 1;
+          else first = y - LAG;
+          if (col_ok) {
 #pragma unroll
-            for (int cb = 0; cb < CG / 8; ++cb)
-              *reinterpret_cast<uint4*>(orow + static_cast<size_t>(cb) * p.out_side * 16) =
-                  make_uint4(hp[0][4 * cb], hp[0][4 * cb + 1], hp[0][4 * cb + 2], hp[0][4 * cb + 3]);
-          }
-          if (emit1) {
-            uint8_t* orow = out_px + yo1 * out_row_bytes;
+            for (int k = 0; k < NK; ++k) {
+              const int row = first + k;
+              if (row >= 0 && row < it.npo) {
+                uint8_t* orow = optr + static_cast<size_t>(k) * out_row_bytes;
 #pragma unroll
-            for (int cb = 0; cb < CG / 8; ++cb)
-              *reinterpret_cast<uint4*>(orow + static_cast<size_t>(cb) * p.out_side * 16) =
-                  make_uint4(hp[1][4 * cb], hp[1][4 * cb + 1], hp[1][4 * cb + 2], hp[1][4 * cb + 3]);
+                for (int cb = 0; cb < CG / 8; ++cb)
+                  *reinterpret_cast<uint4*>(orow + cb * out_plane_bytes) =
+                      make_uint4(hp[k][4 * cb], hp[k][4 * cb + 1], hp[k][4 * cb + 2], hp[k][4 * cb + 3]);
+                if (CG == 4) *reinterpret_cast<uint2*>(orow) = make_uint2(hp[k][0], hp[k][1]);
+              }
+            }
           }
+          optr += (POOL == 42 ? 1 : 2) * out_row_bytes;
         }
       }
       G += it.nconv;
@@ -727,52 +768,223 @@ __global__ void __launch_bounds__(256) conv0_pool_kernel(const TIn* __restrict__
   }
 }
 
-// out = A*p + B*resize_bilinear_legacy(src) + C on chunked tensors; one thread = one 8-channel chunk.
-__global__ void join_h_kernel(const uint4* __restrict__ p, const uint4* __restrict__ src, uint4* __restrict__ out,
-                              const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ Cc,
-                              int N, int S, int SS, int CBn, int bf16) {
-  const size_t total = static_cast<size_t>(N) * S * CBn * S;
+// out = A*p + B*resize_bilinear_legacy(src) + C on chunked tensors (reference network.py:199-203 folded).
+// One block = one output row (n, y); one warp = one 8-channel plane of that row, lanes walk x, so every
+// global access is a contiguous 512-byte segment and the per-channel coefficients live in registers.
+__global__ void __launch_bounds__(256) join_h_kernel(const uint4* __restrict__ p, const uint4* __restrict__ src,
+                                                     uint4* __restrict__ out, const float* __restrict__ A,
+                                                     const float* __restrict__ B, const float* __restrict__ Cc, int S,
+                                                     int SS, int CBn, int bf16) {
+  const int n = blockIdx.x / S, y = blockIdx.x % S;
+  const int lane = threadIdx.x & 31;
   const float scale = static_cast<float>(SS) / static_cast<float>(S);
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    int x = static_cast<int>(i % S);
-    size_t r = i / S;
-    int cb = static_cast<int>(r % CBn);
-    r /= CBn;
-    int y = static_cast<int>(r % S);
-    int n = static_cast<int>(r / S);
-    float fy = static_cast<float>(y) * scale, fx = static_cast<float>(x) * scale;
-    int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
-    int y1 = min(y0 + 1, SS - 1), x1 = min(x0 + 1, SS - 1);
-    float ty = fy - static_cast<float>(y0), tx = fx - static_cast<float>(x0);
-    const uint4* s_n = src + static_cast<size_t>(n) * SS * CBn * SS;
-    auto at = [&](int yy, int xx) { return s_n[(static_cast<size_t>(yy) * CBn + cb) * SS + xx]; };
-    const uint4 tl = at(y0, x0), tr = at(y0, x1), bl = at(y1, x0), br = at(y1, x1);
-    const uint4 pv = p[i];
-    const uint32_t* ptl = &tl.x;
-    const uint32_t* ptr = &tr.x;
-    const uint32_t* pbl = &bl.x;
-    const uint32_t* pbr = &br.x;
-    const uint32_t* ppv = &pv.x;
-    uint4 o;
-    uint32_t* po = &o.x;
+  const float fy = static_cast<float>(y) * scale;
+  const int y0 = static_cast<int>(floorf(fy));
+  const int y1 = min(y0 + 1, SS - 1);
+  const float ty = fy - static_cast<float>(y0);
+  for (int cb = threadIdx.x >> 5; cb < CBn; cb += blockDim.x >> 5) {
+    float a[8], b[8], c[8];
 #pragma unroll
-    for (int e2 = 0; e2 < 4; ++e2) {
-      float res[2];
-#pragma unroll
-      for (int hl = 0; hl < 2; ++hl) {
-        auto get = [&](const uint32_t* q) { return hl ? unpack_hi(q[e2], bf16) : unpack_lo(q[e2], bf16); };
-        const int c = cb * 8 + e2 * 2 + hl;
-        float a = get(ptl), b = get(ptr), cc = get(pbl), d = get(pbr);
-        float top = a + (b - a) * tx;
-        float bot = cc + (d - cc) * tx;
-        float rs = top + (bot - top) * ty;
-        res[hl] = fmaf(A[c], get(ppv), fmaf(B[c], rs, Cc[c]));
-      }
-      po[e2] = pack2(res[0], res[1], bf16);
+    for (int e = 0; e < 8; ++e) {
+      a[e] = A[cb * 8 + e];
+      b[e] = B[cb * 8 + e];
+      c[e] = Cc[cb * 8 + e];
     }
-    out[i] = o;
+    const uint4* row_p = p + ((static_cast<size_t>(n) * S + y) * CBn + cb) * S;
+    uint4* row_o = out + ((static_cast<size_t>(n) * S + y) * CBn + cb) * S;
+    const uint4* s0 = src + ((static_cast<size_t>(n) * SS + y0) * CBn + cb) * SS;
+    const uint4* s1 = src + ((static_cast<size_t>(n) * SS + y1) * CBn + cb) * SS;
+    for (int x = lane; x < S; x += 32) {
+      const float fx = static_cast<float>(x) * scale;
+      const int x0 = static_cast<int>(floorf(fx));
+      const int x1 = min(x0 + 1, SS - 1);
+      const float tx = fx - static_cast<float>(x0);
+      const uint4 tl = s0[x0], tr = s0[x1], bl = s1[x0], br = s1[x1];
+      const uint4 pv = row_p[x];
+      const uint32_t* ptl = &tl.x;
+      const uint32_t* ptr = &tr.x;
+      const uint32_t* pbl = &bl.x;
+      const uint32_t* pbr = &br.x;
+      const uint32_t* ppv = &pv.x;
+      uint4 o;
+      uint32_t* po = &o.x;
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        float res[2];
+#pragma unroll
+        for (int hl = 0; hl < 2; ++hl) {
+          auto get = [&](const uint32_t* q) { return hl ? unpack_hi(q[e2], bf16) : unpack_lo(q[e2], bf16); };
+          const int e = e2 * 2 + hl;
+          const float va = get(ptl), vb = get(ptr), vc = get(pbl), vd = get(pbr);
+          const float top = va + (vb - va) * tx;
+          const float bot = vc + (vd - vc) * tx;
+          const float rs = top + (bot - top) * ty;
+          res[hl] = fmaf(a[e], get(ppv), fmaf(b[e], rs, c[e]));
+        }
+        po[e2] = pack2(res[0], res[1], bf16);
+      }
+      row_o[x] = o;
+    }
   }
+}
+
+// ---------------------------------------------------------------------------
+// Fused tail for small maps (im_side 224: 21x21x16 in): conv 16->16 + ReLU6 + pool4/2, conv 16->16 + ReLU6 +
+// pool4/2, residual join with the bilinearly resized block input, 4 dense layers, softmax, argmax
+// (reference network.py:230-237, :44-45 in folded form).  One CTA per image, everything in shared memory, fp32.
+// ---------------------------------------------------------------------------
+struct TailParams {
+  const float* w8;  // [9][16][16] HWIO folded
+  const float* b8;
+  const float* w9;
+  const float* b9;
+  const float* ja;  // join coefficients (per channel) for TRUE-scale pooled tensors
+  const float* jb;
+  const float* jc;
+  DenseParams dense;
+  int S7;           // side of the input map
+  float in_scale;   // stored -> true
+  int flat_len;
+};
+
+constexpr int kTailC = 16;
+constexpr int kTailMaxSide = 24;
+
+__device__ __forceinline__ void tail_conv_pool(const float* __restrict__ in, int S, const float* __restrict__ w,
+                                               const float* __restrict__ bias, float* __restrict__ conv,
+                                               float* __restrict__ pooled, float* s_w) {
+  // in: [16][S][S] channel-major; conv: [16][S-2][S-2]; pooled: [16][P][P], P = (S-2-4)/2+1
+  const int CS = S - 2, P = (CS - 4) / 2 + 1;
+  for (int i = threadIdx.x; i < 9 * 16 * 16; i += blockDim.x) s_w[i] = w[i];
+  __syncthreads();
+  for (int item = threadIdx.x; item < CS * CS * 4; item += blockDim.x) {
+    const int g = item / (CS * CS), px = item % (CS * CS);
+    const int y = px / CS, x = px % CS;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < 16; ++c) {
+      const float* ip = in + (c * S + y) * S + x;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const float a = ip[(tap / 3) * S + (tap % 3)];
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[(tap * 16 + c) * 16 + g * 4]);
+        acc[0] = fmaf(a, wv.x, acc[0]);
+        acc[1] = fmaf(a, wv.y, acc[1]);
+        acc[2] = fmaf(a, wv.z, acc[2]);
+        acc[3] = fmaf(a, wv.w, acc[3]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) conv[((g * 4 + o) * CS + y) * CS + x] = relu6f(acc[o] + bias[g * 4 + o]);
+  }
+  __syncthreads();
+  for (int item = threadIdx.x; item < 16 * P * P; item += blockDim.x) {
+    const int c = item / (P * P), py = (item / P) % P, qx = item % P;
+    float sum = 0.f;
+    for (int dy = 0; dy < 4; ++dy)
+      for (int dx = 0; dx < 4; ++dx) sum += conv[(c * CS + 2 * py + dy) * CS + 2 * qx + dx];
+    pooled[item] = sum * 0.0625f;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) tail_fused_kernel(const uint16_t* __restrict__ p7, TailParams tp, int bf16,
+                                                         long long* __restrict__ top1, float* __restrict__ probs,
+                                                         float* __restrict__ logits, float* __restrict__ dbg8,
+                                                         float* __restrict__ dbg9) {
+  extern __shared__ __align__(16) float sm[];
+  const int S = tp.S7, S8 = (S - 2 - 4) / 2 + 1, S9 = (S8 - 2 - 4) / 2 + 1;
+  float* s_in = sm;                                  // [16][S][S]
+  float* s_conv = s_in + 16 * S * S;                 // [16][S-2][S-2]
+  float* s_p8 = s_conv + 16 * (S - 2) * (S - 2);     // [16][S8][S8]
+  float* s_p9 = s_p8 + 16 * S8 * S8;                 // [16][S9][S9]
+  float* s_flat = s_p9 + 16 * S9 * S9;               // [S9*S9*16] NHWC order
+  float* s_w = s_flat + 16 * S9 * S9;                // [9*16*16]
+  const int n = blockIdx.x;
+  // chunked 16-bit [y][cb(2)][x][8] -> channel-major fp32, true scale
+  const uint16_t* src = p7 + static_cast<size_t>(n) * S * S * kTailC;
+  for (int i = threadIdx.x; i < S * S * kTailC; i += blockDim.x) {
+    const int e = i % 8, x = (i / 8) % S, cb = (i / (8 * S)) % 2, y = i / (16 * S);
+    const uint16_t raw = src[i];
+    float f;
+    if (bf16) {
+      f = __uint_as_float(static_cast<uint32_t>(raw) << 16);
+    } else {
+      __half h = *reinterpret_cast<const __half*>(&raw);
+      f = __half2float(h);
+    }
+    s_in[((cb * 8 + e) * S + y) * S + x] = f * tp.in_scale;
+  }
+  __syncthreads();
+  tail_conv_pool(s_in, S, tp.w8, tp.b8, s_conv, s_p8, s_w);
+  tail_conv_pool(s_p8, S8, tp.w9, tp.b9, s_conv, s_p9, s_w);
+  if (dbg8)
+    for (int i = threadIdx.x; i < 16 * S8 * S8; i += blockDim.x) {  // NHWC for the parity tests
+      const int c = i % 16, px = i / 16;
+      dbg8[static_cast<size_t>(n) * 16 * S8 * S8 + i] = s_p8[c * S8 * S8 + px];
+    }
+  // residual join: A*p9 + B*resize(p7 -> S9 x S9) + C, written in NHWC flatten order (h, w, c)
+  const float scale = static_cast<float>(S) / static_cast<float>(S9);
+  for (int i = threadIdx.x; i < 16 * S9 * S9; i += blockDim.x) {
+    const int c = i % 16, x = (i / 16) % S9, y = i / (16 * S9);
+    const float fy = static_cast<float>(y) * scale, fx = static_cast<float>(x) * scale;
+    const int y0 = static_cast<int>(floorf(fy)), x0 = static_cast<int>(floorf(fx));
+    const int y1 = min(y0 + 1, S - 1), x1 = min(x0 + 1, S - 1);
+    const float ty = fy - static_cast<float>(y0), tx = fx - static_cast<float>(x0);
+    const float* ch = s_in + c * S * S;
+    const float tl = ch[y0 * S + x0], tr = ch[y0 * S + x1], bl = ch[y1 * S + x0], br = ch[y1 * S + x1];
+    const float top = tl + (tr - tl) * tx, bot = bl + (br - bl) * tx;
+    const float rs = top + (bot - top) * ty;
+    const float v = fmaf(tp.ja[c], s_p9[(c * S9 + y) * S9 + x], fmaf(tp.jb[c], rs, tp.jc[c]));
+    s_flat[i] = v;
+    if (dbg9) dbg9[static_cast<size_t>(n) * 16 * S9 * S9 + i] = v;
+  }
+  __syncthreads();
+  // dense head on warp 0 (same arithmetic as dense_tail_kernel in kernels_f32.cu)
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  const DenseParams& dp = tp.dense;
+  float v = 0.f;
+  {
+    const int on = dp.out[0];
+    if (lane < on) {
+      float acc = 0.f;
+      for (int r = 0; r < tp.flat_len; ++r) acc = fmaf(s_flat[r], dp.w[0][static_cast<size_t>(r) * on + lane], acc);
+      v = relu6f(acc + dp.b[0][lane]);
+    }
+  }
+#pragma unroll
+  for (int l = 1; l < 4; ++l) {
+    const int in = dp.out[l - 1], on = dp.out[l];
+    float acc = 0.f;
+    for (int r = 0; r < in; ++r) {
+      float xr = __shfl_sync(0xffffffffu, v, r);
+      if (lane < on) acc = fmaf(xr, dp.w[l][r * on + lane], acc);
+    }
+    if (lane < on) acc += dp.b[l][lane];
+    v = relu6f(acc);
+  }
+  const int C = dp.out[3];
+  float m = lane < C ? v : -INFINITY;
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float e = lane < C ? expf(v - m) : 0.f;
+  float ssum = e;
+  for (int o = 16; o; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+  const float prob = e / ssum;
+  float best = lane < C ? prob : -1.f;
+  int bi = lane;
+  for (int o = 16; o; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane < C) {
+    if (probs) probs[static_cast<size_t>(n) * C + lane] = prob;
+    if (logits) logits[static_cast<size_t>(n) * C + lane] = v;
+  }
+  if (lane == 0 && top1) top1[n] = bi;
 }
 
 __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int N, int S, int C,
@@ -997,10 +1209,28 @@ template cudaError_t Conv0PoolH<uint8_t>(const uint8_t*, const float*, const flo
 
 cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, const float* B, const float* C, int N,
                   int S, int SS, int Ch, HalfKind kind, cudaStream_t st) {
-  size_t total = static_cast<size_t>(N) * S * S * (Ch / 8);
-  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  join_h_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint4*>(p), static_cast<const uint4*>(src),
-                                        static_cast<uint4*>(out), A, B, C, N, S, SS, Ch / 8, kind == HalfKind::kBF16);
+  const int cbn = Ch / 8;
+  join_h_kernel<<<N * S, std::min(256, 32 * cbn), 0, st>>>(static_cast<const uint4*>(p), static_cast<const uint4*>(src),
+                                                           static_cast<uint4*>(out), A, B, C, S, SS, cbn,
+                                                           kind == HalfKind::kBF16);
+  return cudaGetLastError();
+}
+
+bool TailFusedSupported(int s7, int channels) { return channels == kTailC && s7 <= kTailMaxSide && s7 >= 11; }
+
+cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float* w8, const float* b8, const float* w9,
+                      const float* b9, const float* ja, const float* jb, const float* jc, const DenseParams& dp,
+                      int flat_len, HalfKind kind, long long* top1, float* probs, float* logits, float* dbg8,
+                      float* dbg9, cudaStream_t st) {
+  TailParams tp{w8, b8, w9, b9, ja, jb, jc, dp, S7, in_scale, flat_len};
+  const int S8 = (S7 - 2 - 4) / 2 + 1, S9 = (S8 - 2 - 4) / 2 + 1;
+  const size_t floats = 16 * S7 * S7 + 16 * (S7 - 2) * (S7 - 2) + 16 * S8 * S8 + 2 * 16 * S9 * S9 + 9 * 16 * 16;
+  const size_t bytes = floats * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(bytes));
+  if (e != cudaSuccess) return e;
+  tail_fused_kernel<<<N, 256, bytes, st>>>(static_cast<const uint16_t*>(p7), tp, kind == HalfKind::kBF16, top1, probs,
+                                           logits, dbg8, dbg9);
   return cudaGetLastError();
 }
 
