@@ -29,8 +29,7 @@ Replica::Replica(int device, const NetShape& shape, int precision, int max_batch
 
 Replica::~Replica() {
   cudaSetDevice(device_);
-  if (compute_) cudaStreamSynchronize(compute_);
-  if (copy_) cudaStreamSynchronize(copy_);
+  cudaDeviceSynchronize();
   for (void* p : allocs_) cudaFree(p);
   for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
@@ -39,6 +38,11 @@ Replica::~Replica() {
     if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
     if (ev_done_[i]) cudaEventDestroy(ev_done_[i]);
   }
+  for (auto& set : sets_) {
+    if (set.stream) cudaStreamDestroy(set.stream);
+    if (set.ev_done) cudaEventDestroy(set.ev_done);
+  }
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (compute_) cudaStreamDestroy(compute_);
   if (copy_) cudaStreamDestroy(copy_);
 }
@@ -72,31 +76,39 @@ cudaError_t Replica::Init() {
   }
   const size_t B = static_cast<size_t>(max_batch_);
   const int C = shape_.num_classes;
+  RN_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  for (int si = 0; si < 2; ++si) {
+  cur_ = &sets_[si];
+  RN_CUDA(cudaStreamCreateWithFlags(&cur_->stream, cudaStreamNonBlocking));
+  RN_CUDA(cudaEventCreateWithFlags(&cur_->ev_done, cudaEventDisableTiming));
   size_t scratch = 0;
   for (int i = first_f32_layer_ == 0 ? 0 : first_f32_layer_; i < kNumConvs; ++i) {
     const ConvShape& cs = shape_.conv[i];
     scratch = std::max(scratch, static_cast<size_t>(cs.conv_side) * cs.conv_side * cs.cout);
   }
-  RN_CUDA(Alloc(reinterpret_cast<void**>(&conv_scratch_), scratch * B * sizeof(float)));
+  RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->conv_scratch), scratch * B * sizeof(float)));
   for (int i = 0; i < kNumConvs; ++i) {
     const ConvShape& cs = shape_.conv[i];
     size_t elems = static_cast<size_t>(cs.out_side) * cs.out_side * cs.cout * B;
     bool f32_needed = i >= first_f32_layer_ || i == first_f32_layer_ - 1;
     if (f32_needed) {
-      RN_CUDA(Alloc(reinterpret_cast<void**>(&pooled_[i]), elems * sizeof(float)));
-      if (cs.join_src >= 0) RN_CUDA(Alloc(reinterpret_cast<void**>(&joined_[i]), elems * sizeof(float)));
+      RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->pooled[i]), elems * sizeof(float)));
+      if (cs.join_src >= 0) RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->joined[i]), elems * sizeof(float)));
     }
     if (i < first_f32_layer_) {
       size_t bytes = ChunkedBytes(max_batch_, cs.out_side, cs.cout);
-      RN_CUDA(Alloc(&act_h_[i], bytes));
-      RN_CUDA(cudaMemset(act_h_[i], 0, bytes));
+      RN_CUDA(Alloc(&cur_->act_h[i], bytes));
+      RN_CUDA(cudaMemset(cur_->act_h[i], 0, bytes));
       if (cs.join_src >= 0) {
-        RN_CUDA(Alloc(&join_h_[i], bytes));
-        RN_CUDA(cudaMemset(join_h_[i], 0, bytes));
+        RN_CUDA(Alloc(&cur_->join_h[i], bytes));
+        RN_CUDA(cudaMemset(cur_->join_h[i], 0, bytes));
       }
     }
   }
-  if (first_f32_layer_ > 0) RN_CUDA(Alloc(&in_h_, ChunkedBytes(max_batch_, shape_.im_side, 8)));
+  if (first_f32_layer_ > 0) RN_CUDA(Alloc(&cur_->in_h, ChunkedBytes(max_batch_, shape_.im_side, 8)));
+  RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->d_pre), B * C * sizeof(float)));
+  }
+  cur_ = &sets_[0];
   const size_t in_bytes = InputBytesPerImage(shape_, InputKind::kF32Rgb) * B;
   for (int i = 0; i < 2; ++i) {
     RN_CUDA(Alloc(&d_in_[i], in_bytes));
@@ -106,7 +118,6 @@ cudaError_t Replica::Init() {
     RN_CUDA(Alloc(reinterpret_cast<void**>(&d_logits_[i]), B * C * sizeof(float)));
     RN_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_out_[i]), B * (sizeof(long long) + 2 * C * sizeof(float))));
   }
-  RN_CUDA(Alloc(reinterpret_cast<void**>(&d_pre_), B * C * sizeof(float)));
   return cudaSuccess;
 }
 
@@ -120,7 +131,7 @@ cudaError_t Replica::UploadF32(const std::vector<double>& v, float** dptr) {
 
 cudaError_t Replica::Upload(const FoldedNet& f) {
   RN_CUDA(cudaSetDevice(device_));
-  RN_CUDA(cudaStreamSynchronize(compute_));
+  RN_CUDA(cudaDeviceSynchronize());
   const FoldedConv* c0[3] = {&f.conv0_u8bgr, &f.conv0_u8rgb, &f.conv0_f32rgb};
   for (int k = 0; k < 3; ++k) {
     RN_CUDA(UploadF32(c0[k]->w, &w0_[k]));
@@ -252,16 +263,16 @@ cudaError_t Replica::ProfileResults(std::vector<KernelTime>* out) {
 cudaError_t Replica::TailF32(int first_layer, int n, cudaStream_t st) {
   for (int i = first_layer; i < kNumConvs; ++i) {
     const ConvShape& cs = shape_.conv[i];
-    const float* in = shape_.conv[i - 1].join_src >= 0 ? joined_[i - 1] : pooled_[i - 1];
-    float* conv_out = cs.pool_k ? conv_scratch_ : pooled_[i];
+    const float* in = shape_.conv[i - 1].join_src >= 0 ? cur_->joined[i - 1] : cur_->pooled[i - 1];
+    float* conv_out = cs.pool_k ? cur_->conv_scratch : cur_->pooled[i];
     RN_CUDA(Conv3x3Relu6F32<float>(in, cw_[i], cb_[i], conv_out, n, cs.in_side, cs.in_side, cs.cin, cs.cout, st));
     Mark(("conv" + std::to_string(i) + "_f32").c_str(), st);
     if (cs.pool_k) {
-      RN_CUDA(AvgPoolF32(conv_scratch_, pooled_[i], n, cs.conv_side, cs.conv_side, cs.cout, cs.pool_k, cs.pool_s, st));
+      RN_CUDA(AvgPoolF32(cur_->conv_scratch, cur_->pooled[i], n, cs.conv_side, cs.conv_side, cs.cout, cs.pool_k, cs.pool_s, st));
       Mark(("pool" + std::to_string(i) + "_f32").c_str(), st);
     }
     if (cs.join_src >= 0) {
-      RN_CUDA(JoinF32(pooled_[i], pooled_[cs.join_src], joined_[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
+      RN_CUDA(JoinF32(cur_->pooled[i], cur_->pooled[cs.join_src], cur_->joined[i], ja_[i], jb_[i], jc_[i], n, cs.out_side,
                       shape_.conv[cs.join_src].out_side, cs.cout, st));
       Mark(("join" + std::to_string(i) + "_f32").c_str(), st);
     }
@@ -274,13 +285,13 @@ cudaError_t Replica::ForwardF32(const void* d_in, InputKind kind, int n, cudaStr
   const int k = static_cast<int>(kind);
   Mark(nullptr, st);
   if (kind == InputKind::kF32Rgb)
-    RN_CUDA(Conv3x3Relu6F32<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], conv_scratch_, n, c0.in_side,
+    RN_CUDA(Conv3x3Relu6F32<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], cur_->conv_scratch, n, c0.in_side,
                                    c0.in_side, 3, c0.cout, st));
   else
-    RN_CUDA(Conv3x3Relu6F32<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], conv_scratch_, n, c0.in_side,
+    RN_CUDA(Conv3x3Relu6F32<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], cur_->conv_scratch, n, c0.in_side,
                                      c0.in_side, 3, c0.cout, st));
   Mark("conv0_f32", st);
-  RN_CUDA(AvgPoolF32(conv_scratch_, pooled_[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
+  RN_CUDA(AvgPoolF32(cur_->conv_scratch, cur_->pooled[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
   Mark("pool0_f32", st);
   return TailF32(1, n, st);
 }
@@ -292,23 +303,23 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   Mark(nullptr, st);
   if (kind == InputKind::kF32Rgb) {
     // raw float feed: operands need more than 11 bits, keep conv0 in fp32 on the CUDA cores
-    RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], act_h_[0], n, c0.in_side, half_kind_, st));
+    RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], cur_->act_h[0], n, c0.in_side, half_kind_, st));
     Mark("conv0_pool_h", st);
   } else {
-    RN_CUDA(PrepU8(static_cast<const uint8_t*>(d_in), in_h_, n, c0.in_side, half_kind_, st));
+    RN_CUDA(PrepU8(static_cast<const uint8_t*>(d_in), cur_->in_h, n, c0.in_side, half_kind_, st));
     Mark("prep_u8", st);
     TcConvLayer L0 = tc_[0];
     L0.w_packed = tc0_w_[k];
-    RN_CUDA(ConvTc(L0, in_h_, act_h_[0], n, half_kind_, st));
+    RN_CUDA(ConvTc(L0, cur_->in_h, cur_->act_h[0], n, half_kind_, st));
     Mark("conv0_tc", st);
   }
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
-    const void* in = shape_.conv[i - 1].join_src >= 0 ? join_h_[i - 1] : act_h_[i - 1];
-    RN_CUDA(ConvTc(tc_[i], in, act_h_[i], n, half_kind_, st));
+    const void* in = shape_.conv[i - 1].join_src >= 0 ? cur_->join_h[i - 1] : cur_->act_h[i - 1];
+    RN_CUDA(ConvTc(tc_[i], in, cur_->act_h[i], n, half_kind_, st));
     Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
     if (cs.join_src >= 0) {
-      RN_CUDA(JoinH(act_h_[i], act_h_[cs.join_src], join_h_[i], tc_ja_[i], tc_jb_[i], jc_[i], n, cs.out_side,
+      RN_CUDA(JoinH(cur_->act_h[i], cur_->act_h[cs.join_src], cur_->join_h[i], tc_ja_[i], tc_jb_[i], jc_[i], n, cs.out_side,
                     shape_.conv[cs.join_src].out_side, cs.cout, half_kind_, st));
       Mark(("join" + std::to_string(i) + "_h").c_str(), st);
     }
@@ -317,13 +328,13 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   const ConvShape& cl = shape_.conv[last];
   if (last == 7 && TailFusedSupported(cl.out_side, cl.cout) && shape_.conv[8].pool_k == 4 && shape_.conv[8].pool_s == 2 &&
       shape_.conv[9].pool_k == 4 && shape_.conv[9].pool_s == 2 && shape_.conv[9].join_src == 7) {
-    RN_CUDA(TailFused(act_h_[7], n, cl.out_side, static_cast<float>(1.0 / act_scale_[7]), cw_[8], cb_[8], cw_[9], cb_[9],
-                      ja_[9], jb_[9], jc_[9], dense_, shape_.flat_len, half_kind_, d_top1, d_probs, d_logits, pooled_[8],
-                      joined_[9], st));
+    RN_CUDA(TailFused(cur_->act_h[7], n, cl.out_side, static_cast<float>(1.0 / act_scale_[7]), cw_[8], cb_[8], cw_[9], cb_[9],
+                      ja_[9], jb_[9], jc_[9], dense_, shape_.flat_len, half_kind_, d_top1, d_probs, d_logits, cur_->pooled[8],
+                      cur_->joined[9], st));
     Mark("tail_fused", st);
     return cudaSuccess;
   }
-  RN_CUDA(ChunkedToF32(act_h_[last], pooled_[last], n, cl.out_side, cl.cout, half_kind_,
+  RN_CUDA(ChunkedToF32(cur_->act_h[last], cur_->pooled[last], n, cl.out_side, cl.cout, half_kind_,
                        static_cast<float>(1.0 / act_scale_[last]), st));
   Mark("chunked_to_f32", st);
   cudaError_t e = TailF32(first_f32_layer_, n, st);
@@ -333,8 +344,8 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
 
 cudaError_t Replica::DenseTail(int n, long long* d_top1, float* d_probs, float* d_logits, cudaStream_t st) {
   const ConvShape& cl = shape_.conv[kNumConvs - 1];
-  const float* flat = cl.join_src >= 0 ? joined_[kNumConvs - 1] : pooled_[kNumConvs - 1];
-  RN_CUDA(DenseTailF32(flat, n, shape_.flat_len, dense_, d_top1, d_probs, d_logits, d_pre_, st));
+  const float* flat = cl.join_src >= 0 ? cur_->joined[kNumConvs - 1] : cur_->pooled[kNumConvs - 1];
+  RN_CUDA(DenseTailF32(flat, n, shape_.flat_len, dense_, d_top1, d_probs, d_logits, cur_->d_pre, st));
   Mark("dense_tail", st);
   return cudaSuccess;
 }
@@ -353,7 +364,7 @@ cudaError_t Replica::ForwardDevice(const void* d_in, InputKind kind, int n, long
     e = ForwardTc(d_in, kind, n, d_top1, d_probs, d_logits, st);
   }
   if (e != cudaSuccess) return e;
-  last_n_ = n;
+  cur_->last_n = n;
   return cudaSuccess;
 }
 
@@ -364,12 +375,27 @@ cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long l
   last_launches_ = 0;
   const size_t per = InputBytesPerImage(shape_, kind);
   const int C = shape_.num_classes;
-  for (int off = 0; off < n; off += max_batch_) {
-    int m = std::min(max_batch_, n - off);
+  // Two half-size micro-batches on two streams overlap better than one big one (see ActSet); while
+  // profiling everything stays on `st` so that the per-kernel events measure isolated kernels.
+  const bool overlap = !profiling_ && n >= 64;
+  const int chunk = overlap ? std::min(max_batch_, std::max(32, (n + 1) / 2)) : max_batch_;
+  if (overlap) RN_CUDA(cudaEventRecord(ev_fork_, st));
+  int k = 0;
+  for (int off = 0; off < n; off += chunk, ++k) {
+    const int m = std::min(chunk, n - off);
+    cur_ = &sets_[overlap ? (k & 1) : 0];
+    cudaStream_t s = overlap ? cur_->stream : st;
+    if (overlap && k < 2) RN_CUDA(cudaStreamWaitEvent(s, ev_fork_, 0));
     cudaError_t e = ForwardDevice(static_cast<const char*>(d_in) + per * off, kind, m, d_top1 ? d_top1 + off : nullptr,
                                   d_probs ? d_probs + static_cast<size_t>(off) * C : nullptr,
-                                  d_logits ? d_logits + static_cast<size_t>(off) * C : nullptr, st);
+                                  d_logits ? d_logits + static_cast<size_t>(off) * C : nullptr, s);
     if (e != cudaSuccess) return e;
+  }
+  if (overlap) {
+    for (int si = 0; si < std::min(k, 2); ++si) {
+      RN_CUDA(cudaEventRecord(sets_[si].ev_done, sets_[si].stream));
+      RN_CUDA(cudaStreamWaitEvent(st, sets_[si].ev_done, 0));
+    }
   }
   return cudaSuccess;
 }
@@ -401,10 +427,12 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
     return cudaSuccess;
   };
   (void)out_stride;
+  // at least two micro-batches per call when the call is large: H2D of one overlaps compute of the other
+  const int chunk = n >= 64 ? std::min(max_batch_, std::max(32, (n + 1) / 2)) : max_batch_;
   int k = 0;
-  for (int off = 0; off < n; off += max_batch_, ++k) {
+  for (int off = 0; off < n; off += chunk, ++k) {
     const int slot = k & 1;
-    const int m = std::min(max_batch_, n - off);
+    const int m = std::min(chunk, n - off);
     cudaError_t e = drain(slot);  // slot buffers (d_in_, h_in_, outputs) are free after this
     if (e != cudaSuccess) return e;
     const char* src = static_cast<const char*>(h_in) + per * off;
@@ -414,16 +442,18 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
     }
     RN_CUDA(cudaMemcpyAsync(d_in_[slot], src, per * m, cudaMemcpyHostToDevice, copy_));
     RN_CUDA(cudaEventRecord(ev_h2d_[slot], copy_));
-    RN_CUDA(cudaStreamWaitEvent(compute_, ev_h2d_[slot], 0));
-    e = ForwardDevice(d_in_[slot], kind, m, d_top1_[slot], d_probs_[slot], d_logits_[slot], compute_);
+    cur_ = &sets_[profiling_ ? 0 : slot];
+    cudaStream_t cs = profiling_ ? compute_ : cur_->stream;
+    RN_CUDA(cudaStreamWaitEvent(cs, ev_h2d_[slot], 0));
+    e = ForwardDevice(d_in_[slot], kind, m, d_top1_[slot], d_probs_[slot], d_logits_[slot], cs);
     if (e != cudaSuccess) return e;
     char* base = h_out_[slot];
-    RN_CUDA(cudaMemcpyAsync(base, d_top1_[slot], m * sizeof(long long), cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaMemcpyAsync(base, d_top1_[slot], m * sizeof(long long), cudaMemcpyDeviceToHost, cs));
     RN_CUDA(cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[slot], m * C * sizeof(float),
-                            cudaMemcpyDeviceToHost, compute_));
+                            cudaMemcpyDeviceToHost, cs));
     RN_CUDA(cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[slot],
-                            m * C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
-    RN_CUDA(cudaEventRecord(ev_done_[slot], compute_));
+                            m * C * sizeof(float), cudaMemcpyDeviceToHost, cs));
+    RN_CUDA(cudaEventRecord(ev_done_[slot], cs));
     pend[slot].off = off;
     pend[slot].m = m;
     pend[slot].active = true;
@@ -438,26 +468,26 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
 
 cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dims[4]) {
   RN_CUDA(cudaSetDevice(device_));
-  if (layer < 0 || layer >= kNumConvs || last_n_ <= 0) {
+  if (layer < 0 || layer >= kNumConvs || cur_->last_n <= 0) {
     err_ = "no activation recorded for that layer";
     return cudaErrorInvalidValue;
   }
   const ConvShape& cs = shape_.conv[layer];
-  dims[0] = last_n_;
+  dims[0] = cur_->last_n;
   dims[1] = dims[2] = cs.out_side;
   dims[3] = cs.cout;
-  size_t elems = static_cast<size_t>(last_n_) * cs.out_side * cs.out_side * cs.cout;
+  size_t elems = static_cast<size_t>(cur_->last_n) * cs.out_side * cs.out_side * cs.cout;
   out->resize(elems);
-  RN_CUDA(cudaStreamSynchronize(compute_));
+  RN_CUDA(cudaDeviceSynchronize());
   const float* src = nullptr;
   float* tmp = nullptr;
   if (layer >= first_f32_layer_) {
-    src = cs.join_src >= 0 ? joined_[layer] : pooled_[layer];
+    src = cs.join_src >= 0 ? cur_->joined[layer] : cur_->pooled[layer];
   } else {
     RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), elems * sizeof(float)));
-    const void* h = cs.join_src >= 0 ? join_h_[layer] : act_h_[layer];
+    const void* h = cs.join_src >= 0 ? cur_->join_h[layer] : cur_->act_h[layer];
     const float sc = cs.join_src >= 0 ? 1.f : static_cast<float>(1.0 / act_scale_[layer]);
-    cudaError_t e = ChunkedToF32(h, tmp, last_n_, cs.out_side, cs.cout, half_kind_, sc, compute_);
+    cudaError_t e = ChunkedToF32(h, tmp, cur_->last_n, cs.out_side, cs.cout, half_kind_, sc, compute_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(compute_);
     if (e != cudaSuccess) {
       cudaFree(tmp);

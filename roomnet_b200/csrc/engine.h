@@ -28,7 +28,7 @@ class Replica {
   int device() const { return device_; }
   int max_batch() const { return max_batch_; }
 
-  // n <= max_batch images already resident on this device; enqueues on `st`, no sync.
+  // n <= max_batch images already resident on this device; enqueues on `st` using activation set `cur_`.
   cudaError_t ForwardDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
                             float* d_logits, cudaStream_t st);
   // Arbitrary n from host memory (pinned or pageable), double-buffered micro-batches; synchronous.
@@ -65,7 +65,6 @@ class Replica {
   bool loaded_ = false;
   std::string err_;
   int last_launches_ = 0;
-  int last_n_ = 0;
   bool profiling_ = false;
   std::vector<cudaEvent_t> prof_events_;
   std::vector<std::string> prof_names_;  // prof_names_[i] = kernel between event i and i+1 ("" = gap)
@@ -92,17 +91,28 @@ class Replica {
   double act_scale_[kNumConvs] = {};
   float* tc_bias_[kNumConvs] = {};
   void* tc0_w_[2] = {nullptr, nullptr};  // conv0 packed weights for uint8 BGR / RGB byte order
-  void* in_h_ = nullptr;                // uint8 image expanded to pixel-pair chunks (PrepU8)
   float* tc_ja_[kNumConvs] = {};
   float* tc_jb_[kNumConvs] = {};
   HalfKind half_kind_ = HalfKind::kF16;
 
-  // activations
-  float* conv_scratch_ = nullptr;
-  float* pooled_[kNumConvs] = {};
-  float* joined_[kNumConvs] = {};
-  void* act_h_[kNumConvs] = {};
-  void* join_h_[kNumConvs] = {};
+  // Activations.  Two independent sets, each with its own stream: consecutive micro-batches alternate between
+  // them so that the memory-bound kernels of one (residual joins, image expansion, tail) overlap the
+  // tensor-core kernels of the other on the same SMs.
+  struct ActSet {
+    float* conv_scratch = nullptr;
+    float* pooled[kNumConvs] = {};
+    float* joined[kNumConvs] = {};
+    void* act_h[kNumConvs] = {};
+    void* join_h[kNumConvs] = {};
+    void* in_h = nullptr;  // uint8 image expanded to pixel-pair chunks (PrepU8)
+    float* d_pre = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_done = nullptr;
+    int last_n = 0;
+  };
+  ActSet sets_[2];
+  ActSet* cur_ = &sets_[0];
+  cudaEvent_t ev_fork_ = nullptr;
   int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
 
   // staging
@@ -111,7 +121,6 @@ class Replica {
   long long* d_top1_[2] = {nullptr, nullptr};
   float* d_probs_[2] = {nullptr, nullptr};
   float* d_logits_[2] = {nullptr, nullptr};
-  float* d_pre_ = nullptr;
   char* h_out_[2] = {nullptr, nullptr};
 };
 
