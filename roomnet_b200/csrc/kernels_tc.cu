@@ -21,6 +21,7 @@
 //   * Epilogue warps read a finished conv row from TMEM (lane = pixel, column =
 //     channel), add bias, clip, keep the vertical pooling window in registers, do
 //     the horizontal window with warp shuffles, and write 16-byte channel chunks.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -73,6 +74,15 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+// 4-D tiled TMA load (cp.async.bulk.tensor): box -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_tensor4_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -140,6 +150,8 @@ struct TcParams {
   int n_strips;
   int strip_step_in;  // input/conv column step between strips
   int strip_step_out; // output column step between strips
+  int win_step_in;    // POOL != 0: input-pixel step between the four 32-lane windows of a tile
+  int win_step_out;   // ... and the number of output columns each window produces
   int rows_per_item;  // pooled (output) rows per work item
   int n_rowblocks;
   int n_items;
@@ -151,8 +163,11 @@ struct TcParams {
 // AMODE: 0 = channel-chunk planes (Cin >= 16), 1 = Cin 8: pixel pairs form a K=16 step (LBO = 16 B),
 //        2 = conv0: a 16-byte chunk holds pixels (x, x+1) x (c0,c1,c2,0); chunks x and x+2 (LBO = 32 B) form one
 //            K=16 step that covers all three dx taps; the two k-steps are the hi and lo halves of the weights
-template <int CB, int COUT, int AMODE>
+template <int CB, int COUT, int AMODE, bool WINDOWS>
 struct TcCfg {
+  // windowed tiles are written by one tiled TMA box [CB][4 windows][32 px][8] -> dense 128-pixel planes
+  static constexpr int kPlanePxT = WINDOWS ? 128 : kPlanePx;
+  static constexpr int kPlaneBytesT = kPlanePxT * 16;
   static constexpr int kPlanes = AMODE == 0 ? 3 * CB : 4;       // weight planes
   static constexpr int kKSteps = AMODE == 0 ? 3 * (CB / 2) : 2; // MMAs per input row
   static constexpr int kSlots = (512 / COUT) > 16 ? 16 : (512 / COUT);
@@ -160,16 +175,15 @@ struct TcCfg {
   static_assert(kSlots == 16 || kSlots == 8, "ring size must be a power of two");
   static constexpr int kTmemCols = kSlots * COUT;
   static constexpr int kWBytes = kPlanes * 3 * COUT * 16;
-  static constexpr int kStageBytes = CB * kPlaneBytes;
-  static constexpr int kXgBytes = 2 * 2 * 4 * 2 * (COUT / 4) * 16;  // [grp][parity][quad][out row][pair] uint4
-  static constexpr int kFixedBytes = kWBytes + COUT * 4 + kXgBytes + 1024;
+  static constexpr int kStageBytes = CB * kPlaneBytesT + (WINDOWS ? 128 : 0);  // + tap over-read of the last plane
+  static constexpr int kFixedBytes = kWBytes + COUT * 4 + 1024;
   static constexpr int kStagesFit = (kSmemBudget - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
   static_assert(kStages >= 3, "not enough shared memory for a 3-stage input ring");
   // descriptor offsets (in 16-byte units) of k-step ks relative to the stage / weight base
   __host__ __device__ static constexpr uint32_t a_off16(int ks) {
-    return AMODE == 0 ? static_cast<uint32_t>((2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * kPlanePx + ks / (CB / 2 > 0 ? CB / 2 : 1))
+    return AMODE == 0 ? static_cast<uint32_t>((2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * kPlanePxT + ks / (CB / 2 > 0 ? CB / 2 : 1))
            : AMODE == 1 ? static_cast<uint32_t>(2 * ks)
                         : 0u;
   }
@@ -177,12 +191,12 @@ struct TcCfg {
     return AMODE == 0 ? static_cast<uint32_t>(((ks / (CB / 2 > 0 ? CB / 2 : 1)) * CB + 2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * 3 * COUT)
                       : static_cast<uint32_t>(2 * ks * 3 * COUT);
   }
-  static constexpr uint32_t kALbo16 = AMODE == 0 ? kPlanePx : (AMODE == 1 ? 1 : 2);  // K-direction core-matrix stride / 16
+  static constexpr uint32_t kALbo16 = AMODE == 0 ? kPlanePxT : (AMODE == 1 ? 1 : 2);  // K-direction core-matrix stride / 16
   static constexpr uint32_t kBLbo16 = 3 * COUT;
 };
 
 struct Item {
-  int n0, x_in0, x_out0, po0, npo, c0, nconv;
+  int n0, strip, x_in0, x_out0, po0, npo, c0, nconv;
 };
 
 template <int POOL, int SEG>
@@ -193,6 +207,7 @@ __device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
   int strip = t % p.n_strips;
   int ig = t / p.n_strips;
   it.n0 = ig * SEG;
+  it.strip = strip;
   it.x_in0 = strip * p.strip_step_in;
   it.x_out0 = strip * p.strip_step_out;
   it.po0 = rb * p.rows_per_item;
@@ -345,8 +360,9 @@ constexpr int kThreadsTc = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warp
 // ---------------------------------------------------------------------------
 // CREAL: channels actually produced (<= COUT; conv0 pads 8 -> 16 to satisfy UMMA N % 16 == 0)
 template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT>
-__global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p) {
-  using Cfg = TcCfg<CB, COUT, AMODE>;
+__global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+  using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
+  static_assert(POOL == 0 || SEG == 1, "windowed (pooled) tiles hold one image");
   using HH = H2<BF16>;
   constexpr int R = Cfg::kSlots;
   constexpr int LOGR = Cfg::kLogSlots;
@@ -355,15 +371,17 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
   constexpr int NG = 2;                    // epilogue channel groups (4 warps each)
   constexpr int CG = CREAL / NG;           // channels per epilogue group
   constexpr int NP = CG / 2;     // half2 pairs per thread
-  constexpr uint32_t kStageTx = CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16);
+  // POOL != 0: the 128 lanes are four 32-pixel windows that overlap in the image (each window carries its own
+  // pooling halo), so no epilogue warp ever needs a neighbour quadrant's columns.  POOL == 0: one contiguous run.
+  constexpr bool kWindows = POOL != 0;
+  constexpr uint32_t kStageTx = kWindows ? CB * 4 * 32 * 16 : CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16);
   constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
 
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + Cfg::kWBytes;
   float* s_bias = reinterpret_cast<float*>(s_stage + NST * Cfg::kStageBytes);
-  uint4* s_xg = reinterpret_cast<uint4*>(s_bias + COUT);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_xg) + Cfg::kXgBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + COUT);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1 + 2 * R);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -394,6 +412,13 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < COUT; i += kThreadsTc) s_bias[i] = bias_g[i];
+  if (POOL != 0) {
+    // The 128-byte pad behind the last plane of every stage is never written by the TMA box but is read (with
+    // zero weights, Cin = 8 layers) by the tap shift of lane 125: it must hold finite values, so zero it once.
+    for (int i = threadIdx.x; i < NST * 32; i += kThreadsTc)
+      reinterpret_cast<uint32_t*>(s_stage + (i / 32) * Cfg::kStageBytes + CB * Cfg::kPlaneBytesT)[i % 32] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -404,36 +429,66 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
+    // All 32 lanes issue bulk copies (one (plane, window) pair per lane and round) so that the 4*CB small
+    // copies of a windowed row go out in parallel; lane 0 arms the transaction barrier first.
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, Cfg::kWBytes);
       for (int off = 0; off < Cfg::kWBytes; off += 16384) {
         int sz = min(16384, Cfg::kWBytes - off);
         tma_bulk_g2s(smem_u32(s_w + off), w_gmem + off, sz, bar_w);
       }
-      uint32_t st = 0, ph = 1;  // waiting parity 1 on a fresh "empty" barrier passes immediately
-      const uint32_t stage0 = smem_u32(s_stage);
+    }
+    uint32_t st = 0, ph = 1;  // waiting parity 1 on a fresh "empty" barrier passes immediately
+    const uint32_t stage0 = smem_u32(s_stage);
+    if constexpr (kWindows) {
+      // one tiled TMA box per input row: [CB planes][4 windows][32 pixels][8 channels]; the window dimension has
+      // a global stride of win_step pixels (< 32), i.e. the windows overlap in memory and every window arrives
+      // with its own pooling halo
+      if (lane == 0) {
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const Item it = decode_item<POOL, SEG>(p, item);
+          const int nin = it.nconv + 2;
+          int row = it.n0 * p.in_side + it.c0;
+          for (int r = 0; r < nin; ++r, ++row) {
+            mbar_wait(bar_empty0 + 8u * st, ph);
+            const uint32_t full = bar_full0 + 8u * st;
+            mbar_arrive_expect_tx(full, kStageTx);
+            tma_tensor4_g2s(stage0 + st * Cfg::kStageBytes, &tmap, 0, 4 * it.strip, 0, row, full);
+            if (++st == NST) {
+              st = 0;
+              ph ^= 1;
+            }
+          }
+        }
+      }
+    } else {
+      constexpr int kCopies = SEG * CB;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const Item it = decode_item<POOL, SEG>(p, item);
         const int nin = it.nconv + 2;
         const uint8_t* src0 = p.in + it.n0 * in_img_bytes + it.c0 * in_row_bytes + static_cast<size_t>(it.x_in0) * 16;
         const uint8_t* src1 = p.in + min(it.n0 + 1, p.N - 1) * in_img_bytes + it.c0 * in_row_bytes;
+        // per-lane copy descriptors (fixed for the whole item): source, destination offset, size
+        const uint8_t* lsrc[(kCopies + 31) / 32];
+        uint32_t ldst[(kCopies + 31) / 32];
+#pragma unroll
+        for (int k = 0; k < (kCopies + 31) / 32; ++k) {
+          const int idx = min(lane + 32 * k, kCopies - 1);
+          const int c = idx / SEG, sg = idx % SEG;
+          lsrc[k] = (sg ? src1 : src0) + static_cast<size_t>(c) * p.in_side * 16;
+          ldst[k] = c * Cfg::kPlaneBytesT + sg * SEGW * 16;
+        }
         for (int r = 0; r < nin; ++r) {
           mbar_wait(bar_empty0 + 8u * st, ph);
           const uint32_t full = bar_full0 + 8u * st;
-          mbar_arrive_expect_tx(full, kStageTx);
+          if (lane == 0) mbar_arrive_expect_tx(full, kStageTx);
+          __syncwarp();
           const uint32_t dst = stage0 + st * Cfg::kStageBytes;
 #pragma unroll
-          for (int c = 0; c < CB; ++c) {
-            if (SEG == 1) {
-              tma_bulk_g2s(dst + c * kPlaneBytes, src0 + static_cast<size_t>(c) * p.in_side * 16, kLoadPx * 16, full);
-            } else {
-              tma_bulk_g2s(dst + c * kPlaneBytes, src0 + static_cast<size_t>(c) * p.in_side * 16, SEGW * 16, full);
-              tma_bulk_g2s(dst + c * kPlaneBytes + SEGW * 16, src1 + static_cast<size_t>(c) * p.in_side * 16, SEGW * 16,
-                           full);
-            }
+          for (int k = 0; k < (kCopies + 31) / 32; ++k) {
+            if (lane + 32 * k < kCopies) tma_bulk_g2s(dst + ldst[k], lsrc[k], SEG == 1 ? kLoadPx * 16 : SEGW * 16, full);
+            lsrc[k] += in_row_bytes;
           }
-          src0 += in_row_bytes;
-          src1 += in_row_bytes;
           if (++st == NST) {
             st = 0;
             ph ^= 1;
@@ -503,7 +558,6 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
     const size_t out_row_bytes = static_cast<size_t>(p.cb_out_total) * p.out_side * 16;
     const size_t out_img_bytes = out_row_bytes * p.out_side;
     const size_t out_plane_bytes = static_cast<size_t>(p.out_side) * 16;
-    const uint32_t bar_id = 1 + grp;
     constexpr int KW = POOL == 31 ? 3 : 4;        // pooling window
     constexpr int LAG = POOL == 42 ? 2 : KW - 1;  // conv rows between an output row's first row and its last
 
@@ -521,18 +575,19 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
     uint32_t G = 0, iter = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode_item<POOL, SEG>(p, item);
-      const int n_img = it.n0 + seg;
+      int n_img, col;
       bool col_ok;
-      int col;
       if (POOL == 0) {
+        n_img = it.n0 + seg;
         col = it.x_in0 + xs;
         col_ok = col < p.conv_side;
-      } else if (POOL == 42) {
-        col = it.x_out0 + (xs >> 1);
-        col_ok = !(xs & 1) && (xs + 3 < SEGW) && col < p.out_side;
       } else {
-        col = it.x_out0 + xs;
-        col_ok = (xs + KW - 1 < SEGW) && col < p.out_side;
+        // window `win` of this image starts win_step_out output columns after the previous one
+        const int win = SEG == 1 ? quad : (quad & 1);
+        n_img = it.n0 + (SEG == 1 ? 0 : (quad >> 1));
+        const int lcol = POOL == 42 ? (lane >> 1) : lane;  // output column inside the window
+        col = it.x_out0 + win * p.win_step_out + lcol;
+        col_ok = lcol < p.win_step_out && !(POOL == 42 && (lane & 1)) && col < p.out_side;
       }
       col_ok = col_ok && n_img < p.N;
       // output row pointer of the row produced by output slot 0 of the current iteration (may start "before" po0)
@@ -611,61 +666,24 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
           if (POOL != 42) vp[1][i] = HH::pack(o1[0], o1[1]);
         }
 
-        // ---- horizontal window with warp shuffles; the columns owned by the next quadrant come through smem
+        // ---- horizontal window with warp shuffles (every window owns its halo, see kWindows)
         uint32_t hp[2][NP];
         constexpr int NK = (POOL == 42) ? 1 : 2;
-        if (POOL == 0) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k)
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
-            hp[0][i] = vp[0][i];
-            hp[1][i] = vp[1][i];
+            const uint32_t v = vp[k][i];
+            if (POOL == 0) {
+              hp[k][i] = v;
+            } else if (POOL == 42) {
+              const uint32_t u = HH::add(v, __shfl_xor_sync(0xffffffffu, v, 1));
+              hp[k][i] = HH::add(u, __shfl_down_sync(0xffffffffu, u, 2));
+            } else {
+              const uint32_t t = HH::add(v, __shfl_down_sync(0xffffffffu, v, 1));
+              hp[k][i] = HH::add(t, __shfl_down_sync(0xffffffffu, POOL == 41 ? t : v, 2));
+            }
           }
-        } else {
-          // ghost record per (output slot k, pair i): 16 bytes, see the readers below
-          uint32_t* xw = reinterpret_cast<uint32_t*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + quad) * 2) * NP));
-          const uint32_t* xr =
-              reinterpret_cast<const uint32_t*>(s_xg + ((((grp * 2 + (iter & 1)) * 4 + ((quad + 1) & 3)) * 2) * NP));
-          uint32_t tt[2][NP];
-#pragma unroll
-          for (int k = 0; k < NK; ++k)
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-              const uint32_t v = vp[k][i];
-              uint32_t* rec = xw + (k * NP + i) * 4;
-              if (POOL == 42) {
-                const uint32_t u = HH::add(v, __shfl_xor_sync(0xffffffffu, v, 1));
-                tt[k][i] = u;
-                if (lane == 0) rec[0] = u;
-              } else {
-                const uint32_t t = HH::add(v, __shfl_down_sync(0xffffffffu, v, 1));
-                tt[k][i] = t;
-                // record = {x, A | v0, B}: lane 30 of the previous quadrant reads (x, A), lane 31 reads (v0, B)
-                //   41: A = t0, B = t1        31: A = v0, B = v1
-                if (lane < 2) rec[2 * lane + 1] = (POOL == 41) ? t : v;
-                if (lane == 0) rec[2] = v;
-              }
-            }
-          asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-#pragma unroll
-          for (int k = 0; k < NK; ++k)
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-              const uint32_t* rec = xr + (k * NP + i) * 4;
-              if (POOL == 42) {
-                uint32_t nb = __shfl_down_sync(0xffffffffu, tt[k][i], 2);
-                if (lane == 30) nb = rec[0];
-                hp[k][i] = HH::add(tt[k][i], nb);
-              } else {
-                uint2 gg = make_uint2(0u, 0u);
-                if (lane >= 30) gg = *reinterpret_cast<const uint2*>(rec + 2 * (lane - 30));
-                uint32_t t = tt[k][i];
-                if (lane == 31) t = HH::add(vp[k][i], gg.x);
-                uint32_t nb = __shfl_down_sync(0xffffffffu, POOL == 41 ? t : vp[k][i], 2);
-                if (lane >= 30) nb = gg.y;
-                hp[k][i] = HH::add(t, nb);
-              }
-            }
-        }
         // ---- stores: output slot k of this iteration is row (first + k) relative to the item
         {
           int first;  // index (relative to po0 / c0) of output slot 0
@@ -1036,9 +1054,13 @@ __global__ void prep_u8_kernel(const uint8_t* __restrict__ in, uint4* __restrict
   }
 }
 
+using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT>
 cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
-  using Cfg = TcCfg<CB, COUT, AMODE>;
+  using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
   TcParams p{};
   p.in = static_cast<const uint8_t*>(in);
   p.out = static_cast<uint8_t*>(out);
@@ -1055,12 +1077,14 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   if (POOL == 0) {
     p.strip_step_in = p.strip_step_out = kTileM;
     p.n_strips = SEG == 2 ? 1 : (p.conv_side + kTileM - 1) / kTileM;
-  } else if (POOL == 42) {
-    p.strip_step_out = (kTileM - 4) / 2 + 1;  // 63 pooled columns per strip
-    p.strip_step_in = 2 * p.strip_step_out;
-    p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
   } else {
-    p.strip_step_in = p.strip_step_out = kTileM - (POOL == 41 ? 3 : 2);
+    // a 32-lane window yields 30 valid conv columns (taps of lanes 30/31 cross into the next window)
+    p.win_step_out = POOL == 41 ? 27 : (POOL == 31 ? 28 : 14);
+    p.win_step_in = POOL == 42 ? 2 * p.win_step_out : p.win_step_out;
+    const int wins = 4;
+    p.strip_step_out = wins * p.win_step_out;
+    p.strip_step_in = wins * p.win_step_in;
+    if (SEG == 2 && p.out_side > p.strip_step_out) return cudaErrorInvalidValue;
     p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
   }
   const int groups = (N + SEG - 1) / SEG;
@@ -1077,7 +1101,31 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   if (ea != cudaSuccess) return ea;
   const int gx = std::max(1, std::min(p.n_items, 148 / L.cout_parts));
   dim3 grid(gx, L.cout_parts);
-  kern<<<grid, kThreadsTc, Cfg::kSmemBytes, st>>>(p);
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  if (POOL != 0) {
+    // dims (fastest first): 256 elements = one 32-pixel window | window index (stride = win_step pixels, overlapping)
+    //                       | channel-chunk plane | image row.  Box = all four windows x all planes of one row.
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      cudaError_t ee = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+      if (ee != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
+      encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    }
+    const cuuint64_t gdim[4] = {256, static_cast<cuuint64_t>(4 * p.n_strips), static_cast<cuuint64_t>(CB),
+                                static_cast<cuuint64_t>(N) * p.in_side};
+    const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.win_step_in) * 16, static_cast<cuuint64_t>(p.in_side) * 16,
+                                static_cast<cuuint64_t>(CB) * p.in_side * 16};
+    const cuuint32_t box[4] = {256, 4, static_cast<cuuint32_t>(CB), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint8_t*>(p.in), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
+  kern<<<grid, kThreadsTc, Cfg::kSmemBytes, st>>>(p, tmap);
   return cudaGetLastError();
 }
 
@@ -1181,7 +1229,8 @@ cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cu
 
 cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
   const int cb = L.cin / 8, cp = L.cout / L.cout_parts;
-  const bool seg2 = L.in_side <= 64;
+  // two images per tile: 2 x 64 lanes (no pooling) or 2 x 2 windows of 14 pooled columns (4x4/2 pooling)
+  const bool seg2 = L.pool_k ? (L.out_side <= 28 && L.in_side <= 64) : L.in_side <= 64;
   const int pool = L.pool_k * 10 + L.pool_s;
   if (L.amode == 2) return launch_tc<1, 16, 31, 1, 2, 8>(L, in, out, N, kind, st);
   if (cb == 1 && cp == 32 && pool == 41) return launch_tc<1, 32, 41, 1, 1>(L, in, out, N, kind, st);
@@ -1190,8 +1239,7 @@ cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfK
   if (cb == 8 && cp == 64 && pool == 42) return launch_tc<8, 64, 42, 1, 0>(L, in, out, N, kind, st);
   if (cb == 8 && cp == 64 && pool == 0)
     return seg2 ? launch_tc<8, 64, 0, 2, 0>(L, in, out, N, kind, st) : launch_tc<8, 64, 0, 1, 0>(L, in, out, N, kind, st);
-  if (cb == 16 && cp == 16 && pool == 42)
-    return seg2 ? launch_tc<16, 16, 42, 2, 0>(L, in, out, N, kind, st) : launch_tc<16, 16, 42, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 16 && cp == 16 && pool == 42) return launch_tc<16, 16, 42, 1, 0>(L, in, out, N, kind, st);
   return cudaErrorInvalidValue;
 }
 
