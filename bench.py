@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.05)
 
     def stop(self):
         self._stop_evt.set()
@@ -153,6 +153,7 @@ def main():
     from oracle.roomnet_oracle import synthetic_suite
     from oracle.tf_bundle import default_checkpoint_prefix
     from roomnet_b200 import _capi
+    from roomnet_b200.sharding import aggregate_throughput, reduce_max
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
@@ -210,13 +211,8 @@ def main():
         step_device(i)
     ev1.record(stream)
     barrier()
-    clocks = sampler.stop()
-    ms_dev = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev = float(t.item())
-    value = world * B * args.steps / (ms_dev * 1e-3)
+    ms_dev = reduce_max(ev0.elapsed_time(ev1), dev)  # device time, MAX over ranks
+    value = aggregate_throughput(B, world, args.steps, ms_dev * 1e-3)
 
     # ---- per-kernel times (CUDA events between launches on the launching stream), rank 0 ----
     prof = []
@@ -241,12 +237,10 @@ def main():
     for i in range(args.steps):
         step_host(i)
     torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = world * B * args.steps / float(t.item())
+    dt = reduce_max(time.perf_counter() - t0, dev)
+    e2e = aggregate_throughput(B, world, args.steps, dt)
     barrier()
+    clocks = sampler.stop()  # sampled across the device-timed, per-kernel and end-to-end regions
 
     if rank == 0:
         peaks = load_peaks()
@@ -259,8 +253,12 @@ def main():
             if layer is not None:
                 flops_per_launch = conv_flops(layer) * B * args.steps / top["launches"]
                 achieved = flops_per_launch / (top["ms"] / top["launches"] * 1e-3) / 1e12
+                traffic = None
+                tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+                if os.path.exists(tpath):  # dram bytes per launch of this kernel from the committed ncu --set full capture
+                    traffic = json.load(open(tpath)).get(top["name"], {}).get("dram_bytes_per_launch_b%d" % (B // 2))
                 roofline = {"bound": "tensor", "kernel": top["name"], "achieved": achieved, "peak": peaks["tflops"],
-                            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
                             "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
                             "share_of_step": top["ms"] / total_ms,
                             "whole_path": {"achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
@@ -278,9 +276,9 @@ def main():
             "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": "RoomNet final_model @224x224 inference, batch %d per GPU, BN folded, %s operands / "
                                    "fp32 accumulate" % (B, args.precision),
-                       "batch_per_gpu": B, "l2_policy": "%d distinct input batches (%.0f MB) cycled; activations "
-                                                        "(%.0f MB per micro-batch) exceed L2" % (
-                                                            N_INPUT_SETS, N_INPUT_SETS * B * 150528 / 1e6, 14.3 * 64),
+                       "batch_per_gpu": B, "l2_policy": "%d distinct input batches (%.0f MB) cycled; the inter-layer "
+                                                        "activations (~%.0f MB per step) far exceed the 126 MB L2" % (
+                                                            N_INPUT_SETS, N_INPUT_SETS * B * 150528 / 1e6, 15.2 * B),
                        "parallelism": "replicas x%d (no collective)" % world},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": B * 224 * 224 * 3,
