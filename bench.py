@@ -118,8 +118,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "images_per_sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step / ips * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "RoomNet final_model @224x224, CPU restatement of the reference TF graph "
-                               "(TensorFlow 1.13.1 not installable), batch 1", "p50_ms": p50},
+        "config": {"workload": "RoomNet final_model @224x224 inference (reference arm: CPU restatement of the TF-1.13.1 "
+                               "graph, TensorFlow itself is not installable; batch 1, sequential, as infer.py does)",
+                   "batch_per_gpu": BATCH_PER_GPU, "p50_ms": p50},
         "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -160,6 +161,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.batch

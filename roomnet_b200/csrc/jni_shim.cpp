@@ -105,6 +105,7 @@ jint RN_JNI(run)(JNIEnv* env, jclass, jlong handle, jobject img_data, jobjectArr
   }
   jobject row = Slot<JniGetObjectArrayElementFn>(env, kJniGetObjectArrayElement)(env, label_prob_array, 0);
   if (!row || Slot<JniGetArrayLengthFn>(env, kJniGetArrayLength)(env, row) < m->num_classes) {
+    if (row) Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
     Throw(env, "java/lang/IllegalArgumentException", "RoomNet: labelProbArray[0] is shorter than the label count");
     return RN_ERR_INVALID_ARG;
   }
@@ -115,17 +116,16 @@ jint RN_JNI(run)(JNIEnv* env, jclass, jlong handle, jobject img_data, jobjectArr
   } else if (cap == px) {
     rc = rn_infer_u8_rgb(m->h, static_cast<const uint8_t*>(data), 1, nullptr, probs, nullptr);
   } else {
+    rc = RN_ERR_INVALID_ARG;
     Throw(env, "java/lang/IllegalArgumentException",
           "RoomNet: imgData capacity " + std::to_string(cap) + " is neither float32 nor uint8 1xSxSx3");
-    return RN_ERR_INVALID_ARG;
   }
-  if (rc != RN_OK) {
+  if (rc == RN_OK)
+    Slot<JniSetFloatArrayRegionFn>(env, kJniSetFloatArrayRegion)(env, row, 0, m->num_classes, probs);
+  else if (cap == px * 4 || cap == px)
     Throw(env, "java/lang/IllegalStateException", std::string("RoomNet: ") + rn_last_error(m->h));
-    return rc;
-  }
-  Slot<JniSetFloatArrayRegionFn>(env, kJniSetFloatArrayRegion)(env, row, 0, m->num_classes, probs);
-  Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
-  return RN_OK;
+  Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);  // the row reference is released on every path
+  return rc;
 }
 
 // Classifier.close() (Classifier.java:291-301)
