@@ -108,7 +108,7 @@ class Handle:
             raise RoomNetError(rc, lib.rn_last_error(self._h).decode())
 
     def close(self):
-        if getattr(self, "_h", None) and self._h.value:
+        if getattr(self, "_h", None) and self._h.value and lib is not None:  # lib is None at interpreter shutdown
             lib.rn_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -259,19 +260,32 @@ struct H2 {
   }
 };
 
+// Warp-converged call: one elected lane issues D[tmem] += A[smem] * B[smem].  elect.sync (not `lane == 0`) lets ptxas
+// emit ELECT + a predicated UTCHMMA instead of a per-active-lane serialisation loop around every MMA.
 __device__ __forceinline__ void tc_mma_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
                                            uint32_t idesc) {
-  // D[tmem] += A[smem] * B[smem]; both descriptors share the high word (SBO = 128 B, version 1, no swizzle)
+  // both descriptors share the high word (SBO = 128 B, version 1, no swizzle)
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, q;\n\t"
       ".reg .b64 da, db;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
       "setp.eq.b32 p, 0, 0;\n\t"
       "mov.b64 da, {%1, %3};\n\t"
       "mov.b64 db, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
       "}" ::"r"(d_tmem),
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+// Same elected lane (deterministic for a full mask) commits: arrive on `bar` once all its prior MMAs completed.
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}" ::"r"(bar)
       : "memory");
 }
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
@@ -520,25 +534,23 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
         const int nj = jhi - jlo + 1;
         const int len1 = min(nj, R - static_cast<int>(sb));  // slots before the ring wraps
         const uint32_t a_lo = a_lo0 + st * (Cfg::kStageBytes >> 4);
-        if (lane == 0) {
-          {
-            const uint32_t d = tmem_base + sb * COUT;
-            const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
-            const uint32_t b_lo = b_lo0 + jlo * COUT;
+        {
+          const uint32_t d = tmem_base + sb * COUT;
+          const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
+          const uint32_t b_lo = b_lo0 + jlo * COUT;
 #pragma unroll
-            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-              tc_mma_acc(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
-          }
-          if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
-            const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
-            const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
-#pragma unroll
-            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-              tc_mma_acc(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
-          }
-          tc_commit(bar_empty0 + 8u * st);
-          if (r >= 2) tc_commit(bar_accf0 + 8u * ((G + r - 2) & (R - 1)));
+          for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+            tc_mma_acc(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
         }
+        if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
+          const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
+          const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
+#pragma unroll
+          for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+            tc_mma_acc(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+        }
+        tc_commit_elect(bar_empty0 + 8u * st);
+        if (r >= 2) tc_commit_elect(bar_accf0 + 8u * ((G + r - 2) & (R - 1)));
         __syncwarp();
         if (++st == NST) {
           st = 0;
@@ -1118,6 +1130,8 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
                                 static_cast<cuuint64_t>(N) * p.in_side};
     const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.win_step_in) * 16, static_cast<cuuint64_t>(p.in_side) * 16,
                                 static_cast<cuuint64_t>(CB) * p.in_side * 16};
+    cuuint64_t* gstr_mut = const_cast<cuuint64_t*>(gstr);
+    if (std::getenv("RN_EXP_WIN32")) gstr_mut[0] = 512;  // timing experiment only (wrong results)
     const cuuint32_t box[4] = {256, 4, static_cast<cuuint32_t>(CB), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint8_t*>(p.in), gdim, gstr, box, estr,
