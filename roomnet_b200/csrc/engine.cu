@@ -1,5 +1,6 @@
 #include "engine.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "roomnet.h"
@@ -25,6 +26,7 @@ Replica::Replica(int device, const NetShape& shape, int precision, int max_batch
     : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
   half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
   first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
+  fuse_join_ = std::getenv("RN_NO_FUSED_JOIN") == nullptr;
 }
 
 Replica::~Replica() {
@@ -219,6 +221,12 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
         for (auto& v : b) v /= act_scale_[cs.join_src];
         RN_CUDA(UploadF32(a, &tc_ja_[i]));
         RN_CUDA(UploadF32(b, &tc_jb_[i]));
+        std::vector<double> abc(a);
+        abc.insert(abc.end(), b.begin(), b.end());
+        abc.insert(abc.end(), f.join[i].c.begin(), f.join[i].c.end());
+        RN_CUDA(UploadF32(abc, &tc_abc_[i]));
+        L.join_abc = tc_abc_[i];
+        L.join_src_side = shape_.conv[cs.join_src].out_side;
       }
     }
   }
@@ -316,6 +324,13 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const void* in = shape_.conv[i - 1].join_src >= 0 ? cur_->join_h[i - 1] : cur_->act_h[i - 1];
+    if (cs.join_src >= 0 && fuse_join_) {
+      TcConvLayer L = tc_[i];
+      L.join_src = cur_->act_h[cs.join_src];
+      RN_CUDA(ConvTc(L, in, cur_->join_h[i], n, half_kind_, st));
+      Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
+      continue;
+    }
     RN_CUDA(ConvTc(tc_[i], in, cur_->act_h[i], n, half_kind_, st));
     Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
     if (cs.join_src >= 0) {

@@ -93,6 +93,7 @@ class Replica {
   void* tc0_w_[2] = {nullptr, nullptr};  // conv0 packed weights for uint8 BGR / RGB byte order
   float* tc_ja_[kNumConvs] = {};
   float* tc_jb_[kNumConvs] = {};
+  float* tc_abc_[kNumConvs] = {};  // [3][cout] A/B/C for the join fused into the conv epilogue
   HalfKind half_kind_ = HalfKind::kF16;
 
   // Activations.  Two independent sets, each with its own stream: consecutive micro-batches alternate between
@@ -114,6 +115,7 @@ class Replica {
   ActSet* cur_ = &sets_[0];
   cudaEvent_t ev_fork_ = nullptr;
   int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
+  bool fuse_join_ = true;    // residual joins fused into the conv epilogue (RN_NO_FUSED_JOIN=1 keeps the separate kernel)
 
   // staging
   void* d_in_[2] = {nullptr, nullptr};

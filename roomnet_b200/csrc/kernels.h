@@ -42,6 +42,10 @@ struct TcConvLayer {
   int cout_parts;         // cout is processed in `cout_parts` passes of cout/cout_parts channels
   const float* bias;      // device [cout], already divided by 6 (the kernel clips with saturate)
   int amode = 0;          // 2 = conv0 (uint8 image pre-expanded by PrepU8)
+  // fused residual join in the epilogue (null = plain pooled output): out = A*pool + B*resize(join_src) + C
+  const void* join_src = nullptr;  // chunked tensor of the block's first pooled output
+  int join_src_side = 0;
+  const float* join_abc = nullptr;  // device [3][cout]
 };
 
 // Size in bytes of an activation tensor in chunked layout, incl. over-read slack.

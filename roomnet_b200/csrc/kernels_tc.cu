@@ -157,6 +157,11 @@ struct TcParams {
   int n_rowblocks;
   int n_items;
   int w_bytes;        // packed weight bytes per part
+  // fused residual join (JOIN kernels): out = A*h + B*resize_bilinear_legacy(src)[y][x] + C
+  const uint8_t* res_src;  // chunked tensor [n][y][c/8][x][8], side res_side, same channel count as the output
+  int res_side;
+  float res_scale;         // res_side / out_side (float32, as TF computes it)
+  const float* join_abc;   // device [3][cout]: A, B, C (A, B already divided by the stored-activation scales)
 };
 
 // POOL modes: 0 = none, 31 = 3x3/1, 41 = 4x4/1, 42 = 4x4/2.  The kernel stores the window SUM of
@@ -177,7 +182,7 @@ struct TcCfg {
   static constexpr int kTmemCols = kSlots * COUT;
   static constexpr int kWBytes = kPlanes * 3 * COUT * 16;
   static constexpr int kStageBytes = CB * kPlaneBytesT + (WINDOWS ? 128 : 0);  // + tap over-read of the last plane
-  static constexpr int kFixedBytes = kWBytes + COUT * 4 + 1024;
+  static constexpr int kFixedBytes = kWBytes + 4 * COUT * 4 + 1024;  // bias + join A/B/C
   static constexpr int kStagesFit = (kSmemBudget - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
@@ -238,6 +243,13 @@ struct H2 {
     } else {
       __half2 h = __floats2half2_rn(a, b);
       return *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  __device__ static __forceinline__ float2 unpack(uint32_t v) {
+    if constexpr (BF16) {
+      return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+    } else {
+      return __half22float2(*reinterpret_cast<__half2*>(&v));
     }
   }
   __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
@@ -366,15 +378,17 @@ __device__ __forceinline__ void tc_st(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-constexpr int kThreadsTc = 320;  // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 epilogue (2 channel groups x 4 quadrants)
+// warp 0 TMA producer, warp 1 MMA issuer, then 4 epilogue warps (TMEM lane quadrants) per channel group
+__host__ __device__ constexpr int tc_groups(int creal) { return creal >= 32 ? 4 : 2; }
+__host__ __device__ constexpr int tc_threads(int creal) { return 64 + 128 * tc_groups(creal); }
 
 // ---------------------------------------------------------------------------
 // CB   : input channel chunks (Cin/8)         COUT : output channels of this pass
 // POOL : 0 / 31 / 41 / 42                     SEG  : images side by side in one 128-pixel tile
 // ---------------------------------------------------------------------------
 // CREAL: channels actually produced (<= COUT; conv0 pads 8 -> 16 to satisfy UMMA N % 16 == 0)
-template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT>
-__global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
+__global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
   static_assert(POOL == 0 || SEG == 1, "windowed (pooled) tiles hold one image");
   using HH = H2<BF16>;
@@ -382,7 +396,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
   constexpr int LOGR = Cfg::kLogSlots;
   constexpr int NST = Cfg::kStages;
   constexpr int SEGW = kTileM / SEG;
-  constexpr int NG = 2;                    // epilogue channel groups (4 warps each)
+  constexpr int NG = tc_groups(CREAL);     // epilogue channel groups (4 warps each)
+  constexpr int kThreadsTc = tc_threads(CREAL);
   constexpr int CG = CREAL / NG;           // channels per epilogue group
   constexpr int NP = CG / 2;     // half2 pairs per thread
   // POOL != 0: the 128 lanes are four 32-pixel windows that overlap in the image (each window carries its own
@@ -395,7 +410,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + Cfg::kWBytes;
   float* s_bias = reinterpret_cast<float*>(s_stage + NST * Cfg::kStageBytes);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + COUT);
+  float* s_abc = s_bias + COUT;  // [3][COUT] join coefficients (JOIN kernels)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 4 * COUT);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1 + 2 * R);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -426,6 +442,9 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < COUT; i += kThreadsTc) s_bias[i] = bias_g[i];
+  if (JOIN)
+    for (int i = threadIdx.x; i < 3 * COUT; i += kThreadsTc)
+      s_abc[i] = p.join_abc[(i / COUT) * (COUT * gridDim.y) + part * COUT + (i % COUT)];
   if (POOL != 0) {
     // The 128-byte pad behind the last plane of every stage is never written by the TMA box but is read (with
     // zero weights, Cin = 8 layers) by the tap shift of lane 125: it must hold finite values, so zero it once.
@@ -602,6 +621,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
         col_ok = lcol < p.win_step_out && !(POOL == 42 && (lane & 1)) && col < p.out_side;
       }
       col_ok = col_ok && n_img < p.N;
+      // fused residual join: horizontal taps of this thread's output column (fixed for the item)
+      int jx0 = 0, jx1 = 0;
+      float jtx = 0.f;
+      const uint8_t* jsrc = nullptr;
+      if (JOIN) {
+        const float fx = static_cast<float>(col) * p.res_scale;
+        jx0 = static_cast<int>(floorf(fx));
+        jx1 = min(jx0 + 1, p.res_side - 1);
+        jtx = fx - static_cast<float>(jx0);
+        jsrc = p.res_src + static_cast<size_t>(n_img) * p.res_side * p.cb_out_total * p.res_side * 16 +
+               (static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.res_side * 16;
+      }
       // output row pointer of the row produced by output slot 0 of the current iteration (may start "before" po0)
       uint8_t* optr = p.out + n_img * out_img_bytes +
                       ((static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.out_side + col) * 16 +
@@ -623,6 +654,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
       for (int y = 0; y < it.nconv; y += 2, ++iter) {
         const uint32_t gy = G + y;
         const uint32_t slot0 = gy & (R - 1), slot1 = (gy + 1) & (R - 1);
+        if (JOIN && col_ok) {
+          // the residual taps of this iteration's output rows are known now: pull them into L1 while the
+          // accumulators are still being produced, so the gathers further down hit the cache
+          const int first_row = (POOL == 42 ? (y >> 1) - 1 : y - LAG);
+#pragma unroll
+          for (int k = 0; k < (POOL == 42 ? 1 : 2); ++k) {
+            const int row = min(max(first_row + k, 0), it.npo - 1);
+            const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
+            const int y0 = static_cast<int>(floorf(fy));
+            const int y1 = min(y0 + 1, p.res_side - 1);
+            const size_t src_row_bytes = static_cast<size_t>(p.cb_out_total) * p.res_side * 16;
+#pragma unroll
+            for (int cb = 0; cb < CG / 8; ++cb) {
+              const uint8_t* a0 = jsrc + y0 * src_row_bytes + static_cast<size_t>(cb) * p.res_side * 16 + jx0 * 16;
+              const uint8_t* a1 = jsrc + y1 * src_row_bytes + static_cast<size_t>(cb) * p.res_side * 16 + jx0 * 16;
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(a0));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(a1));
+            }
+          }
+        }
         mbar_wait(bar_accf0 + 8u * slot0, (gy >> LOGR) & 1);
         mbar_wait(bar_accf0 + 8u * slot1, ((gy + 1) >> LOGR) & 1);
         tc_fence_after();
@@ -708,6 +759,51 @@ __global__ void __launch_bounds__(kThreadsTc, 1) conv_tc_kernel(const TcParams p
               const int row = first + k;
               if (row >= 0 && row < it.npo) {
                 uint8_t* orow = optr + static_cast<size_t>(k) * out_row_bytes;
+                if (JOIN) {
+                  // reference network.py:199-203 in folded form; same fp32 arithmetic as join_h_kernel
+                  const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
+                  const int y0 = static_cast<int>(floorf(fy));
+                  const int y1 = min(y0 + 1, p.res_side - 1);
+                  const float ty = fy - static_cast<float>(y0);
+                  const size_t src_row_bytes = static_cast<size_t>(p.cb_out_total) * p.res_side * 16;
+                  const uint8_t* s0 = jsrc + y0 * src_row_bytes;
+                  const uint8_t* s1 = jsrc + y1 * src_row_bytes;
+#pragma unroll
+                  for (int cb = 0; cb < CG / 8; ++cb) {
+                    const size_t po = static_cast<size_t>(cb) * p.res_side * 16;
+                    const uint4 tl = *reinterpret_cast<const uint4*>(s0 + po + jx0 * 16);
+                    const uint4 tr = *reinterpret_cast<const uint4*>(s0 + po + jx1 * 16);
+                    const uint4 bl = *reinterpret_cast<const uint4*>(s1 + po + jx0 * 16);
+                    const uint4 br = *reinterpret_cast<const uint4*>(s1 + po + jx1 * 16);
+                    const uint32_t* ptl = &tl.x;
+                    const uint32_t* ptr = &tr.x;
+                    const uint32_t* pbl = &bl.x;
+                    const uint32_t* pbr = &br.x;
+                    // per-channel coefficients of this 8-channel chunk: 6 vector loads instead of 24 scalar ones
+                    float ca[8], cbv[8], cc[8];
+                    {
+                      const int c0 = grp * CG + 8 * cb;
+                      *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(s_abc + c0);
+                      *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(s_abc + c0 + 4);
+                      *reinterpret_cast<float4*>(cbv) = *reinterpret_cast<const float4*>(s_abc + COUT + c0);
+                      *reinterpret_cast<float4*>(cbv + 4) = *reinterpret_cast<const float4*>(s_abc + COUT + c0 + 4);
+                      *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(s_abc + 2 * COUT + c0);
+                      *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(s_abc + 2 * COUT + c0 + 4);
+                    }
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                      const int i = 4 * cb + e2;  // pair index
+                      const float2 va = HH::unpack(ptl[e2]), vb = HH::unpack(ptr[e2]), vc = HH::unpack(pbl[e2]),
+                                   vd = HH::unpack(pbr[e2]), hv = HH::unpack(hp[k][i]);
+                      const float top0 = va.x + (vb.x - va.x) * jtx, bot0 = vc.x + (vd.x - vc.x) * jtx;
+                      const float top1 = va.y + (vb.y - va.y) * jtx, bot1 = vc.y + (vd.y - vc.y) * jtx;
+                      const float rs0 = top0 + (bot0 - top0) * ty, rs1 = top1 + (bot1 - top1) * ty;
+                      const float j0 = fmaf(ca[2 * e2], hv.x, fmaf(cbv[2 * e2], rs0, cc[2 * e2]));
+                      const float j1 = fmaf(ca[2 * e2 + 1], hv.y, fmaf(cbv[2 * e2 + 1], rs1, cc[2 * e2 + 1]));
+                      hp[k][i] = HH::pack(j0, j1);
+                    }
+                  }
+                }
 #pragma unroll
                 for (int cb = 0; cb < CG / 8; ++cb)
                   *reinterpret_cast<uint4*>(orow + cb * out_plane_bytes) =
@@ -1070,7 +1166,7 @@ using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32
                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT>
+template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
 cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
   using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
   TcParams p{};
@@ -1107,7 +1203,14 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   p.rows_per_item = (p.out_side + nrb - 1) / nrb;
   p.n_rowblocks = (p.out_side + p.rows_per_item - 1) / p.rows_per_item;
   p.n_items = groups * p.n_strips * p.n_rowblocks;
-  auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL>;
+  auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL, JOIN>;
+  if (JOIN) {
+    if (!L.join_src || !L.join_abc) return cudaErrorInvalidValue;
+    p.res_src = static_cast<const uint8_t*>(L.join_src);
+    p.res_side = L.join_src_side;
+    p.res_scale = static_cast<float>(L.join_src_side) / static_cast<float>(L.out_side);
+    p.join_abc = L.join_abc;
+  }
   // per device (replicas of several GPUs share the process), and cheap enough to repeat
   cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return ea;
@@ -1139,14 +1242,14 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
-  kern<<<grid, kThreadsTc, Cfg::kSmemBytes, st>>>(p, tmap);
+  kern<<<grid, tc_threads(CREAL), Cfg::kSmemBytes, st>>>(p, tmap);
   return cudaGetLastError();
 }
 
-template <int CB, int COUT, int POOL, int SEG, int AMODE, int CREAL = COUT>
+template <int CB, int COUT, int POOL, int SEG, int AMODE, int CREAL = COUT, bool JOIN = false>
 cudaError_t launch_tc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
-  return kind == HalfKind::kBF16 ? launch_tc_impl<CB, COUT, POOL, SEG, AMODE, true, CREAL>(L, in, out, N, st)
-                                 : launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL>(L, in, out, N, st);
+  return kind == HalfKind::kBF16 ? launch_tc_impl<CB, COUT, POOL, SEG, AMODE, true, CREAL, JOIN>(L, in, out, N, st)
+                                 : launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL, JOIN>(L, in, out, N, st);
 }
 
 uint16_t to_half_bits(double v, HalfKind kind) {
@@ -1248,9 +1351,13 @@ cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfK
   const int pool = L.pool_k * 10 + L.pool_s;
   if (L.amode == 2) return launch_tc<1, 16, 31, 1, 2, 8>(L, in, out, N, kind, st);
   if (cb == 1 && cp == 32 && pool == 41) return launch_tc<1, 32, 41, 1, 1>(L, in, out, N, kind, st);
-  if (cb == 4 && cp == 32 && pool == 41) return launch_tc<4, 32, 41, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 4 && cp == 32 && pool == 41)
+    return L.join_src ? launch_tc<4, 32, 41, 1, 0, 32, true>(L, in, out, N, kind, st)
+                      : launch_tc<4, 32, 41, 1, 0>(L, in, out, N, kind, st);
   if (cb == 4 && cp == 64 && pool == 42) return launch_tc<4, 64, 42, 1, 0>(L, in, out, N, kind, st);
-  if (cb == 8 && cp == 64 && pool == 42) return launch_tc<8, 64, 42, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 8 && cp == 64 && pool == 42)
+    return L.join_src ? launch_tc<8, 64, 42, 1, 0, 64, true>(L, in, out, N, kind, st)
+                      : launch_tc<8, 64, 42, 1, 0>(L, in, out, N, kind, st);
   if (cb == 8 && cp == 64 && pool == 0)
     return seg2 ? launch_tc<8, 64, 0, 2, 0>(L, in, out, N, kind, st) : launch_tc<8, 64, 0, 1, 0>(L, in, out, N, kind, st);
   if (cb == 16 && cp == 16 && pool == 42) return launch_tc<16, 16, 42, 1, 0>(L, in, out, N, kind, st);
