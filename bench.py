@@ -18,6 +18,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -252,8 +253,15 @@ def main():
             total_ms = sum(p["ms"] for p in prof)
             convs = [p for p in prof if p["name"].startswith("conv") and p["name"].endswith("_tc")] or prof
             top = max(convs, key=lambda p: p["ms"])  # dominant tensor-core kernel
-            layer = int("".join(ch for ch in top["name"] if ch.isdigit()) or 0) if top["name"].startswith("conv") else None
-            if layer is not None:
+            m = re.match(r"conv(\d+)_tc$", top["name"])
+            layer = int(m.group(1)) if m else None
+            if layer is None:  # FP32 path: CUDA-core kernels, no tensor-pipe roofline; report the whole path only
+                roofline = {"bound": "tensor", "kernel": top["name"], "achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
+                            "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": value / world * FLOP_PER_IMAGE_224 / 1e12 / peaks["tflops"], "traffic": None,
+                            "note": "fp32 CUDA-core path: whole-path FLOP rate against the bf16 tensor peak",
+                            "kernels_ms_per_step": {p["name"]: round(p["ms"] / args.steps, 4) for p in prof}}
+            else:
                 flops_per_launch = conv_flops(layer) * B * args.steps / top["launches"]
                 achieved = flops_per_launch / (top["ms"] / top["launches"] * 1e-3) / 1e12
                 traffic = None
