@@ -162,6 +162,7 @@ struct TcParams {
   int res_side;
   float res_scale;         // res_side / out_side (float32, as TF computes it)
   const float* join_abc;   // device [3][cout]: A, B, C (A, B already divided by the stored-activation scales)
+  int dbg;                 // timing experiments only (RN_TC_DBG): 1 = no stores, 2 = no pooling math, 4 = no TMEM re-init
 };
 
 // POOL modes: 0 = none, 31 = 3x3/1, 41 = 4x4/1, 42 = 4x4/2.  The kernel stores the window SUM of
@@ -181,12 +182,13 @@ struct TcCfg {
   static_assert(kSlots == 16 || kSlots == 8, "ring size must be a power of two");
   static constexpr int kTmemCols = kSlots * COUT;
   static constexpr int kWBytes = kPlanes * 3 * COUT * 16;
-  static constexpr int kStageBytes = CB * kPlaneBytesT + (WINDOWS ? 128 : 0);  // + tap over-read of the last plane
+  static constexpr int kRowBytes = CB * kPlaneBytesT;                       // one input row, all planes
+  static constexpr int kStageBytes = 2 * kRowBytes + (WINDOWS ? 128 : 0);  // a stage holds a PAIR of input rows (+ tap over-read pad)
   static constexpr int kFixedBytes = kWBytes + 4 * COUT * 4 + 1024;  // bias + join A/B/C
   static constexpr int kStagesFit = (kSmemBudget - kFixedBytes) / kStageBytes;
   static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
-  static_assert(kStages >= 3, "not enough shared memory for a 3-stage input ring");
+  static_assert(kStages >= 2, "not enough shared memory for a double-buffered input ring");
   // descriptor offsets (in 16-byte units) of k-step ks relative to the stage / weight base
   __host__ __device__ static constexpr uint32_t a_off16(int ks) {
     return AMODE == 0 ? static_cast<uint32_t>((2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * kPlanePxT + ks / (CB / 2 > 0 ? CB / 2 : 1))
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
   // POOL != 0: the 128 lanes are four 32-pixel windows that overlap in the image (each window carries its own
   // pooling halo), so no epilogue warp ever needs a neighbour quadrant's columns.  POOL == 0: one contiguous run.
   constexpr bool kWindows = POOL != 0;
-  constexpr uint32_t kStageTx = kWindows ? CB * 4 * 32 * 16 : CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16);
+  constexpr uint32_t kStageTx = 2 * (kWindows ? CB * 4 * 32 * 16 : CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16));
   constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
 
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -433,12 +435,14 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
   float* s_bias = reinterpret_cast<float*>(s_stage + NST * Cfg::kStageBytes);
   float* s_abc = s_bias + COUT;  // [3][COUT] join coefficients (JOIN kernels)
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 4 * COUT);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1 + 2 * R);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1 + R);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(s_bar);
   const uint32_t bar_full0 = bar0, bar_empty0 = bar0 + 8u * NST, bar_w = bar0 + 8u * (2 * NST);
-  const uint32_t bar_accf0 = bar0 + 8u * (2 * NST + 1), bar_acce0 = bar_accf0 + 8u * R;
+  // accumulator barriers work on PAIRS of conv rows (the epilogue consumes two rows per iteration)
+  constexpr int RP = R / 2;
+  const uint32_t bar_accf0 = bar0 + 8u * (2 * NST + 1), bar_acce0 = bar_accf0 + 8u * RP;
 
   const int part = blockIdx.y;
   const uint8_t* w_gmem = p.w + static_cast<size_t>(part) * p.w_bytes;
@@ -450,7 +454,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       mbar_init(bar_empty0 + 8u * s, 1);
     }
     mbar_init(bar_w, 1);
-    for (int s = 0; s < R; ++s) {
+    for (int s = 0; s < RP; ++s) {
       mbar_init(bar_accf0 + 8u * s, 1);
       mbar_init(bar_acce0 + 8u * s, 4 * NG);
     }
@@ -470,7 +474,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     // The 128-byte pad behind the last plane of every stage is never written by the TMA box but is read (with
     // zero weights, Cin = 8 layers) by the tap shift of lane 125: it must hold finite values, so zero it once.
     for (int i = threadIdx.x; i < NST * 32; i += kThreadsTc)
-      reinterpret_cast<uint32_t*>(s_stage + (i / 32) * Cfg::kStageBytes + CB * Cfg::kPlaneBytesT)[i % 32] = 0u;
+      reinterpret_cast<uint32_t*>(s_stage + (i / 32) * Cfg::kStageBytes + 2 * Cfg::kRowBytes)[i % 32] = 0u;
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
@@ -501,9 +505,9 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       if (lane == 0) {
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const Item it = decode_item<POOL, SEG>(p, item);
-          const int nin = it.nconv + 2;
+          const int nin = it.nconv + 2;  // even
           int row = it.n0 * p.in_side + it.c0;
-          for (int r = 0; r < nin; ++r, ++row) {
+          for (int r = 0; r < nin; r += 2, row += 2) {
             mbar_wait(bar_empty0 + 8u * st, ph);
             const uint32_t full = bar_full0 + 8u * st;
             mbar_arrive_expect_tx(full, kStageTx);
@@ -516,7 +520,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         }
       }
     } else {
-      constexpr int kCopies = SEG * CB;
+      constexpr int kCopies = 2 * SEG * CB;  // two input rows per stage
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const Item it = decode_item<POOL, SEG>(p, item);
         const int nin = it.nconv + 2;
@@ -528,11 +532,11 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 #pragma unroll
         for (int k = 0; k < (kCopies + 31) / 32; ++k) {
           const int idx = min(lane + 32 * k, kCopies - 1);
-          const int c = idx / SEG, sg = idx % SEG;
-          lsrc[k] = (sg ? src1 : src0) + static_cast<size_t>(c) * p.in_side * 16;
-          ldst[k] = c * Cfg::kPlaneBytesT + sg * SEGW * 16;
+          const int rr = idx / (SEG * CB), c = (idx / SEG) % CB, sg = idx % SEG;
+          lsrc[k] = (sg ? src1 : src0) + rr * in_row_bytes + static_cast<size_t>(c) * p.in_side * 16;
+          ldst[k] = rr * Cfg::kRowBytes + c * Cfg::kPlaneBytesT + sg * SEGW * 16;
         }
-        for (int r = 0; r < nin; ++r) {
+        for (int r = 0; r < nin; r += 2) {
           mbar_wait(bar_empty0 + 8u * st, ph);
           const uint32_t full = bar_full0 + 8u * st;
           if (lane == 0) mbar_arrive_expect_tx(full, kStageTx);
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 #pragma unroll
           for (int k = 0; k < (kCopies + 31) / 32; ++k) {
             if (lane + 32 * k < kCopies) tma_bulk_g2s(dst + ldst[k], lsrc[k], SEG == 1 ? kLoadPx * 16 : SEGW * 16, full);
-            lsrc[k] += in_row_bytes;
+            lsrc[k] += 2 * in_row_bytes;
           }
           if (++st == NST) {
             st = 0;
@@ -561,36 +565,41 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const Item it = decode_item<POOL, SEG>(p, item);
       const int nin = it.nconv + 2;
-      for (int r = 0; r < nin; ++r) {
-        if (r < it.nconv) {  // accumulator of conv row r must have been drained and re-initialised with the bias
-          const uint32_t gy = G + r;
-          mbar_wait(bar_acce0 + 8u * (gy & (R - 1)), (gy >> LOGR) & 1);
+      for (int r0 = 0; r0 < nin; r0 += 2) {
+        if (r0 < it.nconv) {  // accumulators of conv rows r0, r0+1 must have been drained and re-initialised
+          const uint32_t gy = G + r0;
+          mbar_wait(bar_acce0 + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
         }
         mbar_wait(bar_full0 + 8u * st, ph);
         tc_fence_after();
-        const int jlo = max(0, 2 - r);  // j = 2 - dy ; conv row y = r - 2 + j
-        const int jhi = min(2, it.nconv + 1 - r);
-        const uint32_t sb = (G + r - 2 + jlo) & (R - 1);
-        const int nj = jhi - jlo + 1;
-        const int len1 = min(nj, R - static_cast<int>(sb));  // slots before the ring wraps
-        const uint32_t a_lo = a_lo0 + st * (Cfg::kStageBytes >> 4);
-        {
-          const uint32_t d = tmem_base + sb * COUT;
-          const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
-          const uint32_t b_lo = b_lo0 + jlo * COUT;
 #pragma unroll
-          for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-            tc_mma_acc(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
-        }
-        if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
-          const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
-          const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
+        for (int sub = 0; sub < 2; ++sub) {
+          const int r = r0 + sub;
+          const int jlo = max(0, 2 - r);  // j = 2 - dy ; conv row y = r - 2 + j
+          const int jhi = min(2, it.nconv + 1 - r);
+          const uint32_t sb = (G + r - 2 + jlo) & (R - 1);
+          const int nj = jhi - jlo + 1;
+          const int len1 = min(nj, R - static_cast<int>(sb));  // slots before the ring wraps
+          const uint32_t a_lo = a_lo0 + st * (Cfg::kStageBytes >> 4) + sub * (Cfg::kRowBytes >> 4);
+          {
+            const uint32_t d = tmem_base + sb * COUT;
+            const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
+            const uint32_t b_lo = b_lo0 + jlo * COUT;
 #pragma unroll
-          for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-            tc_mma_acc(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+              tc_mma_acc(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+          }
+          if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
+            const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
+            const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+              tc_mma_acc(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+          }
         }
         tc_commit_elect(bar_empty0 + 8u * st);
-        if (r >= 2) tc_commit_elect(bar_accf0 + 8u * ((G + r - 2) & (R - 1)));
+        // conv rows r0-2, r0-1 received their last (dy = 2) contribution from this pair of input rows
+        if (r0 >= 2) tc_commit_elect(bar_accf0 + 8u * (((G + r0 - 2) >> 1) & (RP - 1)));
         __syncwarp();
         if (++st == NST) {
           st = 0;
@@ -622,7 +631,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     tc_fence_before();
     __syncwarp();
     if (lane == 0)
-      for (int s = 0; s < R; ++s) mbar_arrive(bar_acce0 + 8u * s);
+      for (int s = 0; s < RP; ++s) mbar_arrive(bar_acce0 + 8u * s);
 
     uint32_t G = 0, iter = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -695,23 +704,29 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             }
           }
         }
-        mbar_wait(bar_accf0 + 8u * slot0, (gy >> LOGR) & 1);
-        mbar_wait(bar_accf0 + 8u * slot1, ((gy + 1) >> LOGR) & 1);
+        const uint32_t pair = (gy >> 1) & (RP - 1);
+        mbar_wait(bar_accf0 + 8u * pair, (gy >> LOGR) & 1);
         tc_fence_after();
+        if (p.dbg & 8) {  // timing experiment: hand the slots straight back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acce0 + 8u * pair);
+          optr += (POOL == 42 ? 1 : 2) * out_row_bytes;
+          continue;
+        }
         float a[CG], b[CG];
         tc_ld<CG>(t_base + slot0 * COUT, a);
         tc_ld<CG>(t_base + slot1 * COUT, b);
         tc_wait_ld();
         // hand the slots back, pre-loaded with the bias
-        tc_st<CG>(t_base + slot0 * COUT, bias_r);
-        tc_st<CG>(t_base + slot1 * COUT, bias_r);
-        tc_wait_st();
+        if (!(p.dbg & 4)) {
+          tc_st<CG>(t_base + slot0 * COUT, bias_r);
+          tc_st<CG>(t_base + slot1 * COUT, bias_r);
+          tc_wait_st();
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(bar_acce0 + 8u * slot0);
-          mbar_arrive(bar_acce0 + 8u * slot1);
-        }
+        if (lane == 0) mbar_arrive(bar_acce0 + 8u * pair);
 
         // ---- saturate (= ReLU6/6) + vertical window -> packed 16-bit pairs vp[k][i] for output slot k
         // output slot 0 is pooled row (y - LAG) [41/31] or (y - 2)/2 [42] or conv row y [0]; slot 1 the next one
@@ -758,7 +773,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
             const uint32_t v = vp[k][i];
-            if (POOL == 0) {
+            if (POOL == 0 || (p.dbg & 2)) {
               hp[k][i] = v;
             } else if (POOL == 42) {
               const uint32_t u = HH::add(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -774,7 +789,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
           if (POOL == 0) first = y;
           else if (POOL == 42) first = (y >> 1) - 1;
           else first = y - LAG;
-          if (col_ok) {
+          if (col_ok && !(p.dbg & 1)) {
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
               const int row = first + k;
@@ -1257,13 +1272,14 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
                                 static_cast<cuuint64_t>(CB) * p.in_side * 16};
     cuuint64_t* gstr_mut = const_cast<cuuint64_t*>(gstr);
     if (std::getenv("RN_EXP_WIN32")) gstr_mut[0] = 512;  // timing experiment only (wrong results)
-    const cuuint32_t box[4] = {256, 4, static_cast<cuuint32_t>(CB), 1};
+    const cuuint32_t box[4] = {256, 4, static_cast<cuuint32_t>(CB), 2};  // a pair of input rows per TMA
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, const_cast<uint8_t*>(p.in), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
   }
+  if (const char* d = std::getenv("RN_TC_DBG")) p.dbg = std::atoi(d);
   kern<<<grid, tc_threads(CREAL), Cfg::kSmemBytes, st>>>(p, tmap);
   return cudaGetLastError();
 }
