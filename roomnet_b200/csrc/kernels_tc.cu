@@ -497,6 +497,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       }
     }
     uint32_t st = 0, ph = 1;  // waiting parity 1 on a fresh "empty" barrier passes immediately
+    uint32_t Gp = 0;          // global conv-row counter (same sequence as the MMA issuer's G)
     const uint32_t stage0 = smem_u32(s_stage);
     if constexpr (kWindows) {
       // one tiled TMA box per input row: [CB planes][4 windows][32 pixels][8 channels]; the window dimension has
@@ -508,6 +509,10 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
           const int nin = it.nconv + 2;  // even
           int row = it.n0 * p.in_side + it.c0;
           for (int r = 0; r < nin; r += 2, row += 2) {
+            if (r < it.nconv) {  // see the MMA issuer: the accumulators this input pair starts must be free
+              const uint32_t gy = Gp + r;
+              mbar_wait(bar_acce0 + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
+            }
             mbar_wait(bar_empty0 + 8u * st, ph);
             const uint32_t full = bar_full0 + 8u * st;
             mbar_arrive_expect_tx(full, kStageTx);
@@ -517,6 +522,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
               ph ^= 1;
             }
           }
+          Gp += it.nconv;
         }
       }
     } else {
@@ -537,6 +543,10 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
           ldst[k] = rr * Cfg::kRowBytes + c * Cfg::kPlaneBytesT + sg * SEGW * 16;
         }
         for (int r = 0; r < nin; r += 2) {
+          if (r < it.nconv) {
+            const uint32_t gy = Gp + r;
+            mbar_wait(bar_acce0 + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
+          }
           mbar_wait(bar_empty0 + 8u * st, ph);
           const uint32_t full = bar_full0 + 8u * st;
           if (lane == 0) mbar_arrive_expect_tx(full, kStageTx);
@@ -552,6 +562,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             ph ^= 1;
           }
         }
+        Gp += it.nconv;
       }
     }
   } else if (warp == 1) {
@@ -566,10 +577,9 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       const Item it = decode_item<POOL, SEG>(p, item);
       const int nin = it.nconv + 2;
       for (int r0 = 0; r0 < nin; r0 += 2) {
-        if (r0 < it.nconv) {  // accumulators of conv rows r0, r0+1 must have been drained and re-initialised
-          const uint32_t gy = G + r0;
-          mbar_wait(bar_acce0 + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
-        }
+        // The accumulators of conv rows r0, r0+1 (started by this pair) are free: the producer waited for their
+        // "drained + bias re-initialised" barrier BEFORE issuing the TMA that completes full[st] (one wait less on
+        // this warp's critical path; mbarrier arrive/wait are release/acquire, so the ordering is transitive).
         mbar_wait(bar_full0 + 8u * st, ph);
         tc_fence_after();
 #pragma unroll
