@@ -275,6 +275,14 @@ def main():
                             "whole_path": {"achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
                                            "frac": value / world * FLOP_PER_IMAGE_224 / 1e12 / peaks["tflops"]},
                             "kernels_ms_per_step": {p["name"]: round(p["ms"] / args.steps, 4) for p in prof}}
+                # every tensor-core layer kernel against the same peak (algorithmic conv FLOPs only)
+                per_kernel = {}
+                for q in prof:
+                    mq = re.match(r"conv(\d+)_tc$", q["name"])
+                    if mq:
+                        tf = conv_flops(int(mq.group(1))) * B * args.steps / (q["ms"] * 1e-3) / 1e12
+                        per_kernel[q["name"]] = {"tflops": round(tf, 1), "frac": round(tf / peaks["tflops"], 4)}
+                roofline["per_kernel"] = per_kernel
         cpu = None
         if not args.no_cpu_baseline:
             ips, cores, p50 = cpu_reference_throughput(64)

@@ -41,7 +41,7 @@ if os.path.exists(lpath):
     total = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, tag + "_launches_summary.md"), "w") as f:
         f.write("# %s — ncu launch list of `python bench.py --steps 3 --warmup 3` (batch 256, fp16 path)\n\n" % tag)
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 96 -c 400`; times are cold-cache and\n"
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 80 -c 300`; times are cold-cache and\n"
                 "serialised (compare SHARES with bench.py's `kernels_ms_per_step`, not absolutes).\n\n")
         f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
         for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -97,15 +97,13 @@ if os.path.exists(rep):
                 f.write("* %s: %s %s\n" % (name, v, u))
             f.write("\n")
     # map to the engine's kernel names used by bench.py
-    layer_of = {"conv_tc_kernel<1,16,31,1,2,0,8>": "conv0_tc", "conv_tc_kernel<1,32,41,1,1,0,32>": "conv1_tc",
-                "conv_tc_kernel<4,64,42,1,0,0,64>": "conv4_tc", "conv_tc_kernel<8,64,42,1,0,0,64>": "conv5_tc",
-                "conv_tc_kernel<8,64,0,2,0,0,64>": "conv6_tc", "conv_tc_kernel<16,16,42,1,0,0,16>": "conv7_tc",
-                "conv_tc_kernel<4,32,41,1,0,0,32>": "conv2_tc"}
+    layer_of = {"conv_tc_kernel<1,16,31,1,2,0,8,0>": "conv0_tc", "conv_tc_kernel<1,32,41,1,1,0,32,0>": "conv1_tc",
+                "conv_tc_kernel<4,32,41,1,0,0,32,0>": "conv2_tc", "conv_tc_kernel<4,32,41,1,0,0,32,1>": "conv3_tc",
+                "conv_tc_kernel<4,64,42,1,0,0,64,0>": "conv4_tc", "conv_tc_kernel<8,64,42,1,0,0,64,1>": "conv5_tc",
+                "conv_tc_kernel<8,64,0,2,0,0,64,0>": "conv6_tc", "conv_tc_kernel<16,16,42,1,0,0,16,0>": "conv7_tc"}
     tj = {}
     for k, b in traffic.items():
         name = layer_of.get(k, k)
         tj[name] = {"dram_bytes_per_launch_b128": b, "ncu_kernel": k}
-    if "conv2_tc" in tj:
-        tj["conv3_tc"] = dict(tj["conv2_tc"])
     json.dump(tj, open(os.path.join(out_dir, "ncu_traffic.json"), "w"), indent=1)
     print("wrote full summary,", len(lines), "kernels")
