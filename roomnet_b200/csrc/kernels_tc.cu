@@ -817,10 +817,13 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 #pragma unroll
                   for (int cb = 0; cb < CG / 8; ++cb) {
                     const size_t po = static_cast<size_t>(cb) * p.res_side * 16;
-                    const uint4 tl = *reinterpret_cast<const uint4*>(s0 + po + jx0 * 16);
-                    const uint4 tr = *reinterpret_cast<const uint4*>(s0 + po + jx1 * 16);
-                    const uint4 bl = *reinterpret_cast<const uint4*>(s1 + po + jx0 * 16);
-                    const uint4 br = *reinterpret_cast<const uint4*>(s1 + po + jx1 * 16);
+                    uint4 tl = make_uint4(0, 0, 0, 0), tr = tl, bl = tl, br = tl;
+                    if (!(p.dbg & 32)) {  // (dbg 32: timing experiment without the residual gather)
+                      tl = *reinterpret_cast<const uint4*>(s0 + po + jx0 * 16);
+                      tr = *reinterpret_cast<const uint4*>(s0 + po + jx1 * 16);
+                      bl = *reinterpret_cast<const uint4*>(s1 + po + jx0 * 16);
+                      br = *reinterpret_cast<const uint4*>(s1 + po + jx1 * 16);
+                    }
                     const uint32_t* ptl = &tl.x;
                     const uint32_t* ptr = &tr.x;
                     const uint32_t* pbl = &bl.x;
