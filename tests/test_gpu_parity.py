@@ -3,10 +3,13 @@
 Budgets (BASELINE.json north_star): identical top-1 on every image; max |dlogit| <= 1e-3 on the
 FP32 path and <= 2e-2 on the 16-bit tensor-core path, logit = post-ReLU6 out_op (network.py:43).
 """
+import os
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+ROOT_DIR = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 TOL = {"fp32": 1e-3, "fp16": 2e-2}
 
@@ -145,3 +148,40 @@ def test_drop_in_roomnet_class(ckpt_prefix, suite64, golden):
     nn2.load(ckpt_prefix)
     out = nn2.infer(suite64[:16])  # non-optimized graph returns argmax only (network.py:72)
     assert isinstance(out, np.ndarray) and np.array_equal(out, golden["argmax"][:16])
+
+
+def test_bf16_operand_mode_runs_but_is_not_the_parity_path(capi, ckpt_prefix, suite64, golden):
+    """RN_PREC_BF16 = same kernels, bf16 operands.  It keeps top-1 on this suite but misses the 2e-2 logit budget
+    (flat-colour images, ~0.1) — which is why the benchmarked 16-bit path uses fp16 operands."""
+    h = _handle(capi, ckpt_prefix, "bf16")
+    top1, probs, logits = h.infer_u8_bgr(suite64, want_logits=True)
+    err = np.abs(logits - golden["logits"]).max()
+    print("bf16: max|dlogit| vs golden = %.3e, top-1 agreement %.3f" % (err, (top1 == golden["argmax"]).mean()))
+    assert (top1 == golden["argmax"]).mean() >= 0.95
+    assert err <= 0.3
+    np.testing.assert_allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_fused_join_matches_separate_join_kernel(ckpt_prefix, suite64):
+    """The residual join fused into the conv3/conv5 epilogue vs the stand-alone join kernel (RN_NO_FUSED_JOIN=1)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from roomnet_b200 import _capi\n"
+        "from oracle.roomnet_oracle import synthetic_suite\n"
+        "h = _capi.Handle(precision='fp16'); h.load_tf_checkpoint(%r)\n"
+        "t, p, l = h.infer_u8_bgr(synthetic_suite(16), want_logits=True)\n"
+        "np.save(sys.argv[1], l)\n" % (ROOT_DIR, ckpt_prefix))
+    outs = []
+    for env_extra in ({}, {"RN_NO_FUSED_JOIN": "1"}):
+        import os
+        import tempfile
+        path = os.path.join(tempfile.mkdtemp(), "l.npy")
+        env = dict(os.environ, **env_extra)
+        subprocess.check_call([sys.executable, "-c", code, path], env=env)
+        outs.append(np.load(path))
+    diff = np.abs(outs[0] - outs[1]).max()
+    print("fused vs separate join: max|dlogit| = %.3e" % diff)
+    assert diff <= 3e-3
