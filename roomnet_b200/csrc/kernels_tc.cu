@@ -1063,7 +1063,7 @@ __device__ __forceinline__ void tail_conv_pool(const float* __restrict__ in, int
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) tail_fused_kernel(const uint16_t* __restrict__ p7, TailParams tp, int bf16,
+__global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __restrict__ p7, TailParams tp, int bf16,
                                                          long long* __restrict__ top1, float* __restrict__ probs,
                                                          float* __restrict__ logits, float* __restrict__ dbg8,
                                                          float* __restrict__ dbg9) {
@@ -1449,7 +1449,8 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
   cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(bytes));
   if (e != cudaSuccess) return e;
-  tail_fused_kernel<<<N, 256, bytes, st>>>(static_cast<const uint16_t*>(p7), tp, kind == HalfKind::kBF16, top1, probs,
+  // small batches: one image per CTA is latency-critical -> 1024 threads; large batches: 256 threads, more CTAs per SM
+  tail_fused_kernel<<<N, N <= 32 ? 1024 : 256, bytes, st>>>(static_cast<const uint16_t*>(p7), tp, kind == HalfKind::kBF16, top1, probs,
                                            logits, dbg8, dbg9);
   return cudaGetLastError();
 }
