@@ -106,8 +106,18 @@ int rn_infer_u8_rgb(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1,
 int rn_infer_u8_bgr_device(rn_handle* h, const void* d_nhwc, int32_t n, void* d_top1, void* d_probs,
                            void* d_logits, void* cuda_stream);
 
-/* RoomNet.center_crop + cv2.resize                      network.py:137-146, :149-152
- * Host-side geometry helper: writes the crop rectangle the reference would take. */
+/* RoomNet.center_crop + cv2.resize(im, (S, S))          network.py:137-146, :149-152
+ * One BGR/RGB uint8 image [H, W, 3] of any size -> [S, S, 3] on the device: centre crop (with the reference's
+ * floor-division offset) + OpenCV's INTER_LINEAR uint8 fixed-point bilinear (11-bit coefficients; exact 2x shrink
+ * = 2x2 box), bit-identical to cv2.resize.  `out` receives S*S*3 bytes. */
+int rn_preprocess_u8(rn_handle* h, const uint8_t* img, int32_t H, int32_t W, uint8_t* out);
+
+/* RoomNet.infer_optimized(im_in)                        network.py:148-156
+ * The whole per-image call of infer.py:81-82 on the device: rn_preprocess_u8 + rn_infer_u8_bgr for one image. */
+int rn_infer_image_u8_bgr(rn_handle* h, const uint8_t* img, int32_t H, int32_t W, int64_t* top1, float* probs,
+                          float* logits);
+
+/* Host-side geometry helper: writes the crop rectangle the reference would take (network.py:137-146). */
 int rn_center_crop_rect(int32_t h, int32_t w, int32_t* y0, int32_t* x0, int32_t* side);
 
 /* Introspection used by the parity tests (no reference analogue). */

@@ -56,6 +56,8 @@ def _load():
         "rn_infer_u8_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_f32_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_u8_bgr_device": ([vp, vp, i32, vp, vp, vp, vp], C.c_int),
+        "rn_preprocess_u8": ([vp, vp, i32, i32, vp], C.c_int),
+        "rn_infer_image_u8_bgr": ([vp, vp, i32, i32, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
         "rn_flat_len": ([vp], C.c_int),
         "rn_num_kernel_launches": ([vp], C.c_int),
@@ -78,7 +80,7 @@ def _load():
 lib = _load()
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_u8_bgr_device",
-            "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
 
@@ -155,6 +157,26 @@ class Handle:
 
     def infer_f32_rgb(self, x, want_logits=False):
         return self._infer(lib.rn_infer_f32_rgb, x, np.float32, want_logits)
+
+    def preprocess_u8(self, img):
+        """center_crop + cv2.resize(img, (S, S)) on the device (bit-identical to cv2 for uint8)."""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise RoomNetError(RN_ERR_INVALID_ARG, "image must be [H, W, 3] uint8, got %s" % (img.shape,))
+        out = np.empty((self.im_side, self.im_side, 3), np.uint8)
+        self._check(lib.rn_preprocess_u8(self._h, img.ctypes.data, img.shape[0], img.shape[1], out.ctypes.data))
+        return out
+
+    def infer_image_u8_bgr(self, img, want_logits=False):
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        if img.ndim != 3 or img.shape[2] != 3:
+            raise RoomNetError(RN_ERR_INVALID_ARG, "image must be [H, W, 3] uint8, got %s" % (img.shape,))
+        top1 = np.empty((1,), np.int64)
+        probs = np.empty((1, self.num_classes), np.float32)
+        logits = np.empty((1, self.num_classes), np.float32)
+        self._check(lib.rn_infer_image_u8_bgr(self._h, img.ctypes.data, img.shape[0], img.shape[1], top1.ctypes.data,
+                                              probs.ctypes.data, logits.ctypes.data))
+        return (top1, probs, logits) if want_logits else (top1, probs)
 
     def infer_raw(self, fn_name, in_ptr, n, top1_ptr, probs_ptr, logits_ptr):
         """Pointer-level call (pinned host buffers owned by the caller)."""

@@ -229,6 +229,33 @@ int rn_infer_u8_bgr_device(rn_handle* h, const void* d_nhwc, int32_t n, void* d_
   return RN_OK;
 }
 
+int rn_preprocess_u8(rn_handle* h, const uint8_t* img, int32_t hgt, int32_t wid, uint8_t* out) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!img || !out || hgt < 2 || wid < 2) return Fail(h, RN_ERR_INVALID_ARG, "null image or degenerate size");
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU path");
+  if (h->replicas[0]->Preprocess(img, hgt, wid, out) != cudaSuccess) return Fail(h, RN_ERR_CUDA, h->replicas[0]->error());
+  return RN_OK;
+}
+
+int rn_infer_image_u8_bgr(rn_handle* h, const uint8_t* img, int32_t hgt, int32_t wid, int64_t* top1, float* probs,
+                          float* logits) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!img || hgt < 2 || wid < 2) return Fail(h, RN_ERR_INVALID_ARG, "null image or degenerate size");
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+  if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+  auto t0 = std::chrono::steady_clock::now();
+  rn::Replica* r = h->replicas[0].get();
+  if (r->InferImage(img, hgt, wid, top1, probs, logits) != cudaSuccess) return Fail(h, RN_ERR_CUDA, r->error());
+  h->last_launches = r->last_launches();
+  double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (h->lat_ms.size() < (1u << 20)) h->lat_ms.push_back(ms);
+  h->calls += 1;
+  h->images += 1;
+  return RN_OK;
+}
+
 int rn_center_crop_rect(int32_t hgt, int32_t wid, int32_t* y0, int32_t* x0, int32_t* side) {
   if (hgt <= 0 || wid <= 0 || !y0 || !x0 || !side) return RN_ERR_INVALID_ARG;
   // reference network.py:139: offset = abs((w - h) // 2) with Python floor division

@@ -1,5 +1,6 @@
 #include "engine.h"
 
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -33,6 +34,7 @@ Replica::~Replica() {
   cudaSetDevice(device_);
   cudaDeviceSynchronize();
   for (void* p : allocs_) cudaFree(p);
+  if (d_raw_) cudaFree(d_raw_);
   for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i) {
     if (h_in_[i]) cudaFreeHost(h_in_[i]);
@@ -478,6 +480,94 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
     if (e != cudaSuccess) return e;
   }
   RN_CUDA(cudaGetLastError());
+  return cudaSuccess;
+}
+
+namespace {
+// One axis of OpenCV's INTER_LINEAR tap table for uint8 (resize.cpp): index pair + 11-bit weights.
+void ResizeTaps(int dst, int src, bool vertical, int* s0, int* s1, int* w0, int* w1) {
+  const double scale = static_cast<double>(src) / static_cast<double>(dst);
+  for (int d = 0; d < dst; ++d) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    int s = static_cast<int>(std::floor(f));
+    f -= static_cast<float>(s);
+    int a, b;
+    if (vertical) {  // rows: the fraction is kept, only the two row indices are clipped
+      a = std::min(std::max(s, 0), src - 1);
+      b = std::min(std::max(s + 1, 0), src - 1);
+    } else {         // columns: out-of-range taps fold by clamping the fraction
+      if (s < 0) {
+        f = 0.f;
+        s = 0;
+      }
+      if (s >= src - 1) {
+        f = 0.f;
+        s = src - 1;
+      }
+      a = s;
+      b = std::min(s + 1, src - 1);
+    }
+    s0[d] = a;
+    s1[d] = b;
+    w1[d] = static_cast<int>(std::nearbyint(f * 2048.0f));
+    w0[d] = static_cast<int>(std::nearbyint((1.0f - f) * 2048.0f));
+  }
+}
+}  // namespace
+
+cudaError_t Replica::Preprocess(const uint8_t* h_img, int H, int W, uint8_t* h_out) {
+  RN_CUDA(cudaSetDevice(device_));
+  const int S = shape_.im_side;
+  // reference network.py:139: offset = abs((w - h) // 2) with Python floor division
+  const int d = W - H;
+  const int fl = d >= 0 ? d / 2 : -((-d + 1) / 2);
+  const int off = fl < 0 ? -fl : fl;
+  const int side = std::min(H, W), cy = H > W ? off : 0, cx = W > H ? off : 0;
+  const size_t raw_bytes = static_cast<size_t>(H) * W * 3;
+  if (raw_bytes > d_raw_cap_) {
+    if (d_raw_) cudaFree(d_raw_);
+    d_raw_ = nullptr;
+    d_raw_cap_ = 0;
+    RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_raw_), raw_bytes));
+    d_raw_cap_ = raw_bytes;
+  }
+  if (!d_taps_) RN_CUDA(Alloc(reinterpret_cast<void**>(&d_taps_), static_cast<size_t>(8) * S * sizeof(int)));
+  RN_CUDA(cudaMemcpyAsync(d_raw_, h_img, raw_bytes, cudaMemcpyHostToDevice, compute_));
+  uint8_t* dst = static_cast<uint8_t*>(d_in_[0]);
+  if (side == S) {  // already the right size: plain crop copy (network.py:151 skips the resize)
+    RN_CUDA(cudaMemcpy2DAsync(dst, static_cast<size_t>(S) * 3, d_raw_ + (static_cast<size_t>(cy) * W + cx) * 3,
+                              static_cast<size_t>(W) * 3, static_cast<size_t>(S) * 3, S, cudaMemcpyDeviceToDevice,
+                              compute_));
+  } else {
+    std::vector<int> taps(static_cast<size_t>(8) * S);
+    ResizeTaps(S, side, false, &taps[0], &taps[S], &taps[2 * S], &taps[3 * S]);
+    ResizeTaps(S, side, true, &taps[4 * S], &taps[5 * S], &taps[6 * S], &taps[7 * S]);
+    RN_CUDA(cudaMemcpyAsync(d_taps_, taps.data(), taps.size() * sizeof(int), cudaMemcpyHostToDevice, compute_));
+    RN_CUDA(cudaStreamSynchronize(compute_));  // `taps` is a pageable temporary
+    RN_CUDA(CropResizeU8(d_raw_, W, cy, cx, dst, S, d_taps_, side == 2 * S ? 1 : 0, compute_));
+  }
+  if (h_out) RN_CUDA(cudaMemcpyAsync(h_out, dst, static_cast<size_t>(S) * S * 3, cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaStreamSynchronize(compute_));
+  return cudaSuccess;
+}
+
+cudaError_t Replica::InferImage(const uint8_t* h_img, int H, int W, int64_t* top1, float* probs, float* logits) {
+  cudaError_t e = Preprocess(h_img, H, W, nullptr);
+  if (e != cudaSuccess) return e;
+  last_launches_ = 1;
+  cur_ = &sets_[0];
+  const int C = shape_.num_classes;
+  e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, 1, d_top1_[0], d_probs_[0], d_logits_[0], compute_);
+  if (e != cudaSuccess) return e;
+  long long t1 = 0;
+  std::vector<float> buf(2 * C);
+  RN_CUDA(cudaMemcpyAsync(&t1, d_top1_[0], sizeof(long long), cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaMemcpyAsync(buf.data(), d_probs_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaMemcpyAsync(buf.data() + C, d_logits_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaStreamSynchronize(compute_));
+  if (top1) *top1 = t1;
+  if (probs) std::memcpy(probs, buf.data(), C * sizeof(float));
+  if (logits) std::memcpy(logits, buf.data() + C, C * sizeof(float));
   return cudaSuccess;
 }
 

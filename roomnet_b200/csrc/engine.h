@@ -37,6 +37,11 @@ class Replica {
   cudaError_t InferDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
                           float* d_logits, cudaStream_t st);
 
+  // center_crop + cv2.resize(im, (S, S)) of one HxWx3 uint8 image on the device (reference network.py:149-152).
+  // Writes S*S*3 bytes to h_out (host, may be null) and leaves the result in the replica's input slot 0.
+  cudaError_t Preprocess(const uint8_t* h_img, int H, int W, uint8_t* h_out);
+  // infer_optimized for one arbitrary-size BGR image entirely on the device (Preprocess + forward).
+  cudaError_t InferImage(const uint8_t* h_img, int H, int W, int64_t* top1, float* probs, float* logits);
   int last_launches() const { return last_launches_; }
   // Per-kernel device timing (CUDA events on the launching stream, recorded between launches).
   void set_profiling(bool on) { profiling_ = on; }
@@ -117,6 +122,10 @@ class Replica {
   int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
   bool fuse_join_ = true;    // residual joins fused into the conv epilogue (RN_NO_FUSED_JOIN=1 keeps the separate kernel)
 
+  // preprocessing scratch (raw image + tap tables), grown on demand
+  uint8_t* d_raw_ = nullptr;
+  size_t d_raw_cap_ = 0;
+  int* d_taps_ = nullptr;
   // staging
   void* d_in_[2] = {nullptr, nullptr};
   void* h_in_[2] = {nullptr, nullptr};

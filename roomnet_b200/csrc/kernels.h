@@ -25,6 +25,10 @@ cudaError_t JoinF32(const float* p, const float* src, float* out, const float* A
 cudaError_t DenseTailF32(const float* flat, int N, int flat_len, const DenseParams& dp, long long* top1, float* probs,
                          float* logits, float* pre_relu6, cudaStream_t st);
 
+// Centre crop + cv2.resize-compatible (INTER_LINEAR, uint8 fixed point) bilinear resize; `taps` = 8*S int32 on the device.
+cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst, int S, const int* taps, int area2x,
+                         cudaStream_t st);
+
 // ---- 16-bit tensor-core path (kernels_tc.cu) --------------------------------
 // Activation layout between tensor-core layers ("chunked rows"):
 //   T[n][y][cb][x][8]  16-bit elements, cb = channel / 8.  One (n, y, cb) plane row

@@ -196,6 +196,36 @@ __global__ void dense_tail_kernel(const float* __restrict__ flat, int N, int fla
   if (lane == 0 && top1) top1[warp] = bi;
 }
 
+// Centre crop + OpenCV-compatible fixed-point bilinear resize of one uint8 HxWx3 image (reference
+// network.py:137-146 + cv2.resize at :152).  taps[0..3] = x0, x1, a0, a1 (per output column), taps[4..7] = y0, y1,
+// b0, b1 (per output row), all int32; arithmetic = OpenCV's 11-bit coefficient path:
+//   h = S[x0]*a0 + S[x1]*a1 ;  out = (((b0*(h0>>4))>>16) + ((b1*(h1>>4))>>16) + 2) >> 2
+// area2x: exact 2x down-scaling in both directions is the 2x2 box filter (a+b+c+d+2)>>2, as OpenCV does.
+__global__ void crop_resize_u8_kernel(const uint8_t* __restrict__ src, int W, int cy, int cx, uint8_t* __restrict__ dst,
+                                      int S, const int* __restrict__ taps, int area2x) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+  if (dx >= S) return;
+  uint8_t* o = dst + (static_cast<size_t>(dy) * S + dx) * 3;
+  if (area2x) {
+    const uint8_t* p0 = src + (static_cast<size_t>(cy + 2 * dy) * W + cx + 2 * dx) * 3;
+    const uint8_t* p1 = p0 + static_cast<size_t>(W) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+    return;
+  }
+  const int x0 = taps[dx], x1 = taps[S + dx], a0 = taps[2 * S + dx], a1 = taps[3 * S + dx];
+  const int y0 = taps[4 * S + dy], y1 = taps[5 * S + dy], b0 = taps[6 * S + dy], b1 = taps[7 * S + dy];
+  const uint8_t* r0 = src + (static_cast<size_t>(cy + y0) * W + cx) * 3;
+  const uint8_t* r1 = src + (static_cast<size_t>(cy + y1) * W + cx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+    const int h1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+  }
+}
+
 template <int CC, int COG, typename TIn>
 void launch_conv(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin, int Cout,
                  cudaStream_t st) {
@@ -222,6 +252,13 @@ template cudaError_t Conv3x3Relu6F32<float>(const float*, const float*, const fl
                                             int, cudaStream_t);
 template cudaError_t Conv3x3Relu6F32<uint8_t>(const uint8_t*, const float*, const float*, float*, int, int, int,
                                               int, int, cudaStream_t);
+
+cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst, int S, const int* taps, int area2x,
+                         cudaStream_t st) {
+  dim3 grid((S + 127) / 128, S);
+  crop_resize_u8_kernel<<<grid, 128, 0, st>>>(src, W, cy, cx, dst, S, taps, area2x);
+  return cudaGetLastError();
+}
 
 cudaError_t AvgPoolF32(const float* in, float* out, int N, int H, int W, int C, int k, int s, cudaStream_t st) {
   int OH = (H - k) / s + 1, OW = (W - k) / s + 1;

@@ -9,7 +9,7 @@ network.py:49-85, :93-103, :158-170) are out of scope and raise.
 
 Extra, behaviour-preserving keywords: ``precision`` ('fp16' tensor-core path |
 'fp32' | 'bf16'), ``devices`` (CUDA ordinals, images of a batch are split over
-them), ``max_batch``.
+them), ``max_batch``, ``gpu_preprocess`` (crop + resize on the device, bit-identical to cv2).
 """
 from __future__ import annotations
 
@@ -25,7 +25,7 @@ class RoomNet:
     def __init__(self, num_classes, im_side=600, compute_bn_mean_var=True, start_step=0, dropout_enabled=False,
                  learn_rate=1e-4, l2_regularizer_coeff=1e-2, num_steps=10000, dropout_rate=.2,
                  update_batchnorm_means_vars=True, optimized_inference=False,
-                 precision='fp16', devices=(0,), max_batch=0, dense0_kernel=None):
+                 precision='fp16', devices=(0,), max_batch=0, dense0_kernel=None, gpu_preprocess=False):
         if compute_bn_mean_var:
             # reference network.py:193: training=True would use batch statistics; the product
             # implements the frozen-statistics inference path only (infer.py:104 passes False).
@@ -45,6 +45,8 @@ class RoomNet:
         self.devices = tuple(devices)
         self.max_batch = max_batch
         self._dense0_kernel = dense0_kernel
+        # center_crop + cv2.resize on the device (bit-identical to cv2 for uint8 images) instead of on the host
+        self.gpu_preprocess = gpu_preprocess
         self.sess = None  # the libroomnet handle plays the role of tf.Session
 
     # reference network.py:87-91
@@ -108,6 +110,8 @@ class RoomNet:
     # reference network.py:148-156 — one BGR uint8 image of any size
     def infer_optimized(self, im_in):
         self._require()
+        if self.gpu_preprocess and im_in.dtype == np.uint8:
+            return self.sess.infer_image_u8_bgr(im_in)
         im = self.preprocess(im_in)
         if im.dtype == np.uint8:
             out_label_idx, out_label_conf = self.sess.infer_u8_bgr(im[None])
@@ -119,7 +123,10 @@ class RoomNet:
     def infer_optimized_batch(self, ims):
         """Batched form of infer_optimized used by classify_im_dir: list of BGR images of any size."""
         self._require()
-        batch = np.stack([self.preprocess(im) for im in ims])
+        if self.gpu_preprocess:
+            batch = np.stack([self.sess.preprocess_u8(im) for im in ims])
+        else:
+            batch = np.stack([self.preprocess(im) for im in ims])
         return self.sess.infer_u8_bgr(batch)
 
     def train_step(self, x_in, y):
