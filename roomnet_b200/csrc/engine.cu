@@ -444,12 +444,27 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
     return cudaSuccess;
   };
   (void)out_stride;
-  // at least two micro-batches per call when the call is large: H2D of one overlaps compute of the other
-  const int chunk = n >= 64 ? std::min(max_batch_, std::max(32, (n + 1) / 2)) : max_batch_;
-  int k = 0;
-  for (int off = 0; off < n; off += chunk, ++k) {
+  // Micro-batch schedule of one call: the first H2D copy is exposed (nothing to overlap with), so the first
+  // micro-batch is small; the rest are as large as possible (kernel efficiency) while still alternating between
+  // the two staging slots / activation sets so that copies overlap the previous micro-batch's kernels.
+  std::vector<int> sizes;
+  if (n >= 128) {
+    const int first = std::min(max_batch_, std::max(32, n / 4));
+    sizes.push_back(first);
+    int rest = n - first;
+    const int parts = std::max(2, (rest + max_batch_ - 1) / max_batch_);
+    for (int i = 0; i < parts; ++i) {
+      const int m = rest / (parts - i);
+      if (m > 0) sizes.push_back(m);
+      rest -= m;
+    }
+  } else {
+    for (int off = 0; off < n; off += max_batch_) sizes.push_back(std::min(max_batch_, n - off));
+  }
+  int k = 0, off = 0;
+  for (size_t si = 0; si < sizes.size(); off += sizes[si], ++si, ++k) {
     const int slot = k & 1;
-    const int m = std::min(chunk, n - off);
+    const int m = sizes[si];
     cudaError_t e = drain(slot);  // slot buffers (d_in_, h_in_, outputs) are free after this
     if (e != cudaSuccess) return e;
     const char* src = static_cast<const char*>(h_in) + per * off;
