@@ -163,6 +163,7 @@ struct TcParams {
   float res_scale;         // res_side / out_side (float32, as TF computes it)
   const float* join_abc;   // device [3][cout]: A, B, C (A, B already divided by the stored-activation scales)
   int dbg;                 // timing experiments only (RN_TC_DBG): 1 = no stores, 2 = no pooling math, 4 = no TMEM re-init
+                           // (honoured only in builds with -DRN_TC_TIMING_EXPERIMENTS)
 };
 
 // POOL modes: 0 = none, 31 = 3x3/1, 41 = 4x4/1, 42 = 4x4/2.  The kernel stores the window SUM of
@@ -314,6 +315,32 @@ __device__ __forceinline__ void tc_mma_acc(uint32_t d_tmem, uint32_t a_lo, uint3
       : "memory");
 }
 // Same elected lane (deterministic for a full mask) commits: arrive on `bar` once all its prior MMAs completed.
+// variants for code that already runs on a single elected thread
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_acc1(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
   asm volatile(
       "{\n\t"
@@ -410,6 +437,28 @@ __host__ __device__ constexpr int tc_threads(int creal) { return 64 + 128 * tc_g
 // POOL : 0 / 31 / 41 / 42                     SEG  : images side by side in one 128-pixel tile
 // ---------------------------------------------------------------------------
 // CREAL: channels actually produced (<= COUT; conv0 pads 8 -> 16 to satisfy UMMA N % 16 == 0)
+// horizontal leg of the residual resize for one source row: left/right taps of CG channels (16-byte chunks one plane
+// apart), out[i] = l + (r - l) * tx on packed 16-bit pairs
+template <typename HH, int CG>
+__device__ __forceinline__ void join_hlerp(const uint8_t* row, uint32_t dx_bytes, uint32_t plane_bytes, uint32_t tx2,
+                                           uint32_t* out) {
+#pragma unroll
+  for (int cb = 0; cb < CG / 8; ++cb) {
+    const uint4 l = *reinterpret_cast<const uint4*>(row + cb * plane_bytes);
+    const uint4 r = *reinterpret_cast<const uint4*>(row + cb * plane_bytes + dx_bytes);
+    out[4 * cb + 0] = HH::fma(HH::sub(r.x, l.x), tx2, l.x);
+    out[4 * cb + 1] = HH::fma(HH::sub(r.y, l.y), tx2, l.y);
+    out[4 * cb + 2] = HH::fma(HH::sub(r.z, l.z), tx2, l.z);
+    out[4 * cb + 3] = HH::fma(HH::sub(r.w, l.w), tx2, l.w);
+  }
+}
+
+#ifdef RN_TC_TIMING_EXPERIMENTS
+#define RN_TC_DBG_BIT(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define RN_TC_DBG_BIT(p, bit) false
+#endif
+
 template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
 __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
@@ -568,6 +617,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     // Everything here is warp-uniform; only the tcgen05 instructions themselves are issued by lane 0.
+    if (elect_one()) {
     mbar_wait(bar_w, 0);
     const uint32_t a_lo0 = (smem_u32(s_stage) >> 4) | (Cfg::kALbo16 << 16);
     const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | (Cfg::kBLbo16 << 16);
@@ -597,20 +647,19 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             const uint32_t b_lo = b_lo0 + jlo * COUT;
 #pragma unroll
             for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-              tc_mma_acc(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+              tc_mma_acc1(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
           }
           if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
             const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
             const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
 #pragma unroll
             for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-              tc_mma_acc(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+              tc_mma_acc1(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
           }
         }
-        tc_commit_elect(bar_empty0 + 8u * st);
+        tc_commit(bar_empty0 + 8u * st);
         // conv rows r0-2, r0-1 received their last (dy = 2) contribution from this pair of input rows
-        if (r0 >= 2) tc_commit_elect(bar_accf0 + 8u * (((G + r0 - 2) >> 1) & (RP - 1)));
-        __syncwarp();
+        if (r0 >= 2) tc_commit(bar_accf0 + 8u * (((G + r0 - 2) >> 1) & (RP - 1)));
         if (++st == NST) {
           st = 0;
           ph ^= 1;
@@ -618,6 +667,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       }
       G += it.nconv;
     }
+    }
+    __syncwarp();
   } else if (warp < 2 + 4 * NG) {
     // ============================= epilogue =============================
     const int ew = warp - 2;
@@ -635,6 +686,20 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     float bias_r[CG];
 #pragma unroll
     for (int c = 0; c < CG; ++c) bias_r[c] = s_bias[grp * CG + c];
+    // fused join: per-channel coefficients of this thread's channels and the residual tensor's strides
+    constexpr bool kJoinPreload = JOIN && CG == 8 && POOL == 41;
+    constexpr bool kJoinCoefRegs = false;  // the registers are worth more as in-flight residual taps (kJoinPreload)
+    float jca[kJoinCoefRegs ? CG : 1], jcb[kJoinCoefRegs ? CG : 1], jcc[kJoinCoefRegs ? CG : 1];
+    const uint32_t jplane_bytes = static_cast<uint32_t>(p.res_side) * 16;
+    const uint32_t jrow_bytes = static_cast<uint32_t>(p.cb_out_total) * jplane_bytes;
+    if constexpr (kJoinCoefRegs) {
+#pragma unroll
+      for (int c = 0; c < CG; ++c) {
+        jca[c] = s_abc[grp * CG + c];
+        jcb[c] = s_abc[COUT + grp * CG + c];
+        jcc[c] = s_abc[2 * COUT + grp * CG + c];
+      }
+    }
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
     for (int s = 0; s < R; ++s) tc_st<CG>(t_base + s * COUT, bias_r);
     tc_wait_st();
@@ -661,18 +726,37 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         col_ok = lcol < p.win_step_out && !(POOL == 42 && (lane & 1)) && col < p.out_side;
       }
       col_ok = col_ok && n_img < p.N;
-      // fused residual join: horizontal taps of this thread's output column (fixed for the item)
-      int jx0 = 0, jx1 = 0;
-      float jtx = 0.f;
+      // fused residual join: horizontal taps of this thread's output column (fixed for the item).  jsrc points at
+      // the left tap of source row 0, jdx is the byte step to the right tap; jbot keeps the horizontally
+      // interpolated lower source row of the previous output row, which is the upper one of the next output row
+      // whenever the source rows advance by one (the 215 -> 205 join)
       const uint8_t* jsrc = nullptr;
+      uint32_t jdx = 0, jtx2 = 0, jbot[JOIN ? NP : 1];
+      int jy_prev = -1;
+      uint4 jpl[2], jpr[2];  // kJoinPreload: left/right taps of the lower source row of the next two output rows
       if (JOIN) {
         const float fx = static_cast<float>(col) * p.res_scale;
-        jx0 = static_cast<int>(floorf(fx));
-        jx1 = min(jx0 + 1, p.res_side - 1);
-        jtx = fx - static_cast<float>(jx0);
+        const int jx0 = static_cast<int>(fx);
+        jdx = jx0 + 1 < p.res_side ? 16u : 0u;
+        jtx2 = HH::splat(fx - static_cast<float>(jx0));
         jsrc = p.res_src + static_cast<size_t>(n_img) * p.res_side * p.cb_out_total * p.res_side * 16 +
-               (static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.res_side * 16;
+               (static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.res_side * 16 + jx0 * 16;
       }
+      // issue the gathers for output rows first_row, first_row + 1 (relative to the item); they are consumed one
+      // loop iteration later, so their latency hides behind the accumulator wait and the pooling arithmetic
+      auto join_preload = [&](int first_row) {
+        if (col_ok) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int row = min(max(first_row + k, 0), it.npo - 1);
+            const int y1 = min(static_cast<int>(static_cast<float>(it.po0 + row) * p.res_scale) + 1, p.res_side - 1);
+            const uint8_t* a = jsrc + static_cast<uint32_t>(y1) * jrow_bytes;
+            jpl[k] = *reinterpret_cast<const uint4*>(a);
+            jpr[k] = *reinterpret_cast<const uint4*>(a + jdx);
+          }
+        }
+      };
+      if constexpr (kJoinPreload) join_preload(-LAG);
       // output row pointer of the row produced by output slot 0 of the current iteration (may start "before" po0)
       uint8_t* optr = p.out + n_img * out_img_bytes +
                       ((static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.out_side + col) * 16 +
@@ -694,30 +778,10 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       for (int y = 0; y < it.nconv; y += 2, ++iter) {
         const uint32_t gy = G + y;
         const uint32_t slot0 = gy & (R - 1), slot1 = (gy + 1) & (R - 1);
-        if (JOIN && col_ok) {
-          // the residual taps of this iteration's output rows are known now: pull them into L1 while the
-          // accumulators are still being produced, so the gathers further down hit the cache
-          const int first_row = (POOL == 42 ? (y >> 1) - 1 : y - LAG);
-#pragma unroll
-          for (int k = 0; k < (POOL == 42 ? 1 : 2); ++k) {
-            const int row = min(max(first_row + k, 0), it.npo - 1);
-            const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
-            const int y0 = static_cast<int>(floorf(fy));
-            const int y1 = min(y0 + 1, p.res_side - 1);
-            const size_t src_row_bytes = static_cast<size_t>(p.cb_out_total) * p.res_side * 16;
-#pragma unroll
-            for (int cb = 0; cb < CG / 8; ++cb) {
-              const uint8_t* a0 = jsrc + y0 * src_row_bytes + static_cast<size_t>(cb) * p.res_side * 16 + jx0 * 16;
-              const uint8_t* a1 = jsrc + y1 * src_row_bytes + static_cast<size_t>(cb) * p.res_side * 16 + jx0 * 16;
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(a0));
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(a1));
-            }
-          }
-        }
         const uint32_t pair = (gy >> 1) & (RP - 1);
         mbar_wait(bar_accf0 + 8u * pair, (gy >> LOGR) & 1);
         tc_fence_after();
-        if (p.dbg & 8) {  // timing experiment: hand the slots straight back
+        if (RN_TC_DBG_BIT(p, 8)) {  // timing experiment: hand the slots straight back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acce0 + 8u * pair);
@@ -729,7 +793,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         tc_ld<CG>(t_base + slot1 * COUT, b);
         tc_wait_ld();
         // hand the slots back, pre-loaded with the bias
-        if (!(p.dbg & 4)) {
+        if (!RN_TC_DBG_BIT(p, 4)) {
           tc_st<CG>(t_base + slot0 * COUT, bias_r);
           tc_st<CG>(t_base + slot1 * COUT, bias_r);
           tc_wait_st();
@@ -783,7 +847,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
             const uint32_t v = vp[k][i];
-            if (POOL == 0 || (p.dbg & 2)) {
+            if (POOL == 0 || RN_TC_DBG_BIT(p, 2)) {
               hp[k][i] = v;
             } else if (POOL == 42) {
               const uint32_t u = HH::add(v, __shfl_xor_sync(0xffffffffu, v, 1));
@@ -799,59 +863,59 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
           if (POOL == 0) first = y;
           else if (POOL == 42) first = (y >> 1) - 1;
           else first = y - LAG;
-          if (col_ok && !(p.dbg & 1)) {
+          if (col_ok && !RN_TC_DBG_BIT(p, 1)) {
 #pragma unroll
             for (int k = 0; k < NK; ++k) {
               const int row = first + k;
               if (row >= 0 && row < it.npo) {
                 uint8_t* orow = optr + static_cast<size_t>(k) * out_row_bytes;
-                if (JOIN) {
-                  // reference network.py:199-203 in folded form; same fp32 arithmetic as join_h_kernel
+                if constexpr (JOIN) {
+                  // reference network.py:199-203 in folded form; same arithmetic as join_h_kernel: bilinear taps in
+                  // packed 16-bit arithmetic (top = tl + (tr-tl)*tx, ...: the TF formula), the per-channel affine in
+                  // fp32 (CPU emulation, DESIGN.md §2: the 16-bit lerp costs nothing measurable, a 16-bit affine
+                  // would cost 4x the error budget)
                   const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
-                  const int y0 = static_cast<int>(floorf(fy));
+                  const int y0 = static_cast<int>(fy);
                   const int y1 = min(y0 + 1, p.res_side - 1);
-                  const uint32_t ty2 = HH::splat(fy - static_cast<float>(y0)), tx2 = HH::splat(jtx);
-                  const size_t src_row_bytes = static_cast<size_t>(p.cb_out_total) * p.res_side * 16;
-                  const uint8_t* s0 = jsrc + y0 * src_row_bytes;
-                  const uint8_t* s1 = jsrc + y1 * src_row_bytes;
+                  const uint32_t ty2 = HH::splat(fy - static_cast<float>(y0));
+                  uint32_t top[NP];
+                  if (y0 == jy_prev) {
 #pragma unroll
-                  for (int cb = 0; cb < CG / 8; ++cb) {
-                    const size_t po = static_cast<size_t>(cb) * p.res_side * 16;
-                    uint4 tl = make_uint4(0, 0, 0, 0), tr = tl, bl = tl, br = tl;
-                    if (!(p.dbg & 32)) {  // (dbg 32: timing experiment without the residual gather)
-                      tl = *reinterpret_cast<const uint4*>(s0 + po + jx0 * 16);
-                      tr = *reinterpret_cast<const uint4*>(s0 + po + jx1 * 16);
-                      bl = *reinterpret_cast<const uint4*>(s1 + po + jx0 * 16);
-                      br = *reinterpret_cast<const uint4*>(s1 + po + jx1 * 16);
-                    }
-                    const uint32_t* ptl = &tl.x;
-                    const uint32_t* ptr = &tr.x;
-                    const uint32_t* pbl = &bl.x;
-                    const uint32_t* pbr = &br.x;
-                    // per-channel coefficients of this 8-channel chunk: 6 vector loads instead of 24 scalar ones
-                    float ca[8], cbv[8], cc[8];
-                    {
-                      const int c0 = grp * CG + 8 * cb;
-                      *reinterpret_cast<float4*>(ca) = *reinterpret_cast<const float4*>(s_abc + c0);
-                      *reinterpret_cast<float4*>(ca + 4) = *reinterpret_cast<const float4*>(s_abc + c0 + 4);
-                      *reinterpret_cast<float4*>(cbv) = *reinterpret_cast<const float4*>(s_abc + COUT + c0);
-                      *reinterpret_cast<float4*>(cbv + 4) = *reinterpret_cast<const float4*>(s_abc + COUT + c0 + 4);
-                      *reinterpret_cast<float4*>(cc) = *reinterpret_cast<const float4*>(s_abc + 2 * COUT + c0);
-                      *reinterpret_cast<float4*>(cc + 4) = *reinterpret_cast<const float4*>(s_abc + 2 * COUT + c0 + 4);
-                    }
+                    for (int i = 0; i < NP; ++i) top[i] = jbot[i];
+                  } else {
+                    join_hlerp<HH, CG>(jsrc + static_cast<uint32_t>(y0) * jrow_bytes, jdx, jplane_bytes, jtx2, top);
+                  }
+                  if constexpr (kJoinPreload) {
+                    jbot[0] = HH::fma(HH::sub(jpr[k].x, jpl[k].x), jtx2, jpl[k].x);
+                    jbot[1] = HH::fma(HH::sub(jpr[k].y, jpl[k].y), jtx2, jpl[k].y);
+                    jbot[2] = HH::fma(HH::sub(jpr[k].z, jpl[k].z), jtx2, jpl[k].z);
+                    jbot[3] = HH::fma(HH::sub(jpr[k].w, jpl[k].w), jtx2, jpl[k].w);
+                  } else {
+                    join_hlerp<HH, CG>(jsrc + static_cast<uint32_t>(y1) * jrow_bytes, jdx, jplane_bytes, jtx2, jbot);
+                    // the next output row reads source rows y1 + 1 (and y1 + 2): start pulling them into L1 now
+                    const int yn = min(y1 + (POOL == 42 ? 2 : 1), p.res_side - 1);
+                    const uint8_t* pn = jsrc + static_cast<uint32_t>(yn) * jrow_bytes;
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                      const int i = 4 * cb + e2;  // pair index
-                      // bilinear taps in packed 16-bit arithmetic (top = tl + (tr-tl)*tx, ...: the TF formula), the
-                      // per-channel affine in fp32: CPU emulation shows no measurable logit change for
-                      // the 16-bit lerp, while a 16-bit affine would cost 4x the error budget
-                      const uint32_t top = HH::fma(HH::sub(ptr[e2], ptl[e2]), tx2, ptl[e2]);
-                      const uint32_t bot = HH::fma(HH::sub(pbr[e2], pbl[e2]), tx2, pbl[e2]);
-                      const float2 rs = HH::unpack(HH::fma(HH::sub(bot, top), ty2, top)), hv = HH::unpack(hp[k][i]);
-                      const float j0 = fmaf(ca[2 * e2], hv.x, fmaf(cbv[2 * e2], rs.x, cc[2 * e2]));
-                      const float j1 = fmaf(ca[2 * e2 + 1], hv.y, fmaf(cbv[2 * e2 + 1], rs.y, cc[2 * e2 + 1]));
-                      hp[k][i] = HH::pack(j0, j1);
+                    for (int cb = 0; cb < CG / 8; ++cb)
+                      asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + cb * jplane_bytes));
+                  }
+                  jy_prev = y1;
+#pragma unroll
+                  for (int i = 0; i < NP; ++i) {
+                    const float2 rs = HH::unpack(HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]));
+                    const float2 hv = HH::unpack(hp[k][i]);
+                    float2 a2, b2, c2;
+                    if constexpr (kJoinCoefRegs) {
+                      a2 = make_float2(jca[2 * i], jca[2 * i + 1]);
+                      b2 = make_float2(jcb[2 * i], jcb[2 * i + 1]);
+                      c2 = make_float2(jcc[2 * i], jcc[2 * i + 1]);
+                    } else {
+                      const float* co = s_abc + grp * CG + 2 * i;
+                      a2 = *reinterpret_cast<const float2*>(co);
+                      b2 = *reinterpret_cast<const float2*>(co + COUT);
+                      c2 = *reinterpret_cast<const float2*>(co + 2 * COUT);
                     }
+                    hp[k][i] = HH::pack(fmaf(a2.x, hv.x, fmaf(b2.x, rs.x, c2.x)), fmaf(a2.y, hv.y, fmaf(b2.y, rs.y, c2.y)));
                   }
                 }
 #pragma unroll
@@ -863,6 +927,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             }
           }
           optr += (POOL == 42 ? 1 : 2) * out_row_bytes;
+          if constexpr (kJoinPreload) join_preload(first + NK);
         }
       }
       G += it.nconv;
