@@ -394,7 +394,8 @@ cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long l
   const int C = shape_.num_classes;
   // Two half-size micro-batches on two streams overlap better than one big one (see ActSet); while
   // profiling everything stays on `st` so that the per-kernel events measure isolated kernels.
-  const bool overlap = !profiling_ && n >= 64;
+  static const bool no_overlap = std::getenv("RN_NO_OVERLAP") != nullptr;  // experiments
+  const bool overlap = !profiling_ && !no_overlap && n >= 64;
   const int chunk = overlap ? std::min(max_batch_, std::max(32, (n + 1) / 2)) : max_batch_;
   if (overlap) RN_CUDA(cudaEventRecord(ev_fork_, st));
   int k = 0;

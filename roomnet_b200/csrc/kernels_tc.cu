@@ -1311,12 +1311,29 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
     p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
   }
   const int groups = (N + SEG - 1) / SEG;
-  const int base_items = groups * p.n_strips * L.cout_parts;
-  // split rows so that the persistent grid sees >= ~4 waves, but keep >= 8 pooled rows per item
-  int nrb = (4 * 148 + base_items - 1) / base_items;
-  nrb = std::max(1, std::min(nrb, std::max(1, p.out_side / 8)));
-  p.rows_per_item = (p.out_side + nrb - 1) / nrb;
-  p.n_rowblocks = (p.out_side + p.rows_per_item - 1) / p.rows_per_item;
+  // Row blocks: items are dealt round-robin to the persistent CTAs, so the kernel lasts as long as the CTA with the
+  // most items.  Pick the split that minimises (items per CTA, rounded up) x (conv rows per item + pipeline refill),
+  // keeping >= 8 pooled rows per item; a finer split evens out the last round, a coarser one saves halo rows.
+  {
+    const int ctas = std::max(1, 148 / L.cout_parts);
+    const int max_nrb = std::max(1, p.out_side / 8);
+    long best_cost = -1;
+    int best_rows = p.out_side;
+    for (int nrb = 1; nrb <= max_nrb; ++nrb) {
+      const int rows = (p.out_side + nrb - 1) / nrb;
+      const int blocks = (p.out_side + rows - 1) / rows;
+      const int conv_rows = POOL == 0 ? rows : (POOL == 42 ? 2 * rows + 2 : rows + (POOL == 41 ? 3 : 2));
+      const long items = static_cast<long>(groups) * p.n_strips * blocks;
+      const long rounds = (items + ctas - 1) / ctas;
+      const long cost = rounds * (conv_rows + 4);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_rows = rows;
+      }
+    }
+    p.rows_per_item = best_rows;
+    p.n_rowblocks = (p.out_side + best_rows - 1) / best_rows;
+  }
   p.n_items = groups * p.n_strips * p.n_rowblocks;
   auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL, JOIN>;
   if (JOIN) {
