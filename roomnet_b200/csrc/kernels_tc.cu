@@ -38,10 +38,8 @@ namespace {
 
 constexpr int kTileM = 128;           // pixels per row tile (UMMA M)
 constexpr int kPlanePx = 136;         // pixels per channel-chunk plane in a smem stage
-constexpr int kPlaneBytes = kPlanePx * 16;
 constexpr int kLoadPx = 132;          // pixels fetched per plane row (128 + taps, 16B multiple)
 constexpr int kSlackBytes = 128 * 1024;  // over-read slack behind every chunked tensor (row tails + one padding row)
-constexpr int kThreads = 192;         // (v1 layout, kept for the small helper kernels)
 constexpr int kSmemBudget = 227 * 1024;
 
 // ------------------------------------------------------------------ PTX ----
@@ -90,31 +88,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr));
-}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// UMMA shared-memory descriptor, no swizzle, K-major:  ((8,m),(8,2)) : ((16B, SBO), (2B, LBO))
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo_bytes >> 4) << 16) |
-         (static_cast<uint64_t>(sbo_bytes >> 4) << 32) | (1ull << 46);
-}
 // kind::f16 instruction descriptor: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M=128.
 __device__ __forceinline__ uint32_t make_idesc(int n, int bf16) {
   return (1u << 4) | (static_cast<uint32_t>(bf16) << 7) | (static_cast<uint32_t>(bf16) << 10) |
@@ -298,22 +273,6 @@ struct H2 {
 
 // Warp-converged call: one elected lane issues D[tmem] += A[smem] * B[smem].  elect.sync (not `lane == 0`) lets ptxas
 // emit ELECT + a predicated UTCHMMA instead of a per-active-lane serialisation loop around every MMA.
-__device__ __forceinline__ void tc_mma_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
-                                           uint32_t idesc) {
-  // both descriptors share the high word (SBO = 128 B, version 1, no swizzle)
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "setp.eq.b32 p, 0, 0;\n\t"
-      "mov.b64 da, {%1, %3};\n\t"
-      "mov.b64 db, {%2, %3};\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
-      : "memory");
-}
 // Same elected lane (deterministic for a full mask) commits: arrive on `bar` once all its prior MMAs completed.
 // variants for code that already runs on a single elected thread
 __device__ __forceinline__ bool elect_one() {
@@ -340,30 +299,6 @@ __device__ __forceinline__ void tc_mma_acc1(uint32_t d_tmem, uint32_t a_lo, uint
       "}" ::"r"(d_tmem),
       "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
       : "memory");
-}
-__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}" ::"r"(bar)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tc_st8(uint32_t taddr, const float* v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
-               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-               : "memory");
 }
 template <int N>
 __device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
@@ -688,18 +623,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     for (int c = 0; c < CG; ++c) bias_r[c] = s_bias[grp * CG + c];
     // fused join: per-channel coefficients of this thread's channels and the residual tensor's strides
     constexpr bool kJoinPreload = JOIN && CG == 8 && POOL == 41;
-    constexpr bool kJoinCoefRegs = false;  // the registers are worth more as in-flight residual taps (kJoinPreload)
-    float jca[kJoinCoefRegs ? CG : 1], jcb[kJoinCoefRegs ? CG : 1], jcc[kJoinCoefRegs ? CG : 1];
     const uint32_t jplane_bytes = static_cast<uint32_t>(p.res_side) * 16;
     const uint32_t jrow_bytes = static_cast<uint32_t>(p.cb_out_total) * jplane_bytes;
-    if constexpr (kJoinCoefRegs) {
-#pragma unroll
-      for (int c = 0; c < CG; ++c) {
-        jca[c] = s_abc[grp * CG + c];
-        jcb[c] = s_abc[COUT + grp * CG + c];
-        jcc[c] = s_abc[2 * COUT + grp * CG + c];
-      }
-    }
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
     for (int s = 0; s < R; ++s) tc_st<CG>(t_base + s * COUT, bias_r);
     tc_wait_st();
@@ -904,17 +829,11 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
                   for (int i = 0; i < NP; ++i) {
                     const float2 rs = HH::unpack(HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]));
                     const float2 hv = HH::unpack(hp[k][i]);
-                    float2 a2, b2, c2;
-                    if constexpr (kJoinCoefRegs) {
-                      a2 = make_float2(jca[2 * i], jca[2 * i + 1]);
-                      b2 = make_float2(jcb[2 * i], jcb[2 * i + 1]);
-                      c2 = make_float2(jcc[2 * i], jcc[2 * i + 1]);
-                    } else {
-                      const float* co = s_abc + grp * CG + 2 * i;
-                      a2 = *reinterpret_cast<const float2*>(co);
-                      b2 = *reinterpret_cast<const float2*>(co + COUT);
-                      c2 = *reinterpret_cast<const float2*>(co + 2 * COUT);
-                    }
+                    // per-channel coefficients from shared memory (registers are worth more as in-flight taps)
+                    const float* co = s_abc + grp * CG + 2 * i;
+                    const float2 a2 = *reinterpret_cast<const float2*>(co);
+                    const float2 b2 = *reinterpret_cast<const float2*>(co + COUT);
+                    const float2 c2 = *reinterpret_cast<const float2*>(co + 2 * COUT);
                     hp[k][i] = HH::pack(fmaf(a2.x, hv.x, fmaf(b2.x, rs.x, c2.x)), fmaf(a2.y, hv.y, fmaf(b2.y, rs.y, c2.y)));
                   }
                 }
@@ -1446,9 +1365,7 @@ size_t PackTcConv0Weights(const double* w, HalfKind kind, double scale, void* ou
       std::memcpy(&f, &u, 4);
       return static_cast<double>(f);
     }
-    __half h;
-    std::memcpy(&h, &bits, 2);
-    return static_cast<double>(__half2float(h));
+    return static_cast<double>(__half2float(__ushort_as_half(bits)));
   };
   for (int half = 0; half < 2; ++half)
     for (int j = 0; j < 3; ++j)
