@@ -99,6 +99,13 @@ int rn_infer_f32_rgb(rn_handle* h, const float* nhwc, int32_t n, int64_t* top1, 
  * NHWC uint8 RGB (Bitmap channel order, Classifier.java:226-243). */
 int rn_infer_u8_rgb(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits);
 
+/* Classifier.convertBitmapToByteBuffer                   Classifier.java:226-243
+ * bitmap.getPixels(intValues, ...) followed by the per-pixel addPixelValue loop (ClassifierFloatMobileNet.java:74-78:
+ * ((v >> 16) & 0xFF, (v >> 8) & 0xFF, v & 0xFF) -> (p - 127.5) / 127.5) - the 50 k-iteration Java loop moves into the
+ * library: `pixels` is the int[] of Bitmap.getPixels, [n, S, S] 0xAARRGGBB values (alpha ignored); the bytes of
+ * each int are B,G,R,A in memory, so this is rn_infer_u8_bgr with a 4-byte pixel pitch (bit-identical results). */
+int rn_infer_argb8888(rn_handle* h, const int32_t* pixels, int32_t n, int64_t* top1, float* probs, float* logits);
+
 /* Device-resident variant of rn_infer_u8_bgr on replica 0: d_nhwc, d_top1 (int64),
  * d_probs, d_logits are device pointers on devices[0]; work is enqueued on
  * `cuda_stream` (a cudaStream_t, NULL = the replica's own stream) and NOT

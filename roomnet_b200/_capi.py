@@ -55,6 +55,7 @@ def _load():
         "rn_infer_u8_bgr": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_u8_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_f32_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
+        "rn_infer_argb8888": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_u8_bgr_device": ([vp, vp, i32, vp, vp, vp, vp], C.c_int),
         "rn_preprocess_u8": ([vp, vp, i32, i32, vp], C.c_int),
         "rn_infer_image_u8_bgr": ([vp, vp, i32, i32, vp, vp, vp], C.c_int),
@@ -79,7 +80,7 @@ def _load():
 
 lib = _load()
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
-            "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_u8_bgr_device",
+            "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
             "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
@@ -157,6 +158,21 @@ class Handle:
 
     def infer_f32_rgb(self, x, want_logits=False):
         return self._infer(lib.rn_infer_f32_rgb, x, np.float32, want_logits)
+
+    def infer_argb8888(self, pixels, want_logits=False):
+        """[n, S, S] int32 0xAARRGGBB pixels (android.graphics.Bitmap.getPixels)."""
+        x = np.asarray(pixels)
+        if x.ndim != 3 or x.shape[1:] != (self.im_side, self.im_side):
+            raise RoomNetError(RN_ERR_INVALID_ARG, "pixels must be [n,%d,%d] int32, got %s"
+                               % (self.im_side, self.im_side, x.shape))
+        x = np.ascontiguousarray(x, dtype=np.int32)
+        n = x.shape[0]
+        top1 = np.empty((n,), np.int64)
+        probs = np.empty((n, self.num_classes), np.float32)
+        logits = np.empty((n, self.num_classes), np.float32) if want_logits else None
+        self._check(lib.rn_infer_argb8888(self._h, x.ctypes.data, n, top1.ctypes.data, probs.ctypes.data,
+                                          logits.ctypes.data if want_logits else None))
+        return (top1, probs, logits) if want_logits else (top1, probs)
 
     def preprocess_u8(self, img):
         """center_crop + cv2.resize(img, (S, S)) on the device (bit-identical to cv2 for uint8)."""

@@ -61,8 +61,7 @@ int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1
   auto t0 = std::chrono::steady_clock::now();
   const int g = static_cast<int>(h->replicas.size());
   const int C = h->shape.num_classes;
-  const size_t per =
-      static_cast<size_t>(h->shape.im_side) * h->shape.im_side * 3 * (kind == InputKind::kF32Rgb ? 4 : 1);
+  const size_t per = static_cast<size_t>(h->shape.im_side) * h->shape.im_side * rn::InputBytesPerPixel(kind);
   // contiguous, as-even-as-possible split of [0, n) over the replicas
   std::vector<int> begin(g + 1, 0);
   for (int r = 0; r < g; ++r) begin[r + 1] = begin[r] + n / g + (r < n % g ? 1 : 0);
@@ -210,6 +209,9 @@ int rn_infer_u8_rgb(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1,
 }
 int rn_infer_f32_rgb(rn_handle* h, const float* nhwc, int32_t n, int64_t* top1, float* probs, float* logits) {
   return Infer(h, nhwc, InputKind::kF32Rgb, n, top1, probs, logits);
+}
+int rn_infer_argb8888(rn_handle* h, const int32_t* pixels, int32_t n, int64_t* top1, float* probs, float* logits) {
+  return Infer(h, pixels, InputKind::kArgb8888, n, top1, probs, logits);
 }
 
 int rn_infer_u8_bgr_device(rn_handle* h, const void* d_nhwc, int32_t n, void* d_top1, void* d_probs, void* d_logits,

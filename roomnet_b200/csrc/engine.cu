@@ -17,9 +17,11 @@ namespace rn {
     }                                                                                                   \
   } while (0)
 
+size_t InputBytesPerPixel(InputKind k) { return k == InputKind::kF32Rgb ? 12 : (k == InputKind::kArgb8888 ? 4 : 3); }
+
 namespace {
 size_t InputBytesPerImage(const NetShape& s, InputKind k) {
-  return static_cast<size_t>(s.im_side) * s.im_side * 3 * (k == InputKind::kF32Rgb ? 4 : 1);
+  return static_cast<size_t>(s.im_side) * s.im_side * InputBytesPerPixel(k);
 }
 }  // namespace
 
@@ -292,14 +294,15 @@ cudaError_t Replica::TailF32(int first_layer, int n, cudaStream_t st) {
 
 cudaError_t Replica::ForwardF32(const void* d_in, InputKind kind, int n, cudaStream_t st) {
   const ConvShape& c0 = shape_.conv[0];
-  const int k = static_cast<int>(kind);
+  const bool argb = kind == InputKind::kArgb8888;  // BGRA bytes: the BGR weights with a 4-byte pixel pitch
+  const int k = static_cast<int>(argb ? InputKind::kU8Bgr : kind);
   Mark(nullptr, st);
   if (kind == InputKind::kF32Rgb)
     RN_CUDA(Conv3x3Relu6F32<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], cur_->conv_scratch, n, c0.in_side,
                                    c0.in_side, 3, c0.cout, st));
   else
     RN_CUDA(Conv3x3Relu6F32<uint8_t>(static_cast<const uint8_t*>(d_in), w0_[k], b0_[k], cur_->conv_scratch, n, c0.in_side,
-                                     c0.in_side, 3, c0.cout, st));
+                                     c0.in_side, 3, c0.cout, st, argb ? 4 : 3));
   Mark("conv0_f32", st);
   RN_CUDA(AvgPoolF32(cur_->conv_scratch, cur_->pooled[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
   Mark("pool0_f32", st);
@@ -309,14 +312,15 @@ cudaError_t Replica::ForwardF32(const void* d_in, InputKind kind, int n, cudaStr
 cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
                                float* d_logits, cudaStream_t st) {
   const ConvShape& c0 = shape_.conv[0];
-  const int k = static_cast<int>(kind);
+  const bool argb = kind == InputKind::kArgb8888;
+  const int k = static_cast<int>(argb ? InputKind::kU8Bgr : kind);
   Mark(nullptr, st);
   if (kind == InputKind::kF32Rgb) {
     // raw float feed: operands need more than 11 bits, keep conv0 in fp32 on the CUDA cores
     RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], cur_->act_h[0], n, c0.in_side, half_kind_, st));
     Mark("conv0_pool_h", st);
   } else {
-    RN_CUDA(PrepU8(static_cast<const uint8_t*>(d_in), cur_->in_h, n, c0.in_side, half_kind_, st));
+    RN_CUDA(PrepU8(static_cast<const uint8_t*>(d_in), cur_->in_h, n, c0.in_side, half_kind_, st, argb ? 4 : 3));
     Mark("prep_u8", st);
     TcConvLayer L0 = tc_[0];
     L0.w_packed = tc0_w_[k];

@@ -13,7 +13,9 @@
 
 namespace rn {
 
-enum class InputKind : int { kU8Bgr = 0, kU8Rgb = 1, kF32Rgb = 2 };
+// kArgb8888: one 32-bit 0xAARRGGBB int per pixel (android.graphics.Bitmap.getPixels), i.e. bytes B,G,R,A in memory
+enum class InputKind : int { kU8Bgr = 0, kU8Rgb = 1, kF32Rgb = 2, kArgb8888 = 3 };
+size_t InputBytesPerPixel(InputKind k);
 
 class Replica {
  public:

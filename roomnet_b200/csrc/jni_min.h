@@ -23,6 +23,7 @@ typedef jobject jstring;
 typedef jobject jarray;
 typedef jobject jobjectArray;
 typedef jobject jfloatArray;
+typedef jobject jintArray;
 typedef jobject jthrowable;
 
 struct JNINativeInterface_;
@@ -37,6 +38,8 @@ enum {
   kJniReleaseStringUTFChars = 170,
   kJniGetArrayLength = 171,
   kJniGetObjectArrayElement = 173,
+  kJniGetIntArrayElements = 187,
+  kJniReleaseIntArrayElements = 195,
   kJniSetFloatArrayRegion = 213,
   kJniGetDirectBufferAddress = 230,
   kJniGetDirectBufferCapacity = 231,
@@ -54,6 +57,8 @@ typedef const char* (*JniGetStringUTFCharsFn)(JNIEnv*, jstring, jboolean*);
 typedef void (*JniReleaseStringUTFCharsFn)(JNIEnv*, jstring, const char*);
 typedef jsize (*JniGetArrayLengthFn)(JNIEnv*, jarray);
 typedef jobject (*JniGetObjectArrayElementFn)(JNIEnv*, jobjectArray, jsize);
+typedef jint* (*JniGetIntArrayElementsFn)(JNIEnv*, jintArray, jboolean*);
+typedef void (*JniReleaseIntArrayElementsFn)(JNIEnv*, jintArray, jint*, jint);
 typedef void (*JniSetFloatArrayRegionFn)(JNIEnv*, jfloatArray, jsize, jsize, const jfloat*);
 typedef void* (*JniGetDirectBufferAddressFn)(JNIEnv*, jobject);
 typedef jlong (*JniGetDirectBufferCapacityFn)(JNIEnv*, jobject);

@@ -10,6 +10,7 @@
 //   final class RoomNetNative {
 //     static native long create(String checkpointPrefix, int device, int imSide, int precision);
 //     static native int run(long handle, java.nio.ByteBuffer imgData, float[][] labelProbArray);
+//     static native int runArgb(long handle, int[] intValues, float[][] labelProbArray);
 //     static native void close(long handle);
 //   }
 #include <cstring>
@@ -125,6 +126,46 @@ jint RN_JNI(run)(JNIEnv* env, jclass, jlong handle, jobject img_data, jobjectArr
   else if (cap == px * 4 || cap == px)
     Throw(env, "java/lang/IllegalStateException", std::string("RoomNet: ") + rn_last_error(m->h));
   Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);  // the row reference is released on every path
+  return rc;
+}
+
+// The demo's Bitmap -> ByteBuffer conversion folded into the native call: `int_values` is the int[] that
+// convertBitmapToByteBuffer fills with bitmap.getPixels(...) (Classifier.java:226-231), S*S 0xAARRGGBB values; the
+// per-pixel addPixelValue loop (:233-240, ClassifierFloatMobileNet.java:74-78) runs on the device instead.
+jint RN_JNI(runArgb)(JNIEnv* env, jclass, jlong handle, jintArray int_values, jobjectArray label_prob_array) {
+  JniModel* m = reinterpret_cast<JniModel*>(handle);
+  if (!m || !m->h) {
+    Throw(env, "java/lang/IllegalStateException", "RoomNet: classifier is closed");
+    return RN_ERR_INVALID_ARG;
+  }
+  const jlong px = static_cast<jlong>(m->im_side) * m->im_side;
+  if (!int_values || Slot<JniGetArrayLengthFn>(env, kJniGetArrayLength)(env, int_values) != px) {
+    Throw(env, "java/lang/IllegalArgumentException", "RoomNet: intValues must hold imageSizeX * imageSizeY pixels");
+    return RN_ERR_INVALID_ARG;
+  }
+  if (!label_prob_array || Slot<JniGetArrayLengthFn>(env, kJniGetArrayLength)(env, label_prob_array) < 1) {
+    Throw(env, "java/lang/IllegalArgumentException", "RoomNet: labelProbArray must be float[1][numLabels]");
+    return RN_ERR_INVALID_ARG;
+  }
+  jobject row = Slot<JniGetObjectArrayElementFn>(env, kJniGetObjectArrayElement)(env, label_prob_array, 0);
+  if (!row || Slot<JniGetArrayLengthFn>(env, kJniGetArrayLength)(env, row) < m->num_classes) {
+    if (row) Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
+    Throw(env, "java/lang/IllegalArgumentException", "RoomNet: labelProbArray[0] is shorter than the label count");
+    return RN_ERR_INVALID_ARG;
+  }
+  jint* pixels = Slot<JniGetIntArrayElementsFn>(env, kJniGetIntArrayElements)(env, int_values, nullptr);
+  if (!pixels) {  // OutOfMemoryError already pending
+    Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
+    return RN_ERR_INTERNAL;
+  }
+  float probs[32];
+  const int rc = rn_infer_argb8888(m->h, pixels, 1, nullptr, probs, nullptr);
+  Slot<JniReleaseIntArrayElementsFn>(env, kJniReleaseIntArrayElements)(env, int_values, pixels, 2 /* JNI_ABORT */);
+  if (rc == RN_OK)
+    Slot<JniSetFloatArrayRegionFn>(env, kJniSetFloatArrayRegion)(env, row, 0, m->num_classes, probs);
+  else
+    Throw(env, "java/lang/IllegalStateException", std::string("RoomNet: ") + rn_last_error(m->h));
+  Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
   return rc;
 }
 

@@ -18,7 +18,7 @@ struct DenseParams {
 // ---- fp32 CUDA-core kernels (kernels_f32.cu) --------------------------------
 template <typename TIn>
 cudaError_t Conv3x3Relu6F32(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin,
-                            int Cout, cudaStream_t st);
+                            int Cout, cudaStream_t st, int px_stride = 0);
 cudaError_t AvgPoolF32(const float* in, float* out, int N, int H, int W, int C, int k, int s, cudaStream_t st);
 cudaError_t JoinF32(const float* p, const float* src, float* out, const float* A, const float* B, const float* C,
                     int N, int S, int SS, int Ch, cudaStream_t st);
@@ -63,7 +63,7 @@ size_t PackTcWeights(const double* w_hwio, int cin, int cout, int cout_parts, Ha
 // conv0 on the tensor cores: weights [3][3][3][8] (uint8-folded) split into fp16 hi + lo halves.
 size_t PackTcConv0Weights(const double* w_hwio, HalfKind kind, double scale, void* out_host);
 // uint8 NHWC image -> pixel-pair chunks (values / 256, exact) consumed by conv0's A descriptor.
-cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st);
+cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st, int px_bytes = 3);
 
 cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st);
 

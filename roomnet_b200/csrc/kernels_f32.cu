@@ -32,7 +32,7 @@ __device__ __forceinline__ float load_as_float(const TIn* p) {
 template <int CC, int COG, typename TIn>
 __global__ void __launch_bounds__(kTile* kTile)
     conv3x3_relu6_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
-                         float* __restrict__ out, int H, int W, int Cin, int Cout) {
+                         float* __restrict__ out, int H, int W, int Cin, int Cout, int px_stride) {
   __shared__ float s_in[CC][kHalo][kHalo + 1];
   __shared__ __align__(16) float s_w[9][CC][COG];
 
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kTile* kTile)
   const int co0 = (blockIdx.z % groups) * COG;
   const int tx = threadIdx.x % kTile, ty = threadIdx.x / kTile;
   const int oy0 = blockIdx.y * kTile, ox0 = blockIdx.x * kTile;
-  const TIn* in_n = in + static_cast<size_t>(n) * H * W * Cin;
+  const TIn* in_n = in + static_cast<size_t>(n) * H * W * px_stride;  // px_stride > Cin: padded pixels (BGRA)
 
   float acc[COG];
 #pragma unroll
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kTile* kTile)
       int py = idx / (CC * kHalo);
       int iy = oy0 + py, ix = ox0 + px;
       float v = 0.f;
-      if (iy < H && ix < W && c0 + c < Cin) v = load_as_float(in_n + (static_cast<size_t>(iy) * W + ix) * Cin + c0 + c);
+      if (iy < H && ix < W && c0 + c < Cin) v = load_as_float(in_n + (static_cast<size_t>(iy) * W + ix) * px_stride + c0 + c);
       s_in[c][py][px] = v;
     }
     for (int idx = threadIdx.x; idx < 9 * CC * COG; idx += kTile * kTile) {
@@ -228,30 +228,31 @@ __global__ void crop_resize_u8_kernel(const uint8_t* __restrict__ src, int W, in
 
 template <int CC, int COG, typename TIn>
 void launch_conv(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin, int Cout,
-                 cudaStream_t st) {
+                 int px_stride, cudaStream_t st) {
   dim3 grid((W - 2 + kTile - 1) / kTile, (H - 2 + kTile - 1) / kTile, N * (Cout / COG));
-  conv3x3_relu6_kernel<CC, COG, TIn><<<grid, kTile * kTile, 0, st>>>(in, w, b, out, H, W, Cin, Cout);
+  conv3x3_relu6_kernel<CC, COG, TIn><<<grid, kTile * kTile, 0, st>>>(in, w, b, out, H, W, Cin, Cout, px_stride);
 }
 
 }  // namespace
 
 template <typename TIn>
 cudaError_t Conv3x3Relu6F32(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin,
-                            int Cout, cudaStream_t st) {
+                            int Cout, cudaStream_t st, int px_stride) {
+  if (px_stride <= 0) px_stride = Cin;
   if (Cin == 3 && Cout % 8 == 0)
-    launch_conv<3, 8, TIn>(in, w, b, out, N, H, W, Cin, Cout, st);
+    launch_conv<3, 8, TIn>(in, w, b, out, N, H, W, Cin, Cout, px_stride, st);
   else if (Cin % 8 == 0 && Cout % 16 == 0)
-    launch_conv<8, 16, TIn>(in, w, b, out, N, H, W, Cin, Cout, st);
+    launch_conv<8, 16, TIn>(in, w, b, out, N, H, W, Cin, Cout, px_stride, st);
   else if (Cin % 8 == 0 && Cout % 8 == 0)
-    launch_conv<8, 8, TIn>(in, w, b, out, N, H, W, Cin, Cout, st);
+    launch_conv<8, 8, TIn>(in, w, b, out, N, H, W, Cin, Cout, px_stride, st);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 template cudaError_t Conv3x3Relu6F32<float>(const float*, const float*, const float*, float*, int, int, int, int,
-                                            int, cudaStream_t);
+                                            int, cudaStream_t, int);
 template cudaError_t Conv3x3Relu6F32<uint8_t>(const uint8_t*, const float*, const float*, float*, int, int, int,
-                                              int, int, cudaStream_t);
+                                              int, int, cudaStream_t, int);
 
 cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst, int S, const int* taps, int area2x,
                          cudaStream_t st) {

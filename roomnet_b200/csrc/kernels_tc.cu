@@ -1173,18 +1173,19 @@ __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __
 
 // uint8 NHWC (3 channels) -> conv0 tensor-core input: out[n][y][x] = 16 bytes {p(x).c0,c1,c2,0, p(x+1).c0,c1,c2,0}
 // with p = pixel/256 (exact in fp16 and bf16).  One thread per output chunk.
-__global__ void prep_u8_kernel(const uint8_t* __restrict__ in, uint4* __restrict__ out, int N, int S, int bf16) {
+__global__ void prep_u8_kernel(const uint8_t* __restrict__ in, uint4* __restrict__ out, int N, int S, int bf16,
+                               int px_bytes) {
   const size_t total = static_cast<size_t>(N) * S * S;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int x = static_cast<int>(i % S);
-    const uint8_t* px = in + i * 3;
+    const uint8_t* px = in + i * px_bytes;  // 3 = packed BGR/RGB, 4 = BGRA (Android ARGB_8888 ints)
     float a0 = px[0], a1 = px[1], a2 = px[2];
     float b0 = 0.f, b1 = 0.f, b2 = 0.f;
     if (x + 1 < S) {
-      b0 = px[3];
-      b1 = px[4];
-      b2 = px[5];
+      b0 = px[px_bytes];
+      b1 = px[px_bytes + 1];
+      b2 = px[px_bytes + 2];
     }
     const float sc = 1.f / 256.f;
     uint4 o;
@@ -1387,10 +1388,10 @@ size_t PackTcConv0Weights(const double* w, HalfKind kind, double scale, void* ou
   return bytes;
 }
 
-cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st) {
+cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st, int px_bytes) {
   size_t total = static_cast<size_t>(N) * S * S;
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
-  prep_u8_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint4*>(out), N, S, kind == HalfKind::kBF16);
+  prep_u8_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint4*>(out), N, S, kind == HalfKind::kBF16, px_bytes);
   return cudaGetLastError();
 }
 

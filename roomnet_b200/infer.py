@@ -6,15 +6,19 @@ overlaid text lines, or a plain copy when ``overlay=False``) and
 ``<dir>_classified_results.xls`` (header IMAGE_NAME / PREDICTED_LABEL, one row
 per file: name, label, confidence as a string), and return the xls path.
 
-What is different: files are decoded up front and go through the network in
-batches of ``BATCH`` images (one C-ABI call each) instead of one
-``Session.run`` per file (reference infer.py:79-82).
+What is different: files go through the network in batches of ``BATCH`` images
+(one C-ABI call each) instead of one ``Session.run`` per file (reference
+infer.py:79-82), and the disk work either side of the network runs on a thread
+pool: the next batch is decoded while the current one is classified, and the
+overlay / copy writes of finished batches proceed in the background (cv2 drops
+the GIL).  The artefacts and the order of the xls rows are unchanged.
 """
 from __future__ import annotations
 
 import os
 import shutil
 import struct
+from concurrent.futures import ThreadPoolExecutor
 from glob import glob
 
 import cv2
@@ -26,6 +30,7 @@ INPUT_MODEL_PATH = './final_model/roomnet'       # reference infer.py:24
 INPUT_IMAGES_DIR = './test_images/set2/images'   # reference infer.py:25
 IMG_SIDE = 224                                   # reference infer.py:26
 BATCH = 256
+IO_THREADS = min(32, os.cpu_count() or 1)
 
 
 class _Biff2Sheet:
@@ -74,15 +79,20 @@ def _annotate(image, label, confidence):
     return image
 
 
-def _read_images(paths):
-    images = []
-    for path in paths:
-        image = cv2.imread(path)
-        if image is None:
-            # the reference dies in center_crop (network.py:138) on an unreadable file; keep the exception type
-            raise AttributeError("'NoneType' object has no attribute 'shape' (cv2.imread failed on %s)" % path)
-        images.append(image)
-    return images
+def _read_image(path):
+    image = cv2.imread(path)
+    if image is None:
+        # the reference dies in center_crop (network.py:138) on an unreadable file; keep the exception type
+        raise AttributeError("'NoneType' object has no attribute 'shape' (cv2.imread failed on %s)" % path)
+    return image
+
+
+def _emit(path, image, target_dir, name, label, confidence, overlay):
+    """Output side of one file (reference infer.py:86-95)."""
+    if overlay:
+        cv2.imwrite(target_dir + os.sep + name, _annotate(image, label, confidence))
+    else:
+        shutil.copy(path, target_dir)
 
 
 def classify_im_dir(nn, imgs_dir, overlay=True):
@@ -97,23 +107,26 @@ def classify_im_dir(nn, imgs_dir, overlay=True):
     sheet.write(0, 0, 'IMAGE_NAME')
     sheet.write(0, 1, 'PREDICTED_LABEL')
     row = 1
-    for start in range(0, len(paths), BATCH):
-        chunk = paths[start:start + BATCH]
-        images = _read_images(chunk)
-        top1, probs = nn.infer_optimized_batch(images)
-        for path, image, cls, prob in zip(chunk, images, top1, probs):
-            label, confidence = CLASS_LABELS[cls], prob[cls]
-            name = path.split(os.sep)[-1]
-            target_dir = out_dir + os.sep + label
-            print(path, '--->', label, confidence)
-            if overlay:
-                cv2.imwrite(target_dir + os.sep + name, _annotate(image, label, confidence))
-            else:
-                shutil.copy(path, target_dir)
-            sheet.write(row, 0, name)
-            sheet.write(row, 1, label)
-            sheet.write(row, 2, str(confidence))
-            row += 1
+    chunks = [paths[start:start + BATCH] for start in range(0, len(paths), BATCH)]
+    with ThreadPoolExecutor(max_workers=IO_THREADS) as pool:
+        writes = []
+        decoding = [pool.submit(_read_image, path) for path in chunks[0]] if chunks else []
+        for ci, chunk in enumerate(chunks):
+            images = [f.result() for f in decoding]
+            if ci + 1 < len(chunks):  # decode the next batch while this one is on the GPU
+                decoding = [pool.submit(_read_image, path) for path in chunks[ci + 1]]
+            top1, probs = nn.infer_optimized_batch(images)
+            for path, image, cls, prob in zip(chunk, images, top1, probs):
+                label, confidence = CLASS_LABELS[cls], prob[cls]
+                name = path.split(os.sep)[-1]
+                print(path, '--->', label, confidence)
+                writes.append(pool.submit(_emit, path, image, out_dir + os.sep + label, name, label, confidence, overlay))
+                sheet.write(row, 0, name)
+                sheet.write(row, 1, label)
+                sheet.write(row, 2, str(confidence))
+                row += 1
+        for w in writes:
+            w.result()  # surface I/O errors before the table is saved
     workbook.save(xl_fpath)
     return xl_fpath
 

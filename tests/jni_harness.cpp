@@ -20,9 +20,10 @@
 
 namespace {
 struct FakeObject {
-  enum Kind { kClass, kString, kFloatArray, kObjectArray, kDirectBuffer } kind;
+  enum Kind { kClass, kString, kFloatArray, kObjectArray, kDirectBuffer, kIntArray } kind;
   std::string str;                 // class name or string chars
   std::vector<float> floats;       // float[]
+  std::vector<jint> ints;          // int[]
   std::vector<FakeObject*> elems;  // Object[]
   void* buf = nullptr;             // direct ByteBuffer
   long long cap = 0;
@@ -52,6 +53,7 @@ const char* GetStringUTFChars(JNIEnv*, jstring s, jboolean* is_copy) {
 void ReleaseStringUTFChars(JNIEnv*, jstring, const char*) {}
 jsize GetArrayLength(JNIEnv*, jarray a) {
   auto* o = reinterpret_cast<FakeObject*>(a);
+  if (o->kind == FakeObject::kIntArray) return static_cast<jsize>(o->ints.size());
   return o->kind == FakeObject::kFloatArray ? static_cast<jsize>(o->floats.size()) : static_cast<jsize>(o->elems.size());
 }
 jobject GetObjectArrayElement(JNIEnv*, jobjectArray a, jsize i) {
@@ -62,6 +64,13 @@ void SetFloatArrayRegion(JNIEnv*, jfloatArray a, jsize start, jsize len, const j
   auto* o = reinterpret_cast<FakeObject*>(a);
   std::copy(src, src + len, o->floats.begin() + start);
 }
+int g_int_pins = 0;
+jint* GetIntArrayElements(JNIEnv*, jintArray a, jboolean* is_copy) {
+  if (is_copy) *is_copy = 0;
+  ++g_int_pins;
+  return reinterpret_cast<FakeObject*>(a)->ints.data();
+}
+void ReleaseIntArrayElements(JNIEnv*, jintArray, jint*, jint) { --g_int_pins; }
 void* GetDirectBufferAddress(JNIEnv*, jobject b) {
   auto* o = reinterpret_cast<FakeObject*>(b);
   return o->kind == FakeObject::kDirectBuffer ? o->buf : nullptr;
@@ -92,6 +101,8 @@ int main(int argc, char** argv) {
   table.slot[kJniGetArrayLength] = reinterpret_cast<void*>(&GetArrayLength);
   table.slot[kJniGetObjectArrayElement] = reinterpret_cast<void*>(&GetObjectArrayElement);
   table.slot[kJniSetFloatArrayRegion] = reinterpret_cast<void*>(&SetFloatArrayRegion);
+  table.slot[kJniGetIntArrayElements] = reinterpret_cast<void*>(&GetIntArrayElements);
+  table.slot[kJniReleaseIntArrayElements] = reinterpret_cast<void*>(&ReleaseIntArrayElements);
   table.slot[kJniGetDirectBufferAddress] = reinterpret_cast<void*>(&GetDirectBufferAddress);
   table.slot[kJniGetDirectBufferCapacity] = reinterpret_cast<void*>(&GetDirectBufferCapacity);
   JNIEnv env = &table;
@@ -104,9 +115,10 @@ int main(int argc, char** argv) {
 #define SYM(name) dlsym(lib, "Java_org_tensorflow_lite_examples_classification_tflite_RoomNetNative_" name)
   auto create = reinterpret_cast<jlong (*)(JNIEnv*, jclass, jstring, jint, jint, jint)>(SYM("create"));
   auto run = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jobject, jobjectArray)>(SYM("run"));
+  auto run_argb = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jintArray, jobjectArray)>(SYM("runArgb"));
   auto close_fn = reinterpret_cast<void (*)(JNIEnv*, jclass, jlong)>(SYM("close"));
   auto stats = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jfloatArray)>(SYM("stats"));
-  CHECK(create && run && close_fn && stats, "JNI symbols");
+  CHECK(create && run && run_argb && close_fn && stats, "JNI symbols");
 
   const std::string mode = argv[3];
   FakeObject prefix{FakeObject::kString};
@@ -128,6 +140,12 @@ int main(int argc, char** argv) {
   bbuf.buf = bimg.data();
   bbuf.cap = static_cast<long long>(bimg.size());
 
+  // Bitmap.getPixels view of the same image: 0xFF000000 | R << 16 | G << 8 | B
+  FakeObject ints{FakeObject::kIntArray};
+  ints.ints.resize(static_cast<size_t>(S) * S);
+  for (size_t i = 0; i < ints.ints.size(); ++i)
+    ints.ints[i] = static_cast<jint>(0xFF000000u | (bimg[3 * i] << 16) | (bimg[3 * i + 1] << 8) | bimg[3 * i + 2]);
+
   if (mode == "errors") {
     FakeObject missing{FakeObject::kString};
     missing.str = "/nonexistent/roomnet";
@@ -140,6 +158,9 @@ int main(int argc, char** argv) {
     g_thrown_class.clear();
     jint rc = run(&env, nullptr, 0, reinterpret_cast<jobject>(&fbuf), reinterpret_cast<jobjectArray>(&out));
     CHECK(rc != 0 && g_thrown_class == "java/lang/IllegalStateException", "run on a closed classifier");
+    g_thrown_class.clear();
+    rc = run_argb(&env, nullptr, 0, reinterpret_cast<jintArray>(&ints), reinterpret_cast<jobjectArray>(&out));
+    CHECK(rc != 0 && g_thrown_class == "java/lang/IllegalStateException", "runArgb on a closed classifier");
     close_fn(&env, nullptr, 0);  // closing twice / closing null is a no-op like Classifier.close()
     CHECK(g_local_refs == 0, "local reference leak");
     std::printf("JNI error paths OK\n");
@@ -167,6 +188,18 @@ int main(int argc, char** argv) {
   std::printf("probs_u8  %.6f %.6f %.6f %.6f %.6f %.6f\n", pb[0], pb[1], pb[2], pb[3], pb[4], pb[5]);
   CHECK(std::abs(sum - 1.f) < 1e-4f, "probabilities sum to 1");
   CHECK(maxdiff < 5e-3f, "float and uint8 ByteBuffer feeds agree");
+  rc = run_argb(&env, nullptr, h, reinterpret_cast<jintArray>(&ints), reinterpret_cast<jobjectArray>(&out));
+  CHECK(rc == 0 && g_int_pins == 0, "argb run");
+  std::vector<float> pa = row.floats;
+  float maxdiff_a = 0;
+  for (int i = 0; i < 6; ++i) maxdiff_a = std::max(maxdiff_a, std::abs(pa[i] - pb[i]));
+  std::printf("probs_argb %.6f %.6f %.6f %.6f %.6f %.6f\n", pa[0], pa[1], pa[2], pa[3], pa[4], pa[5]);
+  CHECK(maxdiff_a < 1e-3f, "int[] (Bitmap.getPixels) and uint8 ByteBuffer feeds agree");
+  FakeObject short_ints{FakeObject::kIntArray};
+  short_ints.ints.assign(10, 0);
+  g_thrown_class.clear();
+  rc = run_argb(&env, nullptr, h, reinterpret_cast<jintArray>(&short_ints), reinterpret_cast<jobjectArray>(&out));
+  CHECK(rc != 0 && g_thrown_class == "java/lang/IllegalArgumentException", "intValues length check");
   FakeObject bad{FakeObject::kDirectBuffer};
   bad.buf = fimg.data();
   bad.cap = 100;

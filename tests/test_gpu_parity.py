@@ -71,6 +71,13 @@ def test_feed_variants_agree(capi, ckpt_prefix, suite64, oracle32, precision):
     assert np.abs(l0 - l2).max() <= TOL[precision]
     ref = oracle32.forward(x)
     assert np.abs(l2 - ref["logits"]).max() <= TOL[precision]
+    # Bitmap.getPixels ints (0xAARRGGBB; Classifier.java:226-243): B,G,R,A bytes in memory = the BGR feed at a
+    # 4-byte pixel pitch -> bit-identical to the u8 BGR result whatever the alpha byte holds
+    bgr = imgs.astype(np.uint32)
+    alpha = np.random.default_rng(3).integers(0, 256, imgs.shape[:3]).astype(np.uint32)
+    argb = ((alpha << 24) | (bgr[..., 2] << 16) | (bgr[..., 1] << 8) | bgr[..., 0]).astype(np.uint32).view(np.int32)
+    t3, p3, l3 = h.infer_argb8888(argb, want_logits=True)
+    assert np.array_equal(t3, t0) and np.array_equal(l3, l0) and np.array_equal(p3, p0)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
