@@ -121,13 +121,12 @@ def test_error_behaviour(capi, ckpt_prefix):
     assert e.value.code == capi.RN_ERR_CUDA
 
 
-@pytest.mark.parametrize("side", [300])
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("side,precision", [(300, "fp32"), (300, "fp16"), (600, "fp16")])
 def test_other_resolutions(capi, ckpt_prefix, weights, precision, side):
     """README's alternate resolutions with a synthesised dense/kernel (BASELINE config 4)."""
     from oracle.roomnet_oracle import RoomNetOracle, synthetic_dense0, synthetic_suite
     d0 = synthetic_dense0(side)
-    imgs = synthetic_suite(4, side)
+    imgs = synthetic_suite(4 if side <= 300 else 2, side)
     orc = RoomNetOracle(im_side=side, dtype=np.float32, weights=weights, dense0_kernel=d0, conv_backend="torch")
     ref = orc.forward(orc.normalise(imgs))
     h = capi.Handle(im_side=side, precision=precision)
@@ -138,6 +137,45 @@ def test_other_resolutions(capi, ckpt_prefix, weights, precision, side):
     print("side %d %s: max|dlogit| %.3e" % (side, precision, err))
     assert np.array_equal(top1, ref["argmax"])
     assert err <= TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp16"])
+def test_full_size_batches_are_periodic(capi, ckpt_prefix, suite64, golden, precision):
+    """BASELINE configs 2/3 at their full sizes through a size-independent property: a batch that tiles the
+    64-image suite must reproduce the suite's logits bit for bit at every position (device-resident batch 256 on two
+    streams; 2,048 host images in micro-batches of 256), and those must match the golden vectors."""
+    import torch
+    h = _handle(capi, ckpt_prefix, precision, max_batch=256)
+    _, _, base = h.infer_u8_bgr(suite64, want_logits=True)
+    assert np.abs(base - golden["logits"]).max() <= TOL[precision]
+    # config 2: 256 images resident on the device
+    d_in = torch.from_numpy(np.ascontiguousarray(np.tile(suite64, (4, 1, 1, 1)))).cuda()
+    d_top1 = torch.empty(256, dtype=torch.int64, device="cuda")
+    d_probs = torch.empty(256, 6, device="cuda")
+    d_logits = torch.empty(256, 6, device="cuda")
+    h.infer_u8_bgr_device(d_in.data_ptr(), 256, d_top1.data_ptr(), d_probs.data_ptr(), d_logits.data_ptr(), None)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_logits.cpu().numpy(), np.tile(base, (4, 1)))
+    assert np.array_equal(d_top1.cpu().numpy(), np.tile(golden["argmax"], 4))
+    # config 3 (one GPU's share): 2,048 host images
+    big = np.tile(suite64, (32, 1, 1, 1))
+    top1, probs, logits = h.infer_u8_bgr(big, want_logits=True)
+    assert np.array_equal(logits, np.tile(base, (32, 1)))
+    assert np.array_equal(top1, np.tile(golden["argmax"], 32))
+    np.testing.assert_allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_replicas_on_two_gpus_are_bit_identical(capi, ckpt_prefix, suite64):
+    """the batch is split contiguously over the replicas; results must not depend on the split."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    one = _handle(capi, ckpt_prefix, "fp16", devices=(0,))
+    two = _handle(capi, ckpt_prefix, "fp16", devices=(0, 1))
+    imgs = np.tile(suite64, (5, 1, 1, 1))[:301]  # odd count: uneven split
+    _, p1, l1 = one.infer_u8_bgr(imgs, want_logits=True)
+    _, p2, l2 = two.infer_u8_bgr(imgs, want_logits=True)
+    assert np.array_equal(l1, l2) and np.array_equal(p1, p2)
 
 
 def test_drop_in_roomnet_class(ckpt_prefix, suite64, golden):
