@@ -1012,11 +1012,11 @@ constexpr int kTailMaxSide = 24;
 
 __device__ __forceinline__ void tail_conv_pool(const float* __restrict__ in, int S, const float* __restrict__ w,
                                                const float* __restrict__ bias, float* __restrict__ conv,
-                                               float* __restrict__ pooled, float* s_w) {
-  // in: [16][S][S] channel-major; conv: [16][S-2][S-2]; pooled: [16][P][P], P = (S-2-4)/2+1
+                                               float* __restrict__ pooled, const float* __restrict__ s_w) {
+  // in: [16][S][S] channel-major; conv: [16][S-2][S-2]; pooled: [16][P][P], P = (S-2-4)/2+1; s_w: the layer's
+  // [9][16][16] weights, already in shared memory (`w` unused: kept for the signature of the callers' tables)
+  (void)w;
   const int CS = S - 2, P = (CS - 4) / 2 + 1;
-  for (int i = threadIdx.x; i < 9 * 16 * 16; i += blockDim.x) s_w[i] = w[i];
-  __syncthreads();
   for (int item = threadIdx.x; item < CS * CS * 4; item += blockDim.x) {
     const int g = item / (CS * CS), px = item % (CS * CS);
     const int y = px / CS, x = px % CS;
@@ -1058,8 +1058,36 @@ __global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __rest
   float* s_p8 = s_conv + 16 * (S - 2) * (S - 2);     // [16][S8][S8]
   float* s_p9 = s_p8 + 16 * S8 * S8;                 // [16][S9][S9]
   float* s_flat = s_p9 + 16 * S9 * S9;               // [S9*S9*16] NHWC order
-  float* s_w = s_flat + 16 * S9 * S9;                // [9*16*16]
+  float* s_w8 = s_flat + 16 * S9 * S9;               // [9*16*16]
+  float* s_w9 = s_w8 + 9 * 16 * 16;                  // [9*16*16]
+  float* s_dw = s_w9 + 9 * 16 * 16;                  // dense kernels [in][out], layer after layer, then the biases
+  const DenseParams& dp = tp.dense;
   const int n = blockIdx.x;
+  // Everything the image needs comes in with ONE round of global loads (the input map, both conv kernels and the
+  // dense head): at batch 1 this kernel is pure latency, and every later phase then runs out of shared memory.
+  for (int i = threadIdx.x; i < 9 * 16 * 16; i += blockDim.x) {
+    s_w8[i] = tp.w8[i];
+    s_w9[i] = tp.w9[i];
+  }
+  int dw_off[5];
+  dw_off[0] = 0;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) {
+    const int cnt = (l == 0 ? tp.flat_len : dp.out[l - 1]) * dp.out[l];
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) s_dw[dw_off[l] + i] = dp.w[l][i];
+    dw_off[l + 1] = dw_off[l] + cnt;
+  }
+  float* s_db = s_dw + dw_off[4];
+  int db_off[4];
+  {
+    int o = 0;
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      db_off[l] = o;
+      for (int i = threadIdx.x; i < dp.out[l]; i += blockDim.x) s_db[o + i] = dp.b[l][i];
+      o += dp.out[l];
+    }
+  }
   // chunked 16-bit [y][cb(2)][x][8] -> channel-major fp32, true scale
   const uint16_t* src = p7 + static_cast<size_t>(n) * S * S * kTailC;
   for (int i = threadIdx.x; i < S * S * kTailC; i += blockDim.x) {
@@ -1075,8 +1103,8 @@ __global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __rest
     s_in[((cb * 8 + e) * S + y) * S + x] = f * tp.in_scale;
   }
   __syncthreads();
-  tail_conv_pool(s_in, S, tp.w8, tp.b8, s_conv, s_p8, s_w);
-  tail_conv_pool(s_p8, S8, tp.w9, tp.b9, s_conv, s_p9, s_w);
+  tail_conv_pool(s_in, S, tp.w8, tp.b8, s_conv, s_p8, s_w8);
+  tail_conv_pool(s_p8, S8, tp.w9, tp.b9, s_conv, s_p9, s_w9);
   if (dbg8)
     for (int i = threadIdx.x; i < 16 * S8 * S8; i += blockDim.x) {  // NHWC for the parity tests
       const int c = i % 16, px = i / 16;
@@ -1102,25 +1130,25 @@ __global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __rest
   // dense head on warp 0 (same arithmetic as dense_tail_kernel in kernels_f32.cu)
   if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x;
-  const DenseParams& dp = tp.dense;
   float v = 0.f;
   {
     const int on = dp.out[0];
     if (lane < on) {
       float acc = 0.f;
-      for (int r = 0; r < tp.flat_len; ++r) acc = fmaf(s_flat[r], dp.w[0][static_cast<size_t>(r) * on + lane], acc);
-      v = relu6f(acc + dp.b[0][lane]);
+      for (int r = 0; r < tp.flat_len; ++r) acc = fmaf(s_flat[r], s_dw[r * on + lane], acc);
+      v = relu6f(acc + s_db[db_off[0] + lane]);
     }
   }
 #pragma unroll
   for (int l = 1; l < 4; ++l) {
     const int in = dp.out[l - 1], on = dp.out[l];
+    const float* wl = s_dw + dw_off[l];
     float acc = 0.f;
     for (int r = 0; r < in; ++r) {
       float xr = __shfl_sync(0xffffffffu, v, r);
-      if (lane < on) acc = fmaf(xr, dp.w[l][r * on + lane], acc);
+      if (lane < on) acc = fmaf(xr, wl[r * on + lane], acc);
     }
-    if (lane < on) acc += dp.b[l][lane];
+    if (lane < on) acc += s_db[db_off[l] + lane];
     v = relu6f(acc);
   }
   const int C = dp.out[3];
@@ -1233,10 +1261,11 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   const int groups = (N + SEG - 1) / SEG;
   // Row blocks: items are dealt round-robin to the persistent CTAs, so the kernel lasts as long as the CTA with the
   // most items.  Pick the split that minimises (items per CTA, rounded up) x (conv rows per item + pipeline refill),
-  // keeping >= 8 pooled rows per item; a finer split evens out the last round, a coarser one saves halo rows.
+  // keeping >= 2 pooled rows per item; a finer split evens out the last round (and, for a handful of images, is
+  // what spreads the work over the SMs at all), a coarser one saves halo rows.
   {
     const int ctas = std::max(1, 148 / L.cout_parts);
-    const int max_nrb = std::max(1, p.out_side / 8);
+    const int max_nrb = std::max(1, p.out_side / 2);
     long best_cost = -1;
     int best_rows = p.out_side;
     for (int nrb = 1; nrb <= max_nrb; ++nrb) {
@@ -1444,7 +1473,8 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
                       float* dbg9, cudaStream_t st) {
   TailParams tp{w8, b8, w9, b9, ja, jb, jc, dp, S7, in_scale, flat_len};
   const int S8 = (S7 - 2 - 4) / 2 + 1, S9 = (S8 - 2 - 4) / 2 + 1;
-  const size_t floats = 16 * S7 * S7 + 16 * (S7 - 2) * (S7 - 2) + 16 * S8 * S8 + 2 * 16 * S9 * S9 + 9 * 16 * 16;
+  size_t floats = 16 * S7 * S7 + 16 * (S7 - 2) * (S7 - 2) + 16 * S8 * S8 + 2 * 16 * S9 * S9 + 2 * 9 * 16 * 16;
+  for (int l = 0; l < 4; ++l) floats += static_cast<size_t>(l == 0 ? flat_len : dp.out[l - 1]) * dp.out[l] + dp.out[l];
   const size_t bytes = floats * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(bytes));
