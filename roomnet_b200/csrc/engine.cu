@@ -453,7 +453,17 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
   // micro-batch is small; the rest are as large as possible (kernel efficiency) while still alternating between
   // the two staging slots / activation sets so that copies overlap the previous micro-batch's kernels.
   std::vector<int> sizes;
-  if (n >= 128) {
+  if (const char* sched = std::getenv("RN_SCHED")) {  // experiments: explicit micro-batch sizes "a,b,c" (rest: max_batch_)
+    int rest = n;
+    for (const char* q = sched; *q && rest > 0;) {
+      const int m = std::min(rest, std::min(max_batch_, std::max(1, std::atoi(q))));
+      sizes.push_back(m);
+      rest -= m;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    for (; rest > 0; rest -= std::min(rest, max_batch_)) sizes.push_back(std::min(rest, max_batch_));
+  } else if (n >= 128) {
     const int first = std::min(max_batch_, std::max(32, n / 4));
     sizes.push_back(first);
     int rest = n - first;
