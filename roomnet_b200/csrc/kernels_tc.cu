@@ -1480,7 +1480,9 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
                                        static_cast<int>(bytes));
   if (e != cudaSuccess) return e;
   // small batches: one image per CTA is latency-critical -> 1024 threads; large batches: 256 threads, more CTAs per SM
-  tail_fused_kernel<<<N, N <= 32 ? 1024 : 256, bytes, st>>>(static_cast<const uint16_t*>(p7), tp, kind == HalfKind::kBF16, top1, probs,
+  // one CTA per image: as many threads as keeps every CTA of the launch resident in one wave (148 SMs)
+  const int tail_threads = N <= 148 ? 1024 : (N <= 296 ? 512 : 256);
+  tail_fused_kernel<<<N, tail_threads, bytes, st>>>(static_cast<const uint16_t*>(p7), tp, kind == HalfKind::kBF16, top1, probs,
                                            logits, dbg8, dbg9);
   return cudaGetLastError();
 }
