@@ -688,6 +688,13 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             jpl[k] = *reinterpret_cast<const uint4*>(a);
             jpr[k] = *reinterpret_cast<const uint4*>(a + jdx);
           }
+          // ... and pull the rows of the iteration after that towards L1/L2 (two source rows further down), so that
+          // the register loads above rarely see a DRAM round trip
+          const int row2 = min(first_row + 3, it.npo - 1);
+          const int y2 = min(static_cast<int>(static_cast<float>(it.po0 + max(row2, 0)) * p.res_scale) + 1, p.res_side - 1);
+          const uint8_t* a2 = jsrc + static_cast<uint32_t>(y2) * jrow_bytes;
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a2));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(a2 - jrow_bytes));
         }
       };
       if constexpr (kJoinPreload) join_preload(-LAG);
