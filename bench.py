@@ -43,6 +43,23 @@ def conv_flops(layer_idx: int, side: int = 224) -> int:
     return 2 * t["conv"] * t["conv"] * chans[layer_idx + 1] * 9 * chans[layer_idx]
 
 
+def conv_bytes(layer_idx: int, side: int = 224) -> int:
+    """Algorithmic HBM bytes of one image through one layer kernel of the 16-bit path: input tensor + output tensor
+    (+ the residual source of the fused joins, conv2d_3 <- pool_1, conv2d_5 <- pool_4), 2 bytes per element; conv0's
+    input is the 16-byte-per-pixel pair-chunk tensor written by prep_u8."""
+    from oracle.roomnet_oracle import CONV_BLOCKS, spatial_trace
+    tr = spatial_trace(side)
+    chans = [3]
+    for (f, _, _, _, d) in CONV_BLOCKS:
+        chans += [f] * d
+    t = tr[layer_idx]
+    b = (t["inp"] ** 2 * (16 if layer_idx == 0 else 2 * chans[layer_idx])) + t["out"] ** 2 * 2 * chans[layer_idx + 1]
+    join_src = {3: 1, 5: 4}.get(layer_idx)
+    if join_src is not None:
+        b += tr[join_src]["out"] ** 2 * 2 * chans[join_src + 1]
+    return b
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -275,14 +292,27 @@ def main():
                             "whole_path": {"achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
                                            "frac": value / world * FLOP_PER_IMAGE_224 / 1e12 / peaks["tflops"]},
                             "kernels_ms_per_step": {p["name"]: round(p["ms"] / args.steps, 4) for p in prof}}
-                # every tensor-core layer kernel against the same peak (algorithmic conv FLOPs only)
+                # every tensor-core layer kernel against the same tensor peak (algorithmic conv FLOPs only), plus its
+                # algorithmic HBM bytes against the measured copy bandwidth: layers whose arithmetic intensity is
+                # below peak_flops / peak_bw (213 FLOP/B) are bound by the second number in a layer-by-layer design
                 per_kernel = {}
+                layerwise_ms = 0.0
                 for q in prof:
                     mq = re.match(r"conv(\d+)_tc$", q["name"])
                     if mq:
-                        tf = conv_flops(int(mq.group(1))) * B * args.steps / (q["ms"] * 1e-3) / 1e12
-                        per_kernel[q["name"]] = {"tflops": round(tf, 1), "frac": round(tf / peaks["tflops"], 4)}
+                        li = int(mq.group(1))
+                        secs = q["ms"] * 1e-3 / (B * args.steps)  # per image
+                        tf = conv_flops(li) / secs / 1e12
+                        gbs = conv_bytes(li) / secs / 1e9
+                        per_kernel[q["name"]] = {"tflops": round(tf, 1), "frac": round(tf / peaks["tflops"], 4),
+                                                 "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm"], 4)}
+                        layerwise_ms += max(conv_flops(li) / (peaks["tflops"] * 1e12),
+                                            conv_bytes(li) / (peaks["hbm"] * 1e9)) * B * 1e3
                 roofline["per_kernel"] = per_kernel
+                roofline["hbm"] = {"kernel": top["name"], "achieved": per_kernel[top["name"]]["hbm_gbs"],
+                                   "peak": peaks["hbm"], "unit": "GB/s", "frac": per_kernel[top["name"]]["hbm_frac"],
+                                   "note": "same kernel against the HBM roof (algorithmic in+out+residual bytes)"}
+                roofline["layer_by_layer_floor_ms"] = round(layerwise_ms, 4)
         cpu = None
         if not args.no_cpu_baseline:
             ips, cores, p50 = cpu_reference_throughput(64)
