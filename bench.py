@@ -33,31 +33,7 @@ BATCH_PER_GPU = 256
 N_INPUT_SETS = 4  # 4 x 38.5 MB of distinct uint8 inputs > 126 MB L2
 
 
-def conv_flops(layer_idx: int, side: int = 224) -> int:
-    from oracle.roomnet_oracle import CONV_BLOCKS, spatial_trace
-    tr = spatial_trace(side)
-    chans = [3]
-    for (f, _, _, _, d) in CONV_BLOCKS:
-        chans += [f] * d
-    t = tr[layer_idx]
-    return 2 * t["conv"] * t["conv"] * chans[layer_idx + 1] * 9 * chans[layer_idx]
-
-
-def conv_bytes(layer_idx: int, side: int = 224) -> int:
-    """Algorithmic HBM bytes of one image through one layer kernel of the 16-bit path: input tensor + output tensor
-    (+ the residual source of the fused joins, conv2d_3 <- pool_1, conv2d_5 <- pool_4), 2 bytes per element; conv0's
-    input is the 16-byte-per-pixel pair-chunk tensor written by prep_u8."""
-    from oracle.roomnet_oracle import CONV_BLOCKS, spatial_trace
-    tr = spatial_trace(side)
-    chans = [3]
-    for (f, _, _, _, d) in CONV_BLOCKS:
-        chans += [f] * d
-    t = tr[layer_idx]
-    b = (t["inp"] ** 2 * (16 if layer_idx == 0 else 2 * chans[layer_idx])) + t["out"] ** 2 * 2 * chans[layer_idx + 1]
-    join_src = {3: 1, 5: 4}.get(layer_idx)
-    if join_src is not None:
-        b += tr[join_src]["out"] ** 2 * 2 * chans[join_src + 1]
-    return b
+from roomnet_b200.workload import conv_bytes, conv_flops  # noqa: E402  (product-side tables, no oracle/)
 
 
 def load_peaks():
@@ -169,8 +145,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from oracle.roomnet_oracle import synthetic_suite
-    from oracle.tf_bundle import default_checkpoint_prefix
+    from roomnet_b200.workload import default_checkpoint_prefix, synthetic_suite
     from roomnet_b200 import _capi
     from roomnet_b200.sharding import aggregate_throughput, reduce_max
 

@@ -15,6 +15,9 @@ struct DenseParams {
   int out[4];
 };
 
+// Number of SMs of the current device (148 on B200; cached per device) - grids are sized in multiples of it.
+int SmCount();
+
 // ---- fp32 CUDA-core kernels (kernels_f32.cu) --------------------------------
 template <typename TIn>
 cudaError_t Conv3x3Relu6F32(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin,

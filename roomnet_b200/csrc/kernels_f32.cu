@@ -10,6 +10,18 @@
 
 namespace rn {
 
+int SmCount() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
 namespace {
 
 __device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
@@ -264,7 +276,7 @@ cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst
 cudaError_t AvgPoolF32(const float* in, float* out, int N, int H, int W, int C, int k, int s, cudaStream_t st) {
   int OH = (H - k) / s + 1, OW = (W - k) / s + 1;
   size_t total = static_cast<size_t>(N) * OH * OW * C;
-  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   avgpool_kernel<<<blocks, 256, 0, st>>>(in, out, N, H, W, C, k, s, OH, OW);
   return cudaGetLastError();
 }
@@ -272,7 +284,7 @@ cudaError_t AvgPoolF32(const float* in, float* out, int N, int H, int W, int C, 
 cudaError_t JoinF32(const float* p, const float* src, float* out, const float* A, const float* B, const float* C,
                     int N, int S, int SS, int Ch, cudaStream_t st) {
   size_t total = static_cast<size_t>(N) * S * S * Ch;
-  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   join_kernel<<<blocks, 256, 0, st>>>(p, src, out, A, B, C, N, S, SS, Ch);
   return cudaGetLastError();
 }

@@ -1305,7 +1305,7 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   // keeping >= 2 pooled rows per item; a finer split evens out the last round (and, for a handful of images, is
   // what spreads the work over the SMs at all), a coarser one saves halo rows.
   {
-    const int ctas = std::max(1, 148 / L.cout_parts);
+    const int ctas = std::max(1, SmCount() / L.cout_parts);
     const int max_nrb = std::max(1, p.out_side / 2);
     long best_cost = -1;
     int best_rows = p.out_side;
@@ -1336,7 +1336,7 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   // per device (replicas of several GPUs share the process), and cheap enough to repeat
   cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return ea;
-  const int gx = std::max(1, std::min(p.n_items, 148 / L.cout_parts));
+  const int gx = std::max(1, std::min(p.n_items, SmCount() / L.cout_parts));
   dim3 grid(gx, L.cout_parts);
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
@@ -1461,7 +1461,7 @@ size_t PackTcConv0Weights(const double* w, HalfKind kind, double scale, void* ou
 
 cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st, int px_bytes) {
   size_t total = static_cast<size_t>(N) * S * S;
-  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   prep_u8_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint4*>(out), N, S, kind == HalfKind::kBF16, px_bytes);
   return cudaGetLastError();
 }
@@ -1522,8 +1522,9 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
                                        static_cast<int>(bytes));
   if (e != cudaSuccess) return e;
   // small batches: one image per CTA is latency-critical -> 1024 threads; large batches: 256 threads, more CTAs per SM
-  // one CTA per image: as many threads as keeps every CTA of the launch resident in one wave (148 SMs)
-  const int tail_threads = N <= 148 ? 1024 : (N <= 296 ? 512 : 256);
+  // one CTA per image: as many threads as keeps every CTA of the launch resident in one wave
+  const int sms = SmCount();
+  const int tail_threads = N <= sms ? 1024 : (N <= 2 * sms ? 512 : 256);
   e = LaunchPdl(tail_fused_kernel, dim3(N), dim3(tail_threads), bytes, st, N, static_cast<const uint16_t*>(p7), tp,
                 static_cast<int>(kind == HalfKind::kBF16), top1, probs, logits, dbg8, dbg9);
   if (e != cudaSuccess) return e;
@@ -1533,7 +1534,7 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
 cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale,
                          cudaStream_t st) {
   size_t total = static_cast<size_t>(N) * S * S * Ch;
-  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, 148 * 16));
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   chunked_to_f32_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(in), out, N, S, Ch,
                                                 kind == HalfKind::kBF16, scale);
   return cudaGetLastError();

@@ -111,3 +111,20 @@ def _read_biff2(path):
             cells[(row, col)] = body[8:8 + n].decode("latin-1")
         pos += 4 + ln
     return cells
+
+
+def test_workload_module_matches_the_oracle_generators():
+    """bench.py / tools use roomnet_b200.workload (no oracle import on the product side); its generators and shape
+    tables must be byte-identical to the oracle's, or the golden fixtures would not describe the benchmark inputs."""
+    import numpy as np
+    from oracle import roomnet_oracle as orc
+    from roomnet_b200 import workload as wl
+    for seed in range(12):
+        for side in (224, 300):
+            assert np.array_equal(wl.synthetic_image(seed, side), orc.synthetic_image(seed, side))
+    assert np.array_equal(wl.synthetic_dense0(300), orc.synthetic_dense0(300))
+    for side in (224, 300, 600):
+        assert wl.spatial_trace(side) == orc.spatial_trace(side) and wl.flat_len(side) == orc.flat_len(side)
+    # SURVEY §8d: 4,486,392,000 conv FLOPs per 224x224 image
+    assert sum(wl.conv_flops(i) for i in range(10)) == 4_486_392_000
+    assert wl.conv_bytes(3) == 210 * 210 * 64 + 205 * 205 * 64 + 215 * 215 * 64

@@ -10,8 +10,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from oracle.roomnet_oracle import synthetic_suite  # noqa: E402
-from oracle.tf_bundle import default_checkpoint_prefix  # noqa: E402
+from roomnet_b200.workload import default_checkpoint_prefix, synthetic_suite  # noqa: E402
 from roomnet_b200 import _capi  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -23,7 +22,7 @@ args = ap.parse_args()
 
 h = _capi.Handle(precision=args.precision, im_side=args.side, max_batch=args.batch)
 if args.side != 224:
-    from oracle.roomnet_oracle import synthetic_dense0
+    from roomnet_b200.workload import synthetic_dense0
     h.set_dense0(synthetic_dense0(args.side))
 h.load_tf_checkpoint(default_checkpoint_prefix())
 imgs = synthetic_suite(64, args.side)[np.arange(args.batch) % 64]

@@ -4,8 +4,7 @@ import numpy as np
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 import torch
-from oracle.roomnet_oracle import synthetic_suite
-from oracle.tf_bundle import default_checkpoint_prefix
+from roomnet_b200.workload import default_checkpoint_prefix, synthetic_suite
 from roomnet_b200 import _capi
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 steps = 10
