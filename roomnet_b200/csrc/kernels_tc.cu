@@ -575,29 +575,45 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         // this warp's critical path; mbarrier arrive/wait are release/acquire, so the ordering is transitive).
         mbar_wait(bar_full0 + 8u * st, ph);
         tc_fence_after();
+        // Interior pair (both rows carry all three dy taps) whose six accumulator slots do not wrap around the ring:
+        // everything but the stage and slot base is a compile-time constant - 12 bare MMAs.
+        const uint32_t sb0 = (G + r0 - 2) & (R - 1);
+        if (r0 >= 2 && r0 + 2 <= it.nconv && sb0 + 4 <= static_cast<uint32_t>(R)) {
+          const uint32_t a0 = a_lo0 + st * (Cfg::kStageBytes >> 4);
+          const uint32_t d0 = tmem_base + sb0 * COUT;
+          constexpr uint32_t kIdescFull = static_cast<uint32_t>((3 * COUT) >> 3) << 17;
 #pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-          const int r = r0 + sub;
-          const int jlo = max(0, 2 - r);  // j = 2 - dy ; conv row y = r - 2 + j
-          const int jhi = min(2, it.nconv + 1 - r);
-          const uint32_t sb = (G + r - 2 + jlo) & (R - 1);
-          const int nj = jhi - jlo + 1;
-          const int len1 = min(nj, R - static_cast<int>(sb));  // slots before the ring wraps
-          const uint32_t a_lo = a_lo0 + st * (Cfg::kStageBytes >> 4) + sub * (Cfg::kRowBytes >> 4);
-          {
-            const uint32_t d = tmem_base + sb * COUT;
-            const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
-            const uint32_t b_lo = b_lo0 + jlo * COUT;
+          for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+            tc_mma_acc1(d0, a0 + Cfg::a_off16(ks), b_lo0 + Cfg::b_off16(ks), kDescHi, idesc0 | kIdescFull);
 #pragma unroll
-            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-              tc_mma_acc1(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
-          }
-          if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
-            const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
-            const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
+          for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+            tc_mma_acc1(d0 + COUT, a0 + (Cfg::kRowBytes >> 4) + Cfg::a_off16(ks), b_lo0 + Cfg::b_off16(ks), kDescHi,
+                        idesc0 | kIdescFull);
+        } else {
 #pragma unroll
-            for (int ks = 0; ks < Cfg::kKSteps; ++ks)
-              tc_mma_acc1(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+          for (int sub = 0; sub < 2; ++sub) {
+            const int r = r0 + sub;
+            const int jlo = max(0, 2 - r);  // j = 2 - dy ; conv row y = r - 2 + j
+            const int jhi = min(2, it.nconv + 1 - r);
+            const uint32_t sb = (G + r - 2 + jlo) & (R - 1);
+            const int nj = jhi - jlo + 1;
+            const int len1 = min(nj, R - static_cast<int>(sb));  // slots before the ring wraps
+            const uint32_t a_lo = a_lo0 + st * (Cfg::kStageBytes >> 4) + sub * (Cfg::kRowBytes >> 4);
+            {
+              const uint32_t d = tmem_base + sb * COUT;
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>((len1 * COUT) >> 3) << 17);
+              const uint32_t b_lo = b_lo0 + jlo * COUT;
+#pragma unroll
+              for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+                tc_mma_acc1(d, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+            }
+            if (len1 < nj) {  // ring wrap: the remaining conv rows start again at slot 0
+              const uint32_t idesc = idesc0 | (static_cast<uint32_t>(((nj - len1) * COUT) >> 3) << 17);
+              const uint32_t b_lo = b_lo0 + (jlo + len1) * COUT;
+#pragma unroll
+              for (int ks = 0; ks < Cfg::kKSteps; ++ks)
+                tc_mma_acc1(tmem_base, a_lo + Cfg::a_off16(ks), b_lo + Cfg::b_off16(ks), kDescHi, idesc);
+            }
           }
         }
         tc_commit(bar_empty0 + 8u * st);
