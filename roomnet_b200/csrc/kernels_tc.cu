@@ -89,6 +89,15 @@ __device__ __forceinline__ void tma_tensor4_g2s(uint32_t dst, const CUtensorMap*
 // the successor grid start launching as SMs become free.  Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// 5-D variant: the extra dimension is the image, for tiles that hold two windows of two images
+__device__ __forceinline__ void tma_tensor5_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], "
+      "[%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -403,7 +412,7 @@ __device__ __forceinline__ void join_hlerp(const uint8_t* row, uint32_t dx_bytes
 template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
 __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
-  static_assert(POOL == 0 || SEG == 1, "windowed (pooled) tiles hold one image");
+  static_assert(POOL == 0 || SEG == 1 || POOL == 42, "two-image windowed tiles exist for 4x4/2 pooling only");
   using HH = H2<BF16>;
   constexpr int R = Cfg::kSlots;
   constexpr int LOGR = Cfg::kLogSlots;
@@ -499,7 +508,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const Item it = decode_item<POOL, SEG>(p, item);
           const int nin = it.nconv + 2;  // even
-          int row = it.n0 * p.in_side + it.c0;
+          // SEG == 1: rows of all images form one dimension; SEG == 2: (image, row) are separate dimensions
+          int row = SEG == 2 ? it.c0 : it.n0 * p.in_side + it.c0;
           for (int r = 0; r < nin; r += 2, row += 2) {
             if (r < it.nconv) {  // see the MMA issuer: the accumulators this input pair starts must be free
               const uint32_t gy = Gp + r;
@@ -508,7 +518,10 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             mbar_wait(bar_empty0 + 8u * st, ph);
             const uint32_t full = bar_full0 + 8u * st;
             mbar_arrive_expect_tx(full, kStageTx);
-            tma_tensor4_g2s(stage0 + st * Cfg::kStageBytes, &tmap, 0, 4 * it.strip, 0, row, full);
+            if constexpr (SEG == 2)  // two windows of images n0, n0 + 1 (past the batch / the image: zero fill)
+              tma_tensor5_g2s(stage0 + st * Cfg::kStageBytes, &tmap, 0, 0, it.n0, 0, row, full);
+            else
+              tma_tensor4_g2s(stage0 + st * Cfg::kStageBytes, &tmap, 0, 4 * it.strip, 0, row, full);
             if (++st == NST) {
               st = 0;
               ph ^= 1;
@@ -1309,7 +1322,7 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
     // a 32-lane window yields 30 valid conv columns (taps of lanes 30/31 cross into the next window)
     p.win_step_out = POOL == 41 ? 27 : (POOL == 31 ? 28 : 14);
     p.win_step_in = POOL == 42 ? 2 * p.win_step_out : p.win_step_out;
-    const int wins = 4;
+    const int wins = SEG == 2 ? 2 : 4;  // SEG == 2: the tile is 2 windows x 2 images
     p.strip_step_out = wins * p.win_step_out;
     p.strip_step_in = wins * p.win_step_in;
     if (SEG == 2 && p.out_side > p.strip_step_out) return cudaErrorInvalidValue;
@@ -1367,6 +1380,21 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
       if (ee != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) return cudaErrorNotSupported;
       encode = reinterpret_cast<PFN_encodeTiled>(fn);
     }
+    if (SEG == 2) {
+      // {window elements | window | image | plane | row of the image}; box = 2 windows x 2 images x all planes x 2 rows,
+      // which lands in shared memory as [row][plane][image][window]: lane quadrant = 2 * image + window
+      const cuuint64_t row_bytes = static_cast<cuuint64_t>(CB) * p.in_side * 16;
+      const cuuint64_t gdim5[5] = {256, 2, static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(CB),
+                                   static_cast<cuuint64_t>(p.in_side)};
+      const cuuint64_t gstr5[4] = {static_cast<cuuint64_t>(p.win_step_in) * 16, row_bytes * p.in_side,
+                                   static_cast<cuuint64_t>(p.in_side) * 16, row_bytes};
+      const cuuint32_t box5[5] = {256, 2, 2, static_cast<cuuint32_t>(CB), 2};
+      const cuuint32_t estr5[5] = {1, 1, 1, 1, 1};
+      CUresult cr5 = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, const_cast<uint8_t*>(p.in), gdim5, gstr5, box5, estr5,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (cr5 != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    } else {
     const cuuint64_t gdim[4] = {256, static_cast<cuuint64_t>(4 * p.n_strips), static_cast<cuuint64_t>(CB),
                                 static_cast<cuuint64_t>(N) * p.in_side};
     const cuuint64_t gstr[3] = {static_cast<cuuint64_t>(p.win_step_in) * 16, static_cast<cuuint64_t>(p.in_side) * 16,
@@ -1379,6 +1407,7 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
   }
   if (const char* d = std::getenv("RN_TC_DBG")) p.dbg = std::atoi(d);
   cudaError_t el = LaunchPdl(kern, grid, dim3(tc_threads(CREAL)), Cfg::kSmemBytes, st, N, p, tmap);
@@ -1498,7 +1527,8 @@ cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfK
                       : launch_tc<8, 64, 42, 1, 0>(L, in, out, N, kind, st);
   if (cb == 8 && cp == 64 && pool == 0)
     return seg2 ? launch_tc<8, 64, 0, 2, 0>(L, in, out, N, kind, st) : launch_tc<8, 64, 0, 1, 0>(L, in, out, N, kind, st);
-  if (cb == 16 && cp == 16 && pool == 42) return launch_tc<16, 16, 42, 1, 0>(L, in, out, N, kind, st);
+  if (cb == 16 && cp == 16 && pool == 42)
+    return seg2 ? launch_tc<16, 16, 42, 2, 0>(L, in, out, N, kind, st) : launch_tc<16, 16, 42, 1, 0>(L, in, out, N, kind, st);
   return cudaErrorInvalidValue;
 }
 
