@@ -89,6 +89,13 @@ __device__ __forceinline__ void tma_tensor4_g2s(uint32_t dst, const CUtensorMap*
 // the successor grid start launching as SMs become free.  Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): issued a few row pairs ahead of the load itself
+__device__ __forceinline__ void tma_prefetch4(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // 5-D variant: the extra dimension is the image, for tiles that hold two windows of two images
 __device__ __forceinline__ void tma_tensor5_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
                                                 int c4, uint32_t bar) {
@@ -425,6 +432,10 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
   // POOL != 0: the 128 lanes are four 32-pixel windows that overlap in the image (each window carries its own
   // pooling halo), so no epilogue warp ever needs a neighbour quadrant's columns.  POOL == 0: one contiguous run.
   constexpr bool kWindows = POOL != 0;
+  // L2 prefetch distance of the TMA producer in row pairs (0 = off).  Measured per layer: it helps the tensor-bound
+  // 32->64 layer (0.333 -> 0.315 ms per 256 images) and costs 2-7 % on the layers that already run near the HBM or
+  // issue limits, so only that instantiation uses it.
+  constexpr int kPrefetchPairs = (CB == 4 && COUT == 64 && !JOIN) ? 6 : 0;
   constexpr uint32_t kStageTx = 2 * (kWindows ? CB * 4 * 32 * 16 : CB * (SEG == 1 ? kLoadPx * 16 : 2 * SEGW * 16));
   constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1, SWIZZLE_NONE
 
@@ -518,10 +529,15 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             mbar_wait(bar_empty0 + 8u * st, ph);
             const uint32_t full = bar_full0 + 8u * st;
             mbar_arrive_expect_tx(full, kStageTx);
-            if constexpr (SEG == 2)  // two windows of images n0, n0 + 1 (past the batch / the image: zero fill)
+            if constexpr (SEG == 2) {  // two windows of images n0, n0 + 1 (past the batch / the image: zero fill)
               tma_tensor5_g2s(stage0 + st * Cfg::kStageBytes, &tmap, 0, 0, it.n0, 0, row, full);
-            else
+            } else {
               tma_tensor4_g2s(stage0 + st * Cfg::kStageBytes, &tmap, 0, 4 * it.strip, 0, row, full);
+              // the ring lets this thread run 7 row pairs ahead of the epilogue; the rows after that are pulled into L2
+              // now, so that the load itself rarely waits for HBM
+              if (kPrefetchPairs > 0 && r + 2 * kPrefetchPairs < nin)
+                tma_prefetch4(&tmap, 0, 4 * it.strip, 0, row + 2 * kPrefetchPairs);
+            }
             if (++st == NST) {
               st = 0;
               ph ^= 1;
