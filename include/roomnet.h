@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RN_ABI_VERSION 1
+#define RN_ABI_VERSION 2
 #define RN_MAX_DEVICES 16
 
 typedef struct rn_handle rn_handle;
@@ -45,6 +45,14 @@ enum rn_precision {
   RN_PREC_BF16 = 2   /* same kernels with bf16 operands; measured to MISS the 2e-2 budget on flat images */
 };
 
+enum rn_flags {
+  /* Run the 16-bit path layer by layer (one kernel per conv layer, every activation written to HBM) instead of
+   * the fused residual-block kernel.  Same arithmetic; exists so that rn_debug_activation can return the
+   * intermediate tensors of a fused block (tf.Session.run can fetch any graph node, network.py:131) and for A/B
+   * timing.  Not the benchmarked configuration. */
+  RN_FLAG_LAYERWISE = 1
+};
+
 /* Replaces the constructor arguments of the reference model object:
  *   RoomNet(num_classes, im_side, ..., optimized_inference=True)   network.py:21-48
  * plus what TensorFlow decided implicitly (device placement, network.py:89). */
@@ -57,6 +65,7 @@ typedef struct rn_config {
                                        0 = host-only handle (load + fold only; inference returns RN_ERR_CUDA) */
   int32_t devices[RN_MAX_DEVICES];  /* CUDA ordinals */
   int32_t max_batch;                /* per-replica micro-batch held resident on the device (0 = default) */
+  int32_t flags;                    /* bit set of rn_flags (0 = default) */
 } rn_config;
 
 /* network.py:21-48 (graph construction) + network.py:87-91 (session creation). */

@@ -13,7 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libroomnet.so")
 
-RN_ABI_VERSION = 1
+RN_ABI_VERSION = 2
+RN_FLAG_LAYERWISE = 1
 RN_MAX_DEVICES = 16
 
 RN_OK, RN_ERR_INVALID_ARG, RN_ERR_IO, RN_ERR_FORMAT, RN_ERR_NOT_LOADED, RN_ERR_CUDA, RN_ERR_INTERNAL = range(7)
@@ -36,6 +37,7 @@ class RnConfig(C.Structure):
         ("n_devices", C.c_int32),
         ("devices", C.c_int32 * RN_MAX_DEVICES),
         ("max_batch", C.c_int32),
+        ("flags", C.c_int32),
     ]
 
 
@@ -89,7 +91,7 @@ EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors
 class Handle:
     """Thin RAII wrapper over rn_handle."""
 
-    def __init__(self, im_side=224, num_classes=6, precision="fp16", devices=(0,), max_batch=0):
+    def __init__(self, im_side=224, num_classes=6, precision="fp16", devices=(0,), max_batch=0, layerwise=False):
         cfg = RnConfig()
         cfg.abi_version = RN_ABI_VERSION
         cfg.im_side = im_side
@@ -100,6 +102,7 @@ class Handle:
         for i, d in enumerate(devices):
             cfg.devices[i] = d
         cfg.max_batch = max_batch
+        cfg.flags = RN_FLAG_LAYERWISE if layerwise else 0
         self.im_side, self.num_classes = im_side, num_classes
         self._h = C.c_void_p()
         rc = lib.rn_create(C.byref(cfg), C.byref(self._h))

@@ -140,7 +140,7 @@ int rn_create(const rn_config* cfg, rn_handle** out) {
   }
   h->cfg.max_batch = mb;
   for (int i = 0; i < cfg->n_devices; ++i) {
-    auto r = std::make_unique<rn::Replica>(cfg->devices[i], h->shape, cfg->precision, mb);
+    auto r = std::make_unique<rn::Replica>(cfg->devices[i], h->shape, cfg->precision, mb, cfg->flags);
     if (r->Init() != cudaSuccess) {
       g_create_error = r->error();
       return RN_ERR_CUDA;

@@ -25,8 +25,9 @@ size_t InputBytesPerImage(const NetShape& s, InputKind k) {
 }
 }  // namespace
 
-Replica::Replica(int device, const NetShape& shape, int precision, int max_batch)
+Replica::Replica(int device, const NetShape& shape, int precision, int max_batch, int flags)
     : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
+  layerwise_ = (flags & RN_FLAG_LAYERWISE) != 0;
   half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
   first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
   fuse_join_ = std::getenv("RN_NO_FUSED_JOIN") == nullptr;
@@ -330,6 +331,14 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const void* in = shape_.conv[i - 1].join_src >= 0 ? cur_->join_h[i - 1] : cur_->act_h[i - 1];
+    if (i == 2 && !layerwise_ && fuse_join_ && shape_.conv[3].join_src == 1 && Block2FusedSupported(tc_[2], tc_[3])) {
+      // residual block 2 in one kernel: conv2d_2's output stays in shared memory (kernels_block2.cu)
+      RN_CUDA(Block2Fused(tc_[2], tc_[3], cur_->act_h[1], cur_->join_h[3], n, half_kind_, st));
+      Mark("block2_tc", st);
+      block2_fused_last_ = true;
+      i = 3;
+      continue;
+    }
     if (cs.join_src >= 0 && fuse_join_) {
       TcConvLayer L = tc_[i];
       L.join_src = cur_->act_h[cs.join_src];
@@ -605,6 +614,10 @@ cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dim
   RN_CUDA(cudaSetDevice(device_));
   if (layer < 0 || layer >= kNumConvs || cur_->last_n <= 0) {
     err_ = "no activation recorded for that layer";
+    return cudaErrorInvalidValue;
+  }
+  if (layer == 2 && block2_fused_last_ && precision_ != RN_PREC_FP32) {
+    err_ = "conv2d_2's output stays on-chip in the fused residual-block kernel; create the handle with RN_FLAG_LAYERWISE";
     return cudaErrorInvalidValue;
   }
   const ConvShape& cs = shape_.conv[layer];

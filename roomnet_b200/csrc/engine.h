@@ -19,7 +19,7 @@ size_t InputBytesPerPixel(InputKind k);
 
 class Replica {
  public:
-  Replica(int device, const NetShape& shape, int precision, int max_batch);
+  Replica(int device, const NetShape& shape, int precision, int max_batch, int flags = 0);
   ~Replica();
   Replica(const Replica&) = delete;
   Replica& operator=(const Replica&) = delete;
@@ -122,7 +122,10 @@ class Replica {
   ActSet* cur_ = &sets_[0];
   cudaEvent_t ev_fork_ = nullptr;
   int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
-  bool fuse_join_ = true;    // residual joins fused into the conv epilogue (RN_NO_FUSED_JOIN=1 keeps the separate kernel)
+  bool fuse_join_ = true;    // residual joins fused into the conv epilogue (RN_NO_FUSED_JOIN=1, read once at construction,
+                             // keeps the separate join kernel: parity cross-check only)
+  bool layerwise_ = false;   // RN_FLAG_LAYERWISE: no fused residual-block kernel
+  bool block2_fused_last_ = false;  // the last forward pass ran residual block 2 as one kernel
 
   // preprocessing scratch (raw image + tap tables), grown on demand
   uint8_t* d_raw_ = nullptr;

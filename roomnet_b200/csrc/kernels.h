@@ -70,6 +70,14 @@ cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cu
 
 cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st);
 
+// Residual block 2 (conv2d_2 -> conv2d_3 + join, reference network.py:183-203 / :227) as one kernel
+// (kernels_block2.cu): `l1`, `l2` are the TcConvLayer records of the two layers as ConvTc would take them
+// (l2.join_abc / join_src_side describe the join; the residual source is `in` itself), `in` = the block's first
+// pooled tensor, `out` = the joined block output.  P2 (the tensor between the layers) never reaches HBM.
+bool Block2FusedSupported(const TcConvLayer& l1, const TcConvLayer& l2);
+cudaError_t Block2Fused(const TcConvLayer& l1, const TcConvLayer& l2, const void* in, void* out, int N, HalfKind kind,
+                        cudaStream_t st);
+
 // conv0 (3->8, CUDA cores, fp32 math) + ReLU6 + 3x3/1 avg-pool, writes chunked 16-bit.
 template <typename TIn>
 cudaError_t Conv0PoolH(const TIn* in, const float* w, const float* b, void* out, int N, int S, HalfKind kind,

@@ -1,0 +1,351 @@
+// Shared device helpers of the sm_100a tensor-core kernels (kernels_tc.cu, kernels_block2.cu): inline-PTX wrappers
+// for mbarrier / TMA / tcgen05, the shared-memory + TMEM configuration of one conv layer and packed 16-bit math.
+#pragma once
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+
+namespace rn {
+namespace {
+
+constexpr int kTileM = 128;           // pixels per row tile (UMMA M)
+constexpr int kPlanePx = 136;         // pixels per channel-chunk plane in a smem stage
+constexpr int kLoadPx = 132;          // pixels fetched per plane row (128 + taps, 16B multiple)
+constexpr int kSlackBytes = 128 * 1024;  // over-read slack behind every chunked tensor (row tails + one padding row)
+constexpr int kSmemBudget = 227 * 1024;
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+// 4-D tiled TMA load (cp.async.bulk.tensor): box -> shared memory, completion on an mbarrier
+__device__ __forceinline__ void tma_tensor4_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::
+          "r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start (and
+// run its prologue: barrier init, TMEM allocation, weight loads) while its predecessor in the stream is still
+// draining; pdl_wait() blocks until the predecessor grid has completed and its writes are visible, pdl_trigger() lets
+// the successor grid start launching as SMs become free.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// L2 prefetch of a 4-D box (no shared-memory destination, no barrier): issued a few row pairs ahead of the load itself
+__device__ __forceinline__ void tma_prefetch4(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// 5-D variant: the extra dimension is the image, for tiles that hold two windows of two images
+__device__ __forceinline__ void tma_tensor5_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                                int c4, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], "
+      "[%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// kind::f16 instruction descriptor: D=f32, A/B = f16 (0) or bf16 (1), both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc(int n, int bf16) {
+  return (1u << 4) | (static_cast<uint32_t>(bf16) << 7) | (static_cast<uint32_t>(bf16) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+}
+
+__device__ __forceinline__ float relu6f(float v) { return fminf(fmaxf(v, 0.f), 6.f); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float unpack_lo(uint32_t v, int bf16) {
+  if (bf16) return __bfloat162float(reinterpret_cast<__nv_bfloat162*>(&v)->x);
+  return __half2float(reinterpret_cast<__half2*>(&v)->x);
+}
+__device__ __forceinline__ float unpack_hi(uint32_t v, int bf16) {
+  if (bf16) return __bfloat162float(reinterpret_cast<__nv_bfloat162*>(&v)->y);
+  return __half2float(reinterpret_cast<__half2*>(&v)->y);
+}
+
+// POOL modes: 0 = none, 31 = 3x3/1, 41 = 4x4/1, 42 = 4x4/2.  The kernel stores the window SUM of
+// saturate(conv/6): the factors k*k and 6 are folded into the consumer's weights by the host.
+// AMODE: 0 = channel-chunk planes (Cin >= 16), 1 = Cin 8: pixel pairs form a K=16 step (LBO = 16 B),
+//        2 = conv0: a 16-byte chunk holds pixels (x, x+1) x (c0,c1,c2,0); chunks x and x+2 (LBO = 32 B) form one
+//            K=16 step that covers all three dx taps; the two k-steps are the hi and lo halves of the weights
+template <int CB, int COUT, int AMODE, bool WINDOWS>
+struct TcCfg {
+  // windowed tiles are written by one tiled TMA box [CB][4 windows][32 px][8] -> dense 128-pixel planes
+  static constexpr int kPlanePxT = WINDOWS ? 128 : kPlanePx;
+  static constexpr int kPlaneBytesT = kPlanePxT * 16;
+  static constexpr int kPlanes = AMODE == 0 ? 3 * CB : 4;       // weight planes
+  static constexpr int kKSteps = AMODE == 0 ? 3 * (CB / 2) : 2; // MMAs per input row
+  static constexpr int kSlots = (512 / COUT) > 16 ? 16 : (512 / COUT);
+  static constexpr int kLogSlots = kSlots == 16 ? 4 : 3;
+  static_assert(kSlots == 16 || kSlots == 8, "ring size must be a power of two");
+  static constexpr int kTmemCols = kSlots * COUT;
+  static constexpr int kWBytes = kPlanes * 3 * COUT * 16;
+  static constexpr int kRowBytes = CB * kPlaneBytesT;                       // one input row, all planes
+  static constexpr int kStageBytes = 2 * kRowBytes + (WINDOWS ? 128 : 0);  // a stage holds a PAIR of input rows (+ tap over-read pad)
+  static constexpr int kFixedBytes = kWBytes + 4 * COUT * 4 + 1024;  // bias + join A/B/C
+  static constexpr int kStagesFit = (kSmemBudget - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
+  static_assert(kStages >= 2, "not enough shared memory for a double-buffered input ring");
+  // descriptor offsets (in 16-byte units) of k-step ks relative to the stage / weight base
+  __host__ __device__ static constexpr uint32_t a_off16(int ks) {
+    return AMODE == 0 ? static_cast<uint32_t>((2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * kPlanePxT + ks / (CB / 2 > 0 ? CB / 2 : 1))
+           : AMODE == 1 ? static_cast<uint32_t>(2 * ks)
+                        : 0u;
+  }
+  __host__ __device__ static constexpr uint32_t b_off16(int ks) {
+    return AMODE == 0 ? static_cast<uint32_t>(((ks / (CB / 2 > 0 ? CB / 2 : 1)) * CB + 2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * 3 * COUT)
+                      : static_cast<uint32_t>(2 * ks * 3 * COUT);
+  }
+  static constexpr uint32_t kALbo16 = AMODE == 0 ? kPlanePxT : (AMODE == 1 ? 1 : 2);  // K-direction core-matrix stride / 16
+  static constexpr uint32_t kBLbo16 = 3 * COUT;
+};
+
+template <bool BF16>
+struct H2 {
+  __device__ static __forceinline__ uint32_t pack(float a, float b) {
+    if constexpr (BF16) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+      __half2 h = __floats2half2_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    }
+  }
+  __device__ static __forceinline__ float2 unpack(uint32_t v) {
+    if constexpr (BF16) {
+      return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
+    } else {
+      return __half22float2(*reinterpret_cast<__half2*>(&v));
+    }
+  }
+  __device__ static __forceinline__ uint32_t splat(float x) { return pack(x, x); }
+  __device__ static __forceinline__ uint32_t sub(uint32_t a, uint32_t b) {
+    if constexpr (BF16) {
+      __nv_bfloat162 r = __hsub2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    } else {
+      __half2 r = __hsub2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  __device__ static __forceinline__ uint32_t fma(uint32_t a, uint32_t b, uint32_t c) {  // a*b + c, single rounding
+    if constexpr (BF16) {
+      __nv_bfloat162 r = __hfma2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b),
+                                 *reinterpret_cast<__nv_bfloat162*>(&c));
+      return *reinterpret_cast<uint32_t*>(&r);
+    } else {
+      __half2 r = __hfma2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b),
+                          *reinterpret_cast<__half2*>(&c));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  __device__ static __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+    if constexpr (BF16) {
+      __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    } else {
+      __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+  __device__ static __forceinline__ uint32_t sixteenth(uint32_t a) {  // exact: power-of-two scale
+    if constexpr (BF16) {
+      __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), __floats2bfloat162_rn(0.0625f, 0.0625f));
+      return *reinterpret_cast<uint32_t*>(&r);
+    } else {
+      __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), __floats2half2_rn(0.0625f, 0.0625f));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+  }
+};
+
+// Warp-converged call: one elected lane issues D[tmem] += A[smem] * B[smem].  elect.sync (not `lane == 0`) lets ptxas
+// emit ELECT + a predicated UTCHMMA instead of a per-active-lane serialisation loop around every MMA.
+// Same elected lane (deterministic for a full mask) commits: arrive on `bar` once all its prior MMAs completed.
+// variants for code that already runs on a single elected thread
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, q;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_mma_acc1(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi,
+                                            uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
+  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM load width");
+  uint32_t r[N];
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr));
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+  } else if constexpr (N == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N>
+__device__ __forceinline__ void tc_st(uint32_t taddr, const float* v) {
+  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM store width");
+#define RN_U(i) "r"(__float_as_uint(v[i]))
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), RN_U(0), RN_U(1), RN_U(2),
+                 RN_U(3)
+                 : "memory");
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), RN_U(0),
+                 RN_U(1), RN_U(2), RN_U(3), RN_U(4), RN_U(5), RN_U(6), RN_U(7)
+                 : "memory");
+  } else if constexpr (N == 16) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+            taddr),
+        RN_U(0), RN_U(1), RN_U(2), RN_U(3), RN_U(4), RN_U(5), RN_U(6), RN_U(7), RN_U(8), RN_U(9), RN_U(10), RN_U(11),
+        RN_U(12), RN_U(13), RN_U(14), RN_U(15)
+        : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+        "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        RN_U(0), RN_U(1), RN_U(2), RN_U(3), RN_U(4), RN_U(5), RN_U(6), RN_U(7), RN_U(8), RN_U(9), RN_U(10), RN_U(11),
+        RN_U(12), RN_U(13), RN_U(14), RN_U(15), RN_U(16), RN_U(17), RN_U(18), RN_U(19), RN_U(20), RN_U(21), RN_U(22),
+        RN_U(23), RN_U(24), RN_U(25), RN_U(26), RN_U(27), RN_U(28), RN_U(29), RN_U(30), RN_U(31)
+        : "memory");
+  }
+#undef RN_U
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// warp 0 TMA producer, warp 1 MMA issuer, then 4 epilogue warps (TMEM lane quadrants) per channel group
+__host__ __device__ constexpr int tc_groups(int creal) { return creal >= 32 ? 4 : 2; }
+__host__ __device__ constexpr int tc_threads(int creal) { return 64 + 128 * tc_groups(creal); }
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait): the kernel may be scheduled while its
+// predecessor in the stream is finishing.  Used for small batches only (measured: batch-1 latency 0.167 -> 0.140 ms);
+// with large micro-batches on two streams a pre-launched CTA would sit on an SM (shared memory, TMEM) that the other
+// stream's kernels could have used (end-to-end throughput -3 %).
+constexpr int kPdlMaxBatch = 32;
+template <typename... KArgs, typename... Args>
+cudaError_t LaunchPdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int batch,
+                      Args... args) {
+  const bool enabled = batch <= kPdlMaxBatch;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = enabled ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
+using PFN_encodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (no -lcuda); resolved once, thread-safe
+// (launches are issued concurrently from one host thread per replica).
+inline PFN_encodeTiled GetEncodeTiled() {
+  static std::once_flag once;
+  static PFN_encodeTiled fn_cached = nullptr;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t ee = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (ee == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn) fn_cached = reinterpret_cast<PFN_encodeTiled>(fn);
+  });
+  return fn_cached;
+}
+
+}  // namespace
+}  // namespace rn

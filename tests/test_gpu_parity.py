@@ -44,7 +44,8 @@ def test_per_layer_activations(capi, ckpt_prefix, suite64, weights, precision):
     from oracle.fold import fold, folded_forward
     imgs = suite64[:4]
     ref = folded_forward(fold(weights), imgs, dtype=np.float64, conv_backend="torch", collect=True)["tensors"]
-    h = _handle(capi, ckpt_prefix, precision)
+    # conv2d_2's output never leaves the SM in the fused residual-block kernel: the layer-by-layer flag materialises it
+    h = _handle(capi, ckpt_prefix, precision, layerwise=True)
     h.infer_u8_bgr(imgs)
     for layer in range(10):
         got = h.debug_activation(layer)
@@ -54,6 +55,32 @@ def test_per_layer_activations(capi, ckpt_prefix, suite64, weights, precision):
         rel = np.abs(got - want).max() / scale
         print("layer %d %s max rel err %.3e (absmax %.3f)" % (layer, got.shape, rel, scale))
         assert rel <= (2e-5 if precision == "fp32" else 6e-3), "layer %d" % layer
+
+
+def test_fused_block2_matches_layerwise_kernels(capi, ckpt_prefix, suite64, weights):
+    """Residual block 2 as ONE kernel (conv2d_2 -> conv2d_3 + join, P2 on-chip) performs the same arithmetic as the
+    layer-by-layer kernels: the block output must agree bit for bit for every batch size / row-block split, and stay
+    inside the per-layer budget against the folded fp64 oracle."""
+    from oracle.fold import fold, folded_forward
+    ref = folded_forward(fold(weights), suite64[:4], dtype=np.float64, conv_backend="torch", collect=True)["tensors"]
+    for n in (1, 3, 4, 37):
+        imgs = suite64[:n]
+        outs = []
+        for lw in (True, False):
+            h = _handle(capi, ckpt_prefix, "fp16", layerwise=lw, max_batch=64)
+            t, p, l = h.infer_u8_bgr(imgs, want_logits=True)
+            outs.append((h.debug_activation(3), l, h.kernel_launches))
+            if not lw:
+                with pytest.raises(capi.RoomNetError):
+                    h.debug_activation(2)  # not materialised
+        assert outs[1][2] < outs[0][2], "the fused handle must launch fewer kernels"
+        assert np.array_equal(outs[0][0], outs[1][0]), "n=%d: block output differs from the layer-by-layer kernels" % n
+        assert np.array_equal(outs[0][1], outs[1][1])
+        if n == 4:
+            want = ref[3]
+            rel = np.abs(outs[1][0] - want).max() / (np.abs(want).max() + 1e-6)
+            print("fused block 2 output vs fp64 folded oracle: max rel err %.3e" % rel)
+            assert rel <= 6e-3
 
 
 @pytest.mark.parametrize("precision", ["fp32", "fp16"])
