@@ -33,7 +33,82 @@ BATCH_PER_GPU = 256
 N_INPUT_SETS = 4  # 4 x 38.5 MB of distinct uint8 inputs > 126 MB L2
 
 
-from roomnet_b200.workload import conv_bytes, conv_flops  # noqa: E402  (product-side tables, no oracle/)
+# NOTE: nothing from roomnet_b200 is imported at module level: `--impl reference` must not map the product's
+# shared libraries (the package import loads libroomnet.so through ctypes).
+
+
+def kernel_layers(name):
+    """Conv layers a profiled kernel covers: convN_tc -> [N]; block2_tc = the fused conv2d_2 -> conv2d_3 + join."""
+    if name == "block2_tc":
+        return [2, 3]
+    m = re.match(r"conv(\d+)_tc$", name)
+    return [int(m.group(1))] if m else []
+
+
+def block2_bytes(side=224):
+    """Algorithmic HBM bytes per image of the fused block: read R2 once, write the joined output (16-bit)."""
+    from roomnet_b200.workload import channels, spatial_trace
+    tr, ch = spatial_trace(side), channels()
+    return tr[2]["inp"] ** 2 * 2 * ch[2] + tr[3]["out"] ** 2 * 2 * ch[4]
+
+
+def build_roofline(prof, per_gpu_value, ms_dev, args, peaks, B, conv_flops, conv_bytes):
+    """The line's `roofline` object.  Top level = the WHOLE PATH (algorithmic FLOPs of one image x images/s per GPU)
+    against the measured BF16 tensor peak; which peak applies follows the length of the timed region (the burst
+    figure was measured over a sub-second run, the sustained one over seconds under the power cap).  The dominant
+    kernel, every kernel's own fractions, and the DRAM traffic of the committed ncu capture sit beside it."""
+    achieved = per_gpu_value * FLOP_PER_IMAGE_224 / 1e12
+    timed_s = ms_dev * 1e-3
+    burst = timed_s < 1.0
+    peak = peaks["tflops_burst"] if burst else peaks["tflops"]
+    roofline = {
+        "bound": "tensor", "kernel": "whole path (all kernels of one step)", "achieved": achieved, "peak": peak,
+        "unit": "TFLOP/s", "frac": achieved / peak,
+        "frac_burst": achieved / peaks["tflops_burst"], "frac_sustained": achieved / peaks["tflops"],
+        "peak_source": "%s bf16 %s (timed region %.3f s %s 1 s)" % (
+            peaks["source"], "burst" if burst else "sustained", timed_s, "<" if burst else ">="),
+        "traffic": None,
+    }
+    if not prof:
+        return roofline
+    total_ms = sum(q["ms"] for q in prof)
+    roofline["kernels_ms_per_step"] = {q["name"]: round(q["ms"] / args.steps, 4) for q in prof}
+    tc = [q for q in prof if kernel_layers(q["name"])]
+    # DRAM traffic of the whole path from the committed `ncu --set full` capture (bytes per launch of half a batch)
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    ncu = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    key = "dram_bytes_per_launch_b%d" % (B // 2)
+    per_launch = {q["name"]: ncu.get(q["name"], {}).get(key) for q in prof}
+    if prof and all(v is not None for v in per_launch.values()):
+        path_bytes = sum(per_launch.values()) / (B // 2)
+        algorithmic = 224 * 224 * 3 + 24  # SURVEY 8d: uint8 image in, 6 float logits out
+        roofline["traffic"] = sum(per_launch.values()) * 2  # bytes per step (two half-batch launches per kernel)
+        roofline["traffic_path_bytes_per_image"] = round(path_bytes)
+        roofline["traffic_vs_algorithmic"] = round(path_bytes / algorithmic, 1)
+        roofline["traffic_source"] = "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+    if not tc:  # FP32 path: CUDA-core kernels only
+        roofline["note"] = "fp32 CUDA-core path: whole-path FLOP rate against the bf16 tensor peak"
+        return roofline
+    # every tensor-core kernel against the same tensor peak (algorithmic conv FLOPs only) and, on its algorithmic HBM
+    # bytes, against the measured copy bandwidth
+    per_kernel = {}
+    floor_ms = 0.0
+    for q in tc:
+        layers = kernel_layers(q["name"])
+        flops = sum(conv_flops(li) for li in layers)
+        nbytes = block2_bytes() if q["name"] == "block2_tc" else sum(conv_bytes(li) for li in layers)
+        secs = q["ms"] * 1e-3 / (B * args.steps)  # per image
+        per_kernel[q["name"]] = {"tflops": round(flops / secs / 1e12, 1), "frac": round(flops / secs / 1e12 / peak, 4),
+                                 "hbm_gbs": round(nbytes / secs / 1e9, 1),
+                                 "hbm_frac": round(nbytes / secs / 1e9 / peaks["hbm"], 4),
+                                 "share_of_step": round(q["ms"] / total_ms, 4)}
+        floor_ms += max(flops / (peak * 1e12), nbytes / (peaks["hbm"] * 1e9)) * B * 1e3
+    top = max(tc, key=lambda q: q["ms"])
+    roofline["dominant"] = dict(per_kernel[top["name"]], kernel=top["name"], traffic=per_launch.get(top["name"]),
+                                note="largest share of the step; traffic = ncu DRAM bytes per half-batch launch")
+    roofline["per_kernel"] = per_kernel
+    roofline["kernel_by_kernel_floor_ms"] = round(floor_ms, 4)
+    return roofline
 
 
 def load_peaks():
@@ -122,6 +197,59 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def config3_leg(_capi, np, torch, n_gpus, precision, suite, n=8192, reps=3):
+    """BASELINE configs[2]: `n` images from ONE pinned host buffer through ONE handle whose replicas cover g GPUs
+    (contiguous shards, one persistent host worker per replica, logits gathered into one pinned host buffer).
+    Timed end to end on the host clock for g = 1 and g = n_gpus; the logits must be bit-identical for every g."""
+    from roomnet_b200.workload import default_checkpoint_prefix
+    n_gpus = max(1, min(n_gpus, torch.cuda.device_count()))
+    big = torch.from_numpy(np.ascontiguousarray(suite[np.arange(n) % 64])).pin_memory()
+    top1 = torch.empty(n, dtype=torch.int64).pin_memory()
+    probs = torch.empty(n, 6, dtype=torch.float32).pin_memory()
+    logits = torch.empty(n, 6, dtype=torch.float32).pin_memory()
+    out, ref = {"images": n, "reps": reps, "per_g": {}}, None
+    for g in sorted({1, n_gpus}):
+        h = _capi.Handle(precision=precision, devices=tuple(range(g)))
+        h.load_tf_checkpoint(default_checkpoint_prefix())
+        call = lambda: h.infer_raw("rn_infer_u8_bgr", big.data_ptr(), n, top1.data_ptr(), probs.data_ptr(), logits.data_ptr())
+        call()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            call()
+        dt = time.perf_counter() - t0
+        got = logits.numpy().copy()
+        if ref is None:
+            ref = got
+        out["per_g"][str(g)] = {"img_s_e2e": n * reps / dt, "bit_identical_to_g1": bool(np.array_equal(got, ref))}
+        h.close()
+    g1 = out["per_g"]["1"]["img_s_e2e"]
+    top = out["per_g"][str(n_gpus)]
+    out.update(n_gpus=n_gpus, img_s_e2e=top["img_s_e2e"], efficiency_vs_g1=top["img_s_e2e"] / (n_gpus * g1),
+               bit_identical=all(v["bit_identical_to_g1"] for v in out["per_g"].values()),
+               h2d_bytes_per_call=n * 224 * 224 * 3)
+    return out
+
+
+def latency_leg(calls=1000):
+    """BASELINE configs[4]: batch-1 p50/p99 through the JNI shim's run() (fake-JNIEnv harness, no JVM in this image);
+    float ByteBuffer resident on the host, wall clock including H2D/D2H."""
+    harness = os.path.join(ROOT, "build", "jni_harness")
+    lib = os.path.join(ROOT, "roomnet_b200", "libroomnet_jni.so")
+    if not (os.path.exists(harness) and os.path.exists(lib)):
+        return {"unavailable": "build/jni_harness not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    from roomnet_b200.workload import default_checkpoint_prefix
+    try:
+        res = subprocess.run([harness, lib, default_checkpoint_prefix(), "run", str(calls)], capture_output=True, text=True,
+                             timeout=120)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": "harness failed: %r" % (e,)}
+    m = re.search(r"latency_ms p50 ([0-9.]+) p99 ([0-9.]+) calls (\d+)", res.stdout)
+    if res.returncode != 0 or not m:
+        return {"unavailable": "harness exit %d" % res.returncode}
+    return {"p50_ms": float(m.group(1)), "p99_ms": float(m.group(2)), "calls": int(m.group(3)), "via": "jni_shim",
+            "launch": "programmatic dependent launch (PDL) chain, one call = 9 kernels"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -132,6 +260,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--max-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the config-3 (one handle, all GPUs) and batch-1 latency legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -145,7 +274,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from roomnet_b200.workload import default_checkpoint_prefix, synthetic_suite
+    from roomnet_b200.workload import conv_bytes, conv_flops, default_checkpoint_prefix, synthetic_suite
     from roomnet_b200 import _capi
     from roomnet_b200.sharding import aggregate_throughput, reduce_max
 
@@ -238,56 +367,16 @@ def main():
     barrier()
     clocks = sampler.stop()  # sampled across the device-timed, per-kernel and end-to-end regions
 
+    # ---- BASELINE configs[2] and configs[4] on the record (rank 0; the other ranks idle at the barrier) ----
+    config3 = latency_b1 = None
+    if rank == 0 and not args.no_extra_legs:
+        config3 = config3_leg(_capi, np, torch, max(world, args.gpus if world == 1 else world), args.precision, suite)
+        latency_b1 = latency_leg()
+    barrier()
+
     if rank == 0:
         peaks = load_peaks()
-        roofline = None
-        if prof:
-            total_ms = sum(p["ms"] for p in prof)
-            convs = [p for p in prof if p["name"].startswith("conv") and p["name"].endswith("_tc")] or prof
-            top = max(convs, key=lambda p: p["ms"])  # dominant tensor-core kernel
-            m = re.match(r"conv(\d+)_tc$", top["name"])
-            layer = int(m.group(1)) if m else None
-            if layer is None:  # FP32 path: CUDA-core kernels, no tensor-pipe roofline; report the whole path only
-                roofline = {"bound": "tensor", "kernel": top["name"], "achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
-                            "peak": peaks["tflops"], "unit": "TFLOP/s",
-                            "frac": value / world * FLOP_PER_IMAGE_224 / 1e12 / peaks["tflops"], "traffic": None,
-                            "note": "fp32 CUDA-core path: whole-path FLOP rate against the bf16 tensor peak",
-                            "kernels_ms_per_step": {p["name"]: round(p["ms"] / args.steps, 4) for p in prof}}
-            else:
-                flops_per_launch = conv_flops(layer) * B * args.steps / top["launches"]
-                achieved = flops_per_launch / (top["ms"] / top["launches"] * 1e-3) / 1e12
-                traffic = None
-                tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-                if os.path.exists(tpath):  # dram bytes per launch of this kernel from the committed ncu --set full capture
-                    traffic = json.load(open(tpath)).get(top["name"], {}).get("dram_bytes_per_launch_b%d" % (B // 2))
-                roofline = {"bound": "tensor", "kernel": top["name"], "achieved": achieved, "peak": peaks["tflops"],
-                            "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": traffic,
-                            "peak_source": peaks["source"] + " bf16 sustained (kernel timed inside a long step)",
-                            "share_of_step": top["ms"] / total_ms,
-                            "whole_path": {"achieved": value / world * FLOP_PER_IMAGE_224 / 1e12,
-                                           "frac": value / world * FLOP_PER_IMAGE_224 / 1e12 / peaks["tflops"]},
-                            "kernels_ms_per_step": {p["name"]: round(p["ms"] / args.steps, 4) for p in prof}}
-                # every tensor-core layer kernel against the same tensor peak (algorithmic conv FLOPs only), plus its
-                # algorithmic HBM bytes against the measured copy bandwidth: layers whose arithmetic intensity is
-                # below peak_flops / peak_bw (213 FLOP/B) are bound by the second number in a layer-by-layer design
-                per_kernel = {}
-                layerwise_ms = 0.0
-                for q in prof:
-                    mq = re.match(r"conv(\d+)_tc$", q["name"])
-                    if mq:
-                        li = int(mq.group(1))
-                        secs = q["ms"] * 1e-3 / (B * args.steps)  # per image
-                        tf = conv_flops(li) / secs / 1e12
-                        gbs = conv_bytes(li) / secs / 1e9
-                        per_kernel[q["name"]] = {"tflops": round(tf, 1), "frac": round(tf / peaks["tflops"], 4),
-                                                 "hbm_gbs": round(gbs, 1), "hbm_frac": round(gbs / peaks["hbm"], 4)}
-                        layerwise_ms += max(conv_flops(li) / (peaks["tflops"] * 1e12),
-                                            conv_bytes(li) / (peaks["hbm"] * 1e9)) * B * 1e3
-                roofline["per_kernel"] = per_kernel
-                roofline["hbm"] = {"kernel": top["name"], "achieved": per_kernel[top["name"]]["hbm_gbs"],
-                                   "peak": peaks["hbm"], "unit": "GB/s", "frac": per_kernel[top["name"]]["hbm_frac"],
-                                   "note": "same kernel against the HBM roof (algorithmic in+out+residual bytes)"}
-                roofline["layer_by_layer_floor_ms"] = round(layerwise_ms, 4)
+        roofline = build_roofline(prof, value / world, ms_dev, args, peaks, B, conv_flops, conv_bytes)
         cpu = None
         if not args.no_cpu_baseline:
             ips, cores, p50 = cpu_reference_throughput(64)
@@ -310,6 +399,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "config3": config3,
+            "latency_b1": latency_b1,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

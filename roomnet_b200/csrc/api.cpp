@@ -2,7 +2,9 @@
 // interface each entry point replaces).
 #include <algorithm>
 #include <chrono>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -16,10 +18,61 @@
 
 using rn::InputKind;
 
+namespace {
+// One persistent host worker per replica (GPU): a call hands every worker its contiguous shard and waits for all
+// of them; no thread is created on the inference path (one host worker thread + streams per GPU).
+class Worker {
+ public:
+  Worker() : th_([this] { Loop(); }) {}
+  ~Worker() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    th_.join();
+  }
+  void Submit(std::function<void()> fn) {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      task_ = std::move(fn);
+      busy_ = true;
+    }
+    cv_.notify_all();
+  }
+  void Wait() {
+    std::unique_lock<std::mutex> l(mu_);
+    done_cv_.wait(l, [this] { return !busy_; });
+  }
+
+ private:
+  void Loop() {
+    std::unique_lock<std::mutex> l(mu_);
+    for (;;) {
+      cv_.wait(l, [this] { return stop_ || task_; });
+      if (stop_) return;
+      std::function<void()> fn = std::move(task_);
+      task_ = nullptr;
+      l.unlock();
+      fn();
+      l.lock();
+      busy_ = false;
+      done_cv_.notify_all();
+    }
+  }
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  std::function<void()> task_;
+  bool busy_ = false, stop_ = false;
+  std::thread th_;
+};
+}  // namespace
+
 struct rn_handle {
   rn_config cfg{};
   rn::NetShape shape{};
   std::vector<std::unique_ptr<rn::Replica>> replicas;
+  std::vector<std::unique_ptr<Worker>> workers;  // one per replica when there are several (declared after: joins first)
   rn::FoldedNet folded;
   bool loaded = false;
   bool has_dense0 = false;
@@ -76,9 +129,8 @@ int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1
   if (g == 1) {
     run(0);
   } else {
-    std::vector<std::thread> th;
-    for (int r = 0; r < g; ++r) th.emplace_back(run, r);
-    for (auto& t : th) t.join();
+    for (int r = 0; r < g; ++r) h->workers[r]->Submit([&run, r] { run(r); });
+    for (int r = 0; r < g; ++r) h->workers[r]->Wait();
   }
   h->last_launches = 0;
   for (int r = 0; r < g; ++r) {
@@ -132,6 +184,14 @@ int rn_create(const rn_config* cfg, rn_handle** out) {
     g_create_error = err;
     return RN_ERR_INVALID_ARG;
   }
+  if (cfg->max_batch > 4096) {
+    g_create_error = "max_batch out of range (<= 4096 images resident per replica; larger calls are micro-batched anyway)";
+    return RN_ERR_INVALID_ARG;
+  }
+  if (cfg->flags & ~RN_FLAG_LAYERWISE) {
+    g_create_error = "unknown bits in rn_config.flags";
+    return RN_ERR_INVALID_ARG;
+  }
   int mb = cfg->max_batch;
   if (mb <= 0) {
     // resident micro-batch: bounded by activation memory, which grows with im_side^2
@@ -147,6 +207,8 @@ int rn_create(const rn_config* cfg, rn_handle** out) {
     }
     h->replicas.push_back(std::move(r));
   }
+  if (cfg->n_devices > 1)
+    for (int i = 0; i < cfg->n_devices; ++i) h->workers.push_back(std::make_unique<Worker>());
   *out = h.release();
   return RN_OK;
 }

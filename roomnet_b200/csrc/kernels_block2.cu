@@ -21,8 +21,10 @@
 //   * the residual source rows are staged by TMA bulk copies into a small shared-memory ring (8 rows x 112 pixels)
 //     a few row pairs ahead of their use, so the join costs shared-memory loads, not L2 gathers.
 //
-// Warp roles: warp 0 = TMA producer (one thread), warp 1 = MMA issuer (one elected thread, both layers, statically
-// interleaved), warps 2..17 = epilogue: warp (quadrant q, channel group g) owns TMEM lanes 32q..32q+31 and
+// Warp roles (one thread each): warp 0 = TMA producer of the R2 row pairs, warp 1 = MMA issuer of layer 1,
+// warp 2 = TMA producer of the residual rows, warp 3 = MMA issuer of layer 2 - four independent dataflow loops
+// coupled only through mbarriers; this first warp group hands most of its registers to the others (setmaxnreg).
+// Warps 4..19 = epilogue: warp (quadrant q, channel group g) owns TMEM lanes 32q..32q+31 and
 // channels 8g..8g+7 of BOTH layers and alternates between them (layer 2 runs kLagEpi row pairs behind layer 1).
 #include <cstring>
 
@@ -46,13 +48,15 @@ constexpr int kB2ResRowBytes = 4 * kB2ResPlaneBytes;
 constexpr int kB2ResGroups = 4;       // barrier ring of the residual stream (one group = rows of one epilogue-2 step)
 constexpr int kB2StripOut = 103;      // output columns owned by a strip
 constexpr int kB2MaxStrips = 8;
-constexpr int kB2LagMma = 5;          // MMA issuer: layer-2 row pair j is issued together with layer-1 pair j + 5
 constexpr int kB2LagEpi = 5;          // epilogue warps: layer-2 pair m is drained after layer-1 pair m + 5
-constexpr int kB2LagRes = 7;          // producer: residual group m is requested together with R2 pair m + 7
-constexpr int kB2Threads = 64 + 16 * 32;
+constexpr int kB2Threads = 128 + 16 * 32;  // warp group 0: two TMA producers + two MMA issuers; 16 epilogue warps
+// Register budget: 20 warps = 5 per scheduler, 16384 registers per scheduler -> 96 per thread at launch.  The first
+// warp group gives most of its registers back (setmaxnreg.dec), the epilogue warp groups take them (setmaxnreg.inc).
+constexpr int kB2RegsCtl = 32, kB2RegsEpi = 112;
+static_assert(4 * kB2RegsCtl + 16 * kB2RegsEpi <= 20 * 96, "setmaxnreg can only redistribute the registers the CTA was launched with");
 constexpr int kB2Bars = 2 * kB2NS1 + 2 * kB2NS2 + 1 + 4 * kB2RP + 2 * kB2ResGroups;
 constexpr int kB2SmemBytes = 2 * B2Cfg::kWBytes + (kB2NS1 + kB2NS2) * B2Cfg::kStageBytes + kB2ResRows * kB2ResRowBytes +
-                             (2 * 32 + 3 * 32) * 4 + kB2Bars * 8 + 16;
+                             (2 * 32 + 3 * 32) * 4 + kB2ResGroups * 16 + kB2Bars * 8 + 16;
 static_assert(kB2SmemBytes <= kSmemBudget, "block-2 kernel does not fit in shared memory");
 static_assert((kB2NS1 & (kB2NS1 - 1)) == 0 && (kB2NS2 & (kB2NS2 - 1)) == 0, "stage rings are indexed with masks");
 
@@ -74,6 +78,7 @@ struct B2Params {
 
 struct B2Maps {
   CUtensorMap m[kB2MaxStrips];  // per strip: R2 windows {256 el | 4 windows, stride 27 px | 4 planes | N*in_side rows}
+  CUtensorMap res;              // R2 as 8-byte elements {2 * in_side | 4 planes | N*in_side rows}: box = 112 px x 4 planes
 };
 
 struct B2Item {
@@ -99,6 +104,14 @@ __device__ __forceinline__ B2Item b2_decode(const B2Params& p, int item) {
   it.n2s = it.nin2 >> 1;
   it.n2e = it.nconv3 >> 1;
   return it;
+}
+
+__device__ __forceinline__ void tma_tensor3_g2s(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+          "r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
 }
 
 // One row PAIR of a tap-stacked layer: D[rows r0-2 .. r0+1] += A[input rows r0, r0+1] x [W(dy=2)|W(dy=1)|W(dy=0)].
@@ -149,17 +162,28 @@ __device__ __forceinline__ void b2_mma_pair(uint32_t a_lo, uint32_t b_lo0, uint3
   }
 }
 
+// saturate as a volatile statement: keeps ptxas from hoisting the clip of the second row above the in-place window
+// update (it would then need a copy to get the value into the state registers)
+__device__ __forceinline__ float sat_here(float v) {
+  float r;
+  asm volatile("add.sat.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // Drain one accumulator row pair (8 channels of this thread's pixel), hand the slots back pre-loaded with the bias,
-// clip (saturate = ReLU6/6, the factor lives in the weights), advance the vertical 4-row window (fp32 registers) and
-// apply the horizontal 4-column window on packed 16-bit pairs with warp shuffles.
+// clip (saturate = ReLU6/6, the factor lives in the weights), advance the vertical 4-row window and apply the
+// horizontal 4-column window on packed 16-bit pairs with warp shuffles.
 // hp[0] = pooled row (y - 3), hp[1] = pooled row (y - 2) for conv rows (y, y + 1) of this call.
+// The vertical window lives in packed fp32 pairs (add.f32x2: one issue slot per two channels) and is updated in
+// place - U = x(y-1), V = x(y-1) + x(y-2), W = x(y-2) + x(y-3) - with the same association as conv_tc_kernel
+// ((x(y) + x(y-1)) + W, (x(y+1) + x(y)) + V), so the fused block stays bit-identical to the layer-by-layer kernels;
+// recomputing the two partial sums into the state registers costs two adds per channel pair but no register moves.
 template <typename HH>
-__device__ __forceinline__ void b2_drain_pool(uint32_t t_base, uint32_t slot0, uint32_t slot1, const float* s_bias8,
-                                              uint32_t bar_free, int lane, float (&r1)[8], float (&q1)[8], float (&q2)[8],
-                                              uint32_t (&hp)[2][4]) {
+__device__ __forceinline__ void b2_drain_pool(uint32_t t_slot0, const float* s_bias8, uint32_t bar_free, bool lane0,
+                                              f32x2_t (&U)[4], f32x2_t (&V)[4], f32x2_t (&W)[4], uint32_t (&hp)[2][4]) {
   float a[8], b[8];
-  tc_ld<8>(t_base + slot0 * 32, a);
-  tc_ld<8>(t_base + slot1 * 32, b);
+  tc_ld<8>(t_slot0, a);
+  tc_ld<8>(t_slot0 + 32, b);
   tc_wait_ld();
   {
     float bias[8];
@@ -167,33 +191,56 @@ __device__ __forceinline__ void b2_drain_pool(uint32_t t_base, uint32_t slot0, u
     const float4 b1 = *reinterpret_cast<const float4*>(s_bias8 + 4);
     bias[0] = b0.x, bias[1] = b0.y, bias[2] = b0.z, bias[3] = b0.w;
     bias[4] = b1.x, bias[5] = b1.y, bias[6] = b1.z, bias[7] = b1.w;
-    tc_st<8>(t_base + slot0 * 32, bias);
-    tc_st<8>(t_base + slot1 * 32, bias);
+    tc_st<8>(t_slot0, bias);
+    tc_st<8>(t_slot0 + 32, bias);
     tc_wait_st();
   }
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(bar_free);
+  if (lane0) mbar_arrive(bar_free);
+  uint32_t v0[4], v1[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float o0[2], o1[2];
+    const f32x2_t x0 = f2_pack(__saturatef(a[2 * i]), __saturatef(a[2 * i + 1]));
+    const f32x2_t o0 = f2_add(f2_add(x0, U[i]), W[i]);
+    W[i] = f2_add_again(U[i], x0);  // operands swapped: bit-identical, but not the same expression for the compiler
+    U[i] = f2_pack(sat_here(b[2 * i]), sat_here(b[2 * i + 1]));
+    const f32x2_t o1 = f2_add(f2_add(U[i], x0), V[i]);
+    V[i] = f2_add_again(x0, U[i]);
+    float lo, hi;
+    f2_unpack(o0, lo, hi);
+    v0[i] = HH::pack(lo, hi);
+    f2_unpack(o1, lo, hi);
+    v1[i] = HH::pack(lo, hi);
+  }
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int c = 2 * i + e;
-      const float x0 = __saturatef(a[c]), x1 = __saturatef(b[c]);
-      const float qa = x0 + r1[c], qb = x1 + x0;
-      o0[e] = qa + q2[c];
-      o1[e] = qb + q1[c];
-      q2[c] = qa;
-      q1[c] = qb;
-      r1[c] = x1;
-    }
-    const uint32_t v0 = HH::pack(o0[0], o0[1]), v1 = HH::pack(o1[0], o1[1]);
-    const uint32_t t0 = HH::add(v0, __shfl_down_sync(0xffffffffu, v0, 1));
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t t0 = HH::add(v0[i], __shfl_down_sync(0xffffffffu, v0[i], 1));
+    const uint32_t t1 = HH::add(v1[i], __shfl_down_sync(0xffffffffu, v1[i], 1));
     hp[0][i] = HH::add(t0, __shfl_down_sync(0xffffffffu, t0, 2));
-    const uint32_t t1 = HH::add(v1, __shfl_down_sync(0xffffffffu, v1, 1));
     hp[1][i] = HH::add(t1, __shfl_down_sync(0xffffffffu, t1, 2));
   }
+}
+
+__device__ __forceinline__ void sts128_if(uint32_t addr, const uint32_t (&v)[4], bool pred) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@p st.shared.v4.b32 [%0], {%1,%2,%3,%4};\n\t"
+      "}" ::"r"(addr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(static_cast<uint32_t>(pred))
+      : "memory");
+}
+__device__ __forceinline__ void stg128_if(void* ptr, const uint32_t (&v)[4], bool pred) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@p st.global.v4.b32 [%0], {%1,%2,%3,%4};\n\t"
+      "}" ::"l"(ptr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(static_cast<uint32_t>(pred))
+      : "memory");
 }
 
 template <bool BF16>
@@ -212,7 +259,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
   uint8_t* s_res = s_st2 + NS2 * Cfg::kStageBytes;
   float* s_bias = reinterpret_cast<float*>(s_res + kB2ResRows * kB2ResRowBytes);  // [2][32]
   float* s_abc = s_bias + 64;                                                     // [3][32]
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_abc + 96);
+  // per residual group (= one epilogue-2 step, two output rows): {ring byte offsets of the upper | lower source row,
+  // vertical interpolation weight as a packed 16-bit pair} per row, written by the producer; 0xffffffff = no such row
+  uint4* s_rdesc = reinterpret_cast<uint4*>(s_abc + 96);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rdesc + kB2ResGroups);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + kB2Bars);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -266,12 +316,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
   const uint32_t tmem_base = *s_tmem;
   pdl_trigger();
 
-  const size_t in_plane_bytes = static_cast<size_t>(p.in_side) * 16;
-  const size_t in_row_bytes = 4 * in_plane_bytes;
-  const size_t in_img_bytes = in_row_bytes * p.in_side;
 
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kB2RegsCtl));
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // ====================== TMA producer: R2 row pairs for layer 1 ======================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar_w, 2 * Cfg::kWBytes);
       for (int off = 0; off < Cfg::kWBytes; off += 9216) {
@@ -281,132 +329,153 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       pdl_wait();  // the weights are constants; R2 is the previous kernel's output
       uint32_t st = 0, ph = 1;  // waiting parity 1 on a fresh "empty" barrier passes immediately
       uint32_t G1 = 0;          // global layer-1 conv-row counter (same sequence as the MMA issuer's)
-      uint32_t GG = 0;          // global residual-group counter (same sequence as the epilogue's)
-      const uint32_t stage0 = smem_u32(s_st1), res0 = smem_u32(s_res);
+      const uint32_t stage0 = smem_u32(s_st1);
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const B2Item it = b2_decode(p, item);
         const CUtensorMap* tmap = &maps.m[it.strip];
         const int row0 = it.n * p.in_side + it.po0;  // tensor-map row of R2 row 0 of the item
-        // residual window of the strip: columns [jb, jb + 112) of the source rows
-        const int jb = static_cast<int>(static_cast<float>(p.x0[it.strip]) * p.res_scale);
-        const uint8_t* res_src = p.in + it.n * in_img_bytes + static_cast<size_t>(jb) * 16;
-        int loaded_hi = -1;
-        const int steps = max(it.n1s, it.n2e + kB2LagRes);
-        for (int s = 0; s < steps; ++s) {
-          if (s < it.n1s) {
-            const int r = 2 * s;
-            if (r < it.nconv2) {  // the accumulators this input pair starts must be drained and re-initialised
-              const uint32_t gy = G1 + r;
-              mbar_wait(bar_acc1_free + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
-            }
-            mbar_wait(bar_l1_empty + 8u * st, ph);
-            const uint32_t full = bar_l1_full + 8u * st;
-            mbar_arrive_expect_tx(full, kStageTx);
-            tma_tensor4_g2s(stage0 + st * Cfg::kStageBytes, tmap, 0, 0, 0, row0 + r, full);
-            if (++st == NS1) {
-              st = 0;
-              ph ^= 1;
-            }
+        for (int r = 0; r < it.nin1; r += 2) {
+          if (r < it.nconv2) {  // the accumulators this input pair starts must be drained and re-initialised
+            const uint32_t gy = G1 + r;
+            mbar_wait_sleep(bar_acc1_free + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
           }
-          const int m = s - kB2LagRes;
-          if (m >= 0 && m < it.n2e) {
-            const uint32_t g = GG + m;
-            // ring space: three consecutive groups of one item span at most 8 source rows; across items wait for
-            // the previous item's last group.  With the static offset kB2LagRes both are normally long complete.
-            if (m >= 3) {
-              mbar_wait(bar_res_done + 8u * ((g - 3) & (kB2ResGroups - 1)), ((g - 3) >> 2) & 1);
-            } else if (GG > 0) {
-              mbar_wait(bar_res_done + 8u * ((GG - 1) & (kB2ResGroups - 1)), ((GG - 1) >> 2) & 1);
-            }
-            const int ra = max(2 * m - 3, 0), rb = min(2 * m - 2, it.npo - 1);
-            const uint32_t full = bar_res_full + 8u * (g & (kB2ResGroups - 1));
-            if (rb >= ra) {
-              const int lo = static_cast<int>(static_cast<float>(it.po0 + ra) * p.res_scale);
-              const int hi = min(static_cast<int>(static_cast<float>(it.po0 + rb) * p.res_scale) + 1, p.in_side - 1);
-              const int first = loaded_hi < 0 ? lo : loaded_hi + 1;
-              const int nrows = hi - first + 1;
-              if (nrows > 0) {
-                mbar_arrive_expect_tx(full, static_cast<uint32_t>(nrows) * kB2ResRowBytes);
-                for (int r = first; r <= hi; ++r) {
-                  const uint8_t* src = res_src + static_cast<size_t>(r) * in_row_bytes;
-                  const uint32_t dst = res0 + (r & (kB2ResRows - 1)) * kB2ResRowBytes;
-#pragma unroll
-                  for (int c = 0; c < 4; ++c)
-                    tma_bulk_g2s(dst + c * kB2ResPlaneBytes, src + c * in_plane_bytes, kB2ResPlaneBytes, full);
-                }
-                loaded_hi = hi;
-              } else {
-                mbar_arrive(full);
-              }
-            } else {
-              mbar_arrive(full);
-            }
+          mbar_wait_sleep(bar_l1_empty + 8u * st, ph);
+          const uint32_t full = bar_l1_full + 8u * st;
+          mbar_arrive_expect_tx(full, kStageTx);
+          tma_tensor4_g2s(stage0 + st * Cfg::kStageBytes, tmap, 0, 0, 0, row0 + r, full);
+          if (++st == NS1) {
+            st = 0;
+            ph ^= 1;
           }
         }
         G1 += it.nconv2;
+      }
+    }
+  } else if (warp == 2) {
+    // ================ TMA producer: residual source rows for the join of layer 2 ================
+    // One group = the source rows the two output rows of one epilogue-2 step need that are not in the ring yet.
+    // Ring space: three consecutive groups of one item span at most 8 source rows, so group g may be loaded once
+    // group g-3 has been released by all epilogue warps; across items, once the previous item is finished.
+    if (lane == 0) {
+      pdl_wait();
+      uint32_t GG = 0;  // global residual-group counter (same sequence as the epilogue's)
+      const uint32_t res0 = smem_u32(s_res);
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const B2Item it = b2_decode(p, item);
+        // residual window of the strip: columns [jb, jb + 112) of the source rows, one TMA box per row
+        const int jb2 = 2 * static_cast<int>(static_cast<float>(p.x0[it.strip]) * p.res_scale);  // in 8-byte elements
+        const int row_base = it.n * p.in_side;
+        constexpr int kNone = -0x40000000;
+        int loaded_hi = kNone;  // highest source row of the item in the ring
+        for (int m = 0; m < it.n2e; ++m) {
+          const uint32_t g = GG + m;
+          if (m >= 3) {
+            mbar_wait_sleep(bar_res_done + 8u * ((g - 3) & (kB2ResGroups - 1)), ((g - 3) >> 2) & 1);
+          } else if (GG > 0) {
+            mbar_wait_sleep(bar_res_done + 8u * ((GG - 1) & (kB2ResGroups - 1)), ((GG - 1) >> 2) & 1);
+          }
+          const uint32_t full = bar_res_full + 8u * (g & (kB2ResGroups - 1));
+          int hi = kNone;
+          uint32_t d[4];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int row = 2 * m - 3 + k;
+            d[2 * k] = 0xffffffffu;
+            d[2 * k + 1] = 0u;
+            if (row >= 0 && row < it.npo) {  // reference network.py:199 (TF-1.13 legacy bilinear: src = dst * scale)
+              const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
+              const int y0 = static_cast<int>(fy);
+              const int y1 = min(y0 + 1, p.in_side - 1);
+              d[2 * k] = static_cast<uint32_t>((y0 & (kB2ResRows - 1)) * kB2ResRowBytes) |
+                         (static_cast<uint32_t>((y1 & (kB2ResRows - 1)) * kB2ResRowBytes) << 16);
+              d[2 * k + 1] = HH::splat(fy - static_cast<float>(y0));
+              if (loaded_hi == kNone) loaded_hi = y0 - 1;  // first row of the item
+              hi = y1;
+            }
+          }
+          s_rdesc[g & (kB2ResGroups - 1)] = make_uint4(d[0], d[1], d[2], d[3]);
+          if (hi > loaded_hi) {
+            mbar_arrive_expect_tx(full, static_cast<uint32_t>(hi - loaded_hi) * kB2ResRowBytes);
+            for (int r = loaded_hi + 1; r <= hi; ++r)
+              tma_tensor3_g2s(res0 + (r & (kB2ResRows - 1)) * kB2ResRowBytes, &maps.res, jb2, 0, row_base + r, full);
+            loaded_hi = hi;
+          } else {
+            mbar_arrive(full);
+          }
+        }
         GG += it.n2e;
       }
     }
   } else if (warp == 1) {
-    // ============================ MMA issuer ============================
+    // ========================= MMA issuer, layer 1 (R2 -> conv2d_2) =========================
     if (elect_one()) {
       mbar_wait(bar_w, 0);
-      const uint32_t a1_lo0 = (smem_u32(s_st1) >> 4) | (Cfg::kALbo16 << 16);
-      const uint32_t a2_lo0 = (smem_u32(s_st2) >> 4) | (Cfg::kALbo16 << 16);
-      const uint32_t b1_lo0 = (smem_u32(s_w1) >> 4) | (Cfg::kBLbo16 << 16);
-      const uint32_t b2_lo0 = (smem_u32(s_w2) >> 4) | (Cfg::kBLbo16 << 16);
+      const uint32_t a_lo0 = (smem_u32(s_st1) >> 4) | (Cfg::kALbo16 << 16);
+      const uint32_t b_lo0 = (smem_u32(s_w1) >> 4) | (Cfg::kBLbo16 << 16);
       const uint32_t idesc0 = make_idesc(0, BF16 ? 1 : 0);
-      uint32_t st1 = 0, ph1 = 0, st2 = 0, ph2 = 0, G1 = 0, G2 = 0;
+      uint32_t st = 0, ph = 0, G = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const B2Item it = b2_decode(p, item);
-        const int steps = max(it.n1s, it.n2s + kB2LagMma);
-        for (int s = 0; s < steps; ++s) {
-          if (s < it.n1s) {
-            const int r0 = 2 * s;
-            mbar_wait(bar_l1_full + 8u * st1, ph1);
-            tc_fence_after();
-            b2_mma_pair(a1_lo0 + st1 * (Cfg::kStageBytes >> 4), b1_lo0, tmem_base, idesc0, G1, r0, it.nconv2);
-            tc_commit(bar_l1_empty + 8u * st1);
-            if (r0 >= 2) tc_commit(bar_acc1_full + 8u * (((G1 + r0 - 2) >> 1) & (RP - 1)));
-            if (++st1 == NS1) {
-              st1 = 0;
-              ph1 ^= 1;
-            }
-          }
-          const int j = s - kB2LagMma;
-          if (j >= 0 && j < it.n2s) {
-            const int r0 = 2 * j;
-            if (r0 < it.nconv3) {
-              const uint32_t gy = G2 + r0;
-              mbar_wait(bar_acc2_free + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
-            }
-            mbar_wait(bar_l2_full + 8u * st2, ph2);
-            tc_fence_after();
-            b2_mma_pair(a2_lo0 + st2 * (Cfg::kStageBytes >> 4), b2_lo0, tmem_base + R * 32, idesc0, G2, r0, it.nconv3);
-            tc_commit(bar_l2_empty + 8u * st2);
-            if (r0 >= 2) tc_commit(bar_acc2_full + 8u * (((G2 + r0 - 2) >> 1) & (RP - 1)));
-            if (++st2 == NS2) {
-              st2 = 0;
-              ph2 ^= 1;
-            }
+        for (int r0 = 0; r0 < it.nin1; r0 += 2) {
+          mbar_wait_sleep(bar_l1_full + 8u * st, ph);
+          tc_fence_after();
+          b2_mma_pair(a_lo0 + st * (Cfg::kStageBytes >> 4), b_lo0, tmem_base, idesc0, G, r0, it.nconv2);
+          tc_commit(bar_l1_empty + 8u * st);
+          if (r0 >= 2) tc_commit(bar_acc1_full + 8u * (((G + r0 - 2) >> 1) & (RP - 1)));
+          if (++st == NS1) {
+            st = 0;
+            ph ^= 1;
           }
         }
-        G1 += it.nconv2;
-        G2 += it.nconv3;
+        G += it.nconv2;
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == 3) {
+    // ========================= MMA issuer, layer 2 (P2 -> conv2d_3) =========================
+    // Its own thread: a P2 stage is multiplied as soon as epilogue 1 has completed it, whatever layer 1 is doing.
+    if (elect_one()) {
+      mbar_wait(bar_w, 0);
+      const uint32_t a_lo0 = (smem_u32(s_st2) >> 4) | (Cfg::kALbo16 << 16);
+      const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | (Cfg::kBLbo16 << 16);
+      const uint32_t idesc0 = make_idesc(0, BF16 ? 1 : 0);
+      uint32_t st = 0, ph = 0, G = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const B2Item it = b2_decode(p, item);
+        for (int r0 = 0; r0 < it.nin2; r0 += 2) {
+          if (r0 < it.nconv3) {  // the accumulators this input pair starts must be drained and re-initialised
+            const uint32_t gy = G + r0;
+            mbar_wait_sleep(bar_acc2_free + 8u * ((gy >> 1) & (RP - 1)), (gy >> LOGR) & 1);
+          }
+          mbar_wait_sleep(bar_l2_full + 8u * st, ph);
+          tc_fence_after();
+          b2_mma_pair(a_lo0 + st * (Cfg::kStageBytes >> 4), b_lo0, tmem_base + R * 32, idesc0, G, r0, it.nconv3);
+          tc_commit(bar_l2_empty + 8u * st);
+          if (r0 >= 2) tc_commit(bar_acc2_full + 8u * (((G + r0 - 2) >> 1) & (RP - 1)));
+          if (++st == NS2) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+        G += it.nconv3;
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
     // ============================= epilogue =============================
-    const int grp = (warp - 2) >> 2;  // channels [8 grp, 8 grp + 8) of both layers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kB2RegsEpi));
+    const int grp = (warp - 4) >> 2;  // channels [8 grp, 8 grp + 8) of both layers
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access = window of the 128-pixel tile
+    const bool lane0 = lane == 0;
     const uint32_t t1_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * 8;
     const uint32_t t2_base = t1_base + R * 32;
     const float* s_bias1 = s_bias + grp * 8;
     const float* s_bias2 = s_bias + 32 + grp * 8;
     // Layer-1 lane (window quad, column lane < 27) holds P2 column 27 quad + lane of the strip.  The layer-2 tile is
     // four windows at P2 columns {0, 27, 54, 76}: every P2 column lands in one or two of its lanes.
-    uint32_t sts_a, sts_b = 0xffffffffu;
+    const bool l1_lane_ok = lane < 27;
+    bool l1_dup = false;
+    uint32_t sts_a, sts_b = 0;
     {
       const int ia = quad == 3 ? 101 + lane : 32 * quad + lane;
       int ib = -1;
@@ -417,16 +486,18 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       } else if (quad == 2 && lane >= 22) {
         ib = 74 + lane;
       }
-      sts_a = grp * Cfg::kPlaneBytesT + ia * 16;
-      if (ib >= 0) sts_b = grp * Cfg::kPlaneBytesT + ib * 16;
+      sts_a = smem_u32(s_st2) + grp * Cfg::kPlaneBytesT + ia * 16;
+      l1_dup = l1_lane_ok && ib >= 0;
+      if (l1_dup) sts_b = smem_u32(s_st2) + grp * Cfg::kPlaneBytesT + ib * 16;
     }
-    const bool l1_lane_ok = lane < 27;
     // layer-2 lane -> output column of the strip
     const int rel2 = (quad == 3 ? 76 : 27 * quad) + lane;
     const bool l2_lane_ok = lane < 27 && (quad < 3 || lane >= 5);
     const size_t out_plane_bytes = static_cast<size_t>(p.out_side) * 16;
     const size_t out_row_bytes = 4 * out_plane_bytes;
     const size_t out_img_bytes = out_row_bytes * p.out_side;
+    const float* s_co = s_abc + grp * 8;  // this thread's A | +32: B | +64: C coefficients
+    const uint32_t res_ring = smem_u32(s_res) + grp * kB2ResPlaneBytes;
 
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
     {
@@ -443,7 +514,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0)
+      if (lane0)
         for (int s = 0; s < RP; ++s) {
           mbar_arrive(bar_acc1_free + 8u * s);
           mbar_arrive(bar_acc2_free + 8u * s);
@@ -451,9 +522,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
     }
     pdl_wait();  // before the first global store
 
-    uint32_t G1 = 0, G2 = 0, J2 = 0, GG = 0;
-    const uint32_t st2_0 = smem_u32(s_st2);
-    const uint8_t* res_ring = s_res + grp * kB2ResPlaneBytes;
+    // ring positions, advanced incrementally (all rings have four entries): accumulator pair + parity of the two
+    // layers, P2 stage + parity of the stage the even row of an epilogue-1 step starts, residual group + parity
+    uint32_t a1 = 0, a1_par = 0, a2 = 0, a2_par = 0, sg = 0, sg_par = 1, rg = 0, rg_par = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const B2Item it = b2_decode(p, item);
       const int x0 = p.x0[it.strip];
@@ -464,131 +535,121 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       const float fx = static_cast<float>(min(col, p.out_side - 1)) * p.res_scale;
       const int jx0 = static_cast<int>(fx);
       const uint32_t jtx2 = HH::splat(fx - static_cast<float>(jx0));
-      const uint32_t joff = static_cast<uint32_t>(min(jx0 - jb, kB2ResPx - 2)) * 16;
-      const uint32_t jdx = jx0 + 1 < p.in_side ? 16u : 0u;
+      const uint32_t jl = res_ring + static_cast<uint32_t>(min(jx0 - jb, kB2ResPx - 2)) * 16;  // left tap, ring row 0
+      const uint32_t jr = jl + (jx0 + 1 < p.in_side ? 16u : 0u);                                // right tap
       uint32_t jbot[4] = {0u, 0u, 0u, 0u};
-      int jy_prev = -1;
+      uint32_t joff_prev = 0xffffffffu;  // ring offset of the source row held in jbot
+      // output row 2m - 3 of epilogue-2 step m (advanced by two rows per step; starts three rows above the item)
       uint8_t* optr = p.out + it.n * out_img_bytes + static_cast<size_t>(it.po0) * out_row_bytes + grp * out_plane_bytes +
-                      static_cast<size_t>(min(col, p.out_side - 1)) * 16;
+                      static_cast<size_t>(min(col, p.out_side - 1)) * 16 - 3 * static_cast<ptrdiff_t>(out_row_bytes);
 
-      float r1a[8], q1a[8], q2a[8], r1b[8], q1b[8], q2b[8];
+      f32x2_t Ua[4], Va[4], Wa[4], Ub[4], Vb[4], Wb[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) r1a[c] = q1a[c] = q2a[c] = r1b[c] = q1b[c] = q2b[c] = 0.f;
+      for (int c = 0; c < 4; ++c) Ua[c] = Va[c] = Wa[c] = Ub[c] = Vb[c] = Wb[c] = 0ull;
 
-      const int steps = max(it.n1e, it.n2e + kB2LagEpi);
+      const int steps = it.n2e + kB2LagEpi;  // = max(n1e, n2e + lag): n1e = n2e + 3
       for (int t = 0; t < steps; ++t) {
         if (t < it.n1e) {
           // ---------------- layer 1: conv rows (2t, 2t+1) -> P2 rows (2t-3, 2t-2) into the layer-2 stages ----
-          const uint32_t gy = G1 + 2 * t;
-          const uint32_t pair = (gy >> 1) & (RP - 1);
-          mbar_wait(bar_acc1_full + 8u * pair, (gy >> LOGR) & 1);
+          mbar_wait_sleep(bar_acc1_full + 8u * a1, a1_par);
           tc_fence_after();
           uint32_t hp[2][4];
-          b2_drain_pool<HH>(t1_base, gy & (R - 1), (gy + 1) & (R - 1), s_bias1, bar_acc1_free + 8u * pair, lane, r1a, q1a,
-                            q2a, hp);
-          const int row_odd = 2 * t - 3, row_even = 2 * t - 2;
-          if (row_even >= 0 && row_even < it.nin2) {  // first row of P2 pair t-1: its stage must have been consumed
-            const uint32_t jg = J2 + (t - 1);
-            const uint32_t stg = jg & (NS2 - 1);
-            mbar_wait(bar_l2_empty + 8u * stg, ((jg / NS2) & 1) ^ 1);
-            const uint32_t dst = st2_0 + stg * Cfg::kStageBytes;
-            if (l1_lane_ok) {
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + sts_a), "r"(hp[1][0]), "r"(hp[1][1]),
-                           "r"(hp[1][2]), "r"(hp[1][3])
-                           : "memory");
-              if (sts_b != 0xffffffffu)
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + sts_b), "r"(hp[1][0]), "r"(hp[1][1]),
-                             "r"(hp[1][2]), "r"(hp[1][3])
-                             : "memory");
-            }
-          }
-          if (row_odd >= 0 && row_odd < it.nin2) {  // second row of P2 pair t-2: completes the stage
-            const uint32_t jg = J2 + (t - 2);
-            const uint32_t stg = jg & (NS2 - 1);
-            const uint32_t dst = st2_0 + stg * Cfg::kStageBytes + Cfg::kRowBytes;
-            if (l1_lane_ok) {
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + sts_a), "r"(hp[0][0]), "r"(hp[0][1]),
-                           "r"(hp[0][2]), "r"(hp[0][3])
-                           : "memory");
-              if (sts_b != 0xffffffffu)
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst + sts_b), "r"(hp[0][0]), "r"(hp[0][1]),
-                             "r"(hp[0][2]), "r"(hp[0][3])
-                             : "memory");
-            }
+          b2_drain_pool<HH>(t1_base + a1 * 64, s_bias1, bar_acc1_free + 8u * a1, lane0, Ua, Va, Wa, hp);
+          a1 = (a1 + 1) & 3;
+          a1_par ^= a1 == 0;
+          // P2 row 2t-3 completes the stage of pair t-2 (= the stage before `sg`), row 2t-2 starts pair t-1 in `sg`
+          if (t >= 2) {
+            const uint32_t dst = ((sg + 3) & 3) * Cfg::kStageBytes + Cfg::kRowBytes;
+            sts128_if(sts_a + dst, hp[0], l1_lane_ok);
+            sts128_if(sts_b + dst, hp[0], l1_dup);
             // generic-proxy writes -> visible to the tensor core's async-proxy reads, then signal the MMA issuer
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_l2_full + 8u * stg);
+            if (lane0) mbar_arrive(bar_l2_full + 8u * ((sg + 3) & 3));
+          }
+          if (t >= 1 && t <= it.n2s) {  // row 2t-2 < nin2
+            mbar_wait_sleep(bar_l2_empty + 8u * sg, sg_par);  // the stage must have been consumed by the layer-2 MMAs
+            const uint32_t dst = sg * Cfg::kStageBytes;
+            sts128_if(sts_a + dst, hp[1], l1_lane_ok);
+            sts128_if(sts_b + dst, hp[1], l1_dup);
+            sg = (sg + 1) & 3;
+            sg_par ^= sg == 0;
           }
         }
         const int m = t - kB2LagEpi;
-        if (m >= 0 && m < it.n2e) {
+        if (m >= 0) {
           // ---------------- layer 2: conv rows (2m, 2m+1) -> output rows (2m-3, 2m-2) + residual join ---------
-          const uint32_t gy = G2 + 2 * m;
-          const uint32_t pair = (gy >> 1) & (RP - 1);
-          mbar_wait(bar_acc2_full + 8u * pair, (gy >> LOGR) & 1);
+          mbar_wait_sleep(bar_acc2_full + 8u * a2, a2_par);
           tc_fence_after();
           uint32_t hp[2][4];
-          b2_drain_pool<HH>(t2_base, gy & (R - 1), (gy + 1) & (R - 1), s_bias2, bar_acc2_free + 8u * pair, lane, r1b, q1b,
-                            q2b, hp);
-          const uint32_t g = GG + m;
-          mbar_wait(bar_res_full + 8u * (g & (kB2ResGroups - 1)), (g >> 2) & 1);
+          b2_drain_pool<HH>(t2_base + a2 * 64, s_bias2, bar_acc2_free + 8u * a2, lane0, Ub, Vb, Wb, hp);
+          a2 = (a2 + 1) & 3;
+          a2_par ^= a2 == 0;
+          mbar_wait_sleep(bar_res_full + 8u * rg, rg_par);
+          // reference network.py:199-203 in folded form: bilinear taps in packed 16-bit arithmetic
+          // (top = tl + (tr - tl) * tx, ... : the TF formula), the per-channel affine in fp32.  Which ring rows and
+          // which vertical weight: the producer's descriptor of this group (one broadcast load).
+          const uint4 rd = s_rdesc[rg];
+          uint32_t rs[2][4];
+          bool row_ok[2];
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            const int row = 2 * m - 3 + k;
-            if (row >= 0 && row < it.npo) {
-              // reference network.py:199-203 in folded form: bilinear taps in packed 16-bit arithmetic
-              // (top = tl + (tr - tl) * tx, ... : the TF formula), the per-channel affine in fp32
-              const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
-              const int y0 = static_cast<int>(fy);
-              const int y1 = min(y0 + 1, p.in_side - 1);
-              const uint32_t ty2 = HH::splat(fy - static_cast<float>(y0));
+            const uint32_t offs = k ? rd.z : rd.x, ty2 = k ? rd.w : rd.y;
+            row_ok[k] = offs != 0xffffffffu;
+            if (row_ok[k]) {
+              const uint32_t o0 = offs & 0xffffu, o1 = offs >> 16;
               uint32_t top[4];
-              if (y0 == jy_prev) {
+              if (o0 == joff_prev) {  // the upper source row is the previous output row's lower one
 #pragma unroll
                 for (int i = 0; i < 4; ++i) top[i] = jbot[i];
               } else {
-                const uint8_t* a = res_ring + (y0 & (kB2ResRows - 1)) * kB2ResRowBytes + joff;
-                const uint4 l = *reinterpret_cast<const uint4*>(a);
-                const uint4 r = *reinterpret_cast<const uint4*>(a + jdx);
+                uint4 l, r;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(jl + o0));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(jr + o0));
                 top[0] = HH::fma(HH::sub(r.x, l.x), jtx2, l.x);
                 top[1] = HH::fma(HH::sub(r.y, l.y), jtx2, l.y);
                 top[2] = HH::fma(HH::sub(r.z, l.z), jtx2, l.z);
                 top[3] = HH::fma(HH::sub(r.w, l.w), jtx2, l.w);
               }
               {
-                const uint8_t* a = res_ring + (y1 & (kB2ResRows - 1)) * kB2ResRowBytes + joff;
-                const uint4 l = *reinterpret_cast<const uint4*>(a);
-                const uint4 r = *reinterpret_cast<const uint4*>(a + jdx);
+                uint4 l, r;
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(jl + o1));
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(jr + o1));
                 jbot[0] = HH::fma(HH::sub(r.x, l.x), jtx2, l.x);
                 jbot[1] = HH::fma(HH::sub(r.y, l.y), jtx2, l.y);
                 jbot[2] = HH::fma(HH::sub(r.z, l.z), jtx2, l.z);
                 jbot[3] = HH::fma(HH::sub(r.w, l.w), jtx2, l.w);
               }
-              jy_prev = y1;
-              uint32_t o[4];
+              joff_prev = o1;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 rs = HH::unpack(HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]));
-                const float2 hv = HH::unpack(hp[k][i]);
-                const float* co = s_abc + grp * 8 + 2 * i;
-                const float2 a2 = *reinterpret_cast<const float2*>(co);
-                const float2 b2 = *reinterpret_cast<const float2*>(co + 32);
-                const float2 c2 = *reinterpret_cast<const float2*>(co + 64);
-                o[i] = HH::pack(fmaf(a2.x, hv.x, fmaf(b2.x, rs.x, c2.x)), fmaf(a2.y, hv.y, fmaf(b2.y, rs.y, c2.y)));
-              }
-              if (col_ok)
-                *reinterpret_cast<uint4*>(optr + static_cast<size_t>(row) * out_row_bytes) = make_uint4(o[0], o[1], o[2], o[3]);
+              for (int i = 0; i < 4; ++i) rs[k][i] = HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]);
             }
           }
+          // the ring rows of this group are in registers: hand the group back to the producer
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_res_done + 8u * (g & (kB2ResGroups - 1)));
+          if (lane0) mbar_arrive(bar_res_done + 8u * rg);
+          rg = (rg + 1) & 3;
+          rg_par ^= rg == 0;
+          // per-channel affine A * pool + B * resized + C on fp32 pairs (fma.f32x2), both rows per coefficient load
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const f32x2_t A2 = *reinterpret_cast<const f32x2_t*>(s_co + 2 * i);
+            const f32x2_t B2 = *reinterpret_cast<const f32x2_t*>(s_co + 32 + 2 * i);
+            const f32x2_t C2 = *reinterpret_cast<const f32x2_t*>(s_co + 64 + 2 * i);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float2 r2 = HH::unpack(rs[k][i]);
+              const float2 h2 = HH::unpack(hp[k][i]);
+              float lo, hi;
+              f2_unpack(f2_fma(A2, f2_pack(h2.x, h2.y), f2_fma(B2, f2_pack(r2.x, r2.y), C2)), lo, hi);
+              hp[k][i] = HH::pack(lo, hi);
+            }
+          }
+          stg128_if(optr, hp[0], col_ok && row_ok[0]);
+          stg128_if(optr + out_row_bytes, hp[1], col_ok && row_ok[1]);
+          optr += 2 * out_row_bytes;
         }
       }
-      G1 += it.nconv2;
-      G2 += it.nconv3;
-      J2 += it.n2s;
-      GG += it.n2e;
     }
   }
 
@@ -673,6 +734,17 @@ cudaError_t Block2Fused(const TcConvLayer& l1, const TcConvLayer& l2, const void
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult cr = encode(&maps.m[k], CU_TENSOR_MAP_DATA_TYPE_UINT16, 4,
                          const_cast<uint8_t*>(p.in) + static_cast<size_t>(p.x0[k]) * 16, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  }
+  {
+    // residual rows: 8-byte elements so that one box row holds 112 pixels (a 16-bit box is limited to 256 elements)
+    const cuuint64_t gdim[3] = {static_cast<cuuint64_t>(2) * p.in_side, 4, static_cast<cuuint64_t>(N) * p.in_side};
+    const cuuint64_t gstr[2] = {static_cast<cuuint64_t>(p.in_side) * 16, static_cast<cuuint64_t>(4) * p.in_side * 16};
+    const cuuint32_t box[3] = {2 * kB2ResPx, 4, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = encode(&maps.res, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(p.in), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
