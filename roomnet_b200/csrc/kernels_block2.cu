@@ -490,13 +490,20 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       l1_dup = l1_lane_ok && ib >= 0;
       if (l1_dup) sts_b = smem_u32(s_st2) + grp * Cfg::kPlaneBytesT + ib * 16;
     }
+    // ptxas would rather recompute these per-thread constants from %tid in every iteration (some 60 instructions) than
+    // keep them in registers: launder them through an opaque move
+    uint32_t t1_base_r = t1_base;
+    uint32_t grp_bytes = static_cast<uint32_t>(grp) * 32u;  // byte offset of this thread's 8 channels in a [32] fp32 row
+    asm volatile("mov.b32 %0, %0;" : "+r"(t1_base_r));
+    asm volatile("mov.b32 %0, %0;" : "+r"(sts_a));
+    asm volatile("mov.b32 %0, %0;" : "+r"(sts_b));
+    asm volatile("mov.b32 %0, %0;" : "+r"(grp_bytes));
     // layer-2 lane -> output column of the strip
     const int rel2 = (quad == 3 ? 76 : 27 * quad) + lane;
     const bool l2_lane_ok = lane < 27 && (quad < 3 || lane >= 5);
     const size_t out_plane_bytes = static_cast<size_t>(p.out_side) * 16;
     const size_t out_row_bytes = 4 * out_plane_bytes;
     const size_t out_img_bytes = out_row_bytes * p.out_side;
-    const float* s_co = s_abc + grp * 8;  // this thread's A | +32: B | +64: C coefficients
     const uint32_t res_ring = smem_u32(s_res) + grp * kB2ResPlaneBytes;
 
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
 
     // ring positions, advanced incrementally (all rings have four entries): accumulator pair + parity of the two
     // layers, P2 stage + parity of the stage the even row of an epilogue-1 step starts, residual group + parity
-    uint32_t a1 = 0, a1_par = 0, a2 = 0, a2_par = 0, sg = 0, sg_par = 1, rg = 0, rg_par = 0;
+    uint32_t a1 = 0, a1_par = 0, a2 = 0, a2_par = 0, sg = 0, sg_par = 1;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const B2Item it = b2_decode(p, item);
       const int x0 = p.x0[it.strip];
@@ -554,7 +561,8 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
           mbar_wait_sleep(bar_acc1_full + 8u * a1, a1_par);
           tc_fence_after();
           uint32_t hp[2][4];
-          b2_drain_pool<HH>(t1_base + a1 * 64, s_bias1, bar_acc1_free + 8u * a1, lane0, Ua, Va, Wa, hp);
+          b2_drain_pool<HH>(t1_base_r + a1 * 64, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_bias) + grp_bytes),
+                            bar_acc1_free + 8u * a1, lane0, Ua, Va, Wa, hp);
           a1 = (a1 + 1) & 3;
           a1_par ^= a1 == 0;
           // P2 row 2t-3 completes the stage of pair t-2 (= the stage before `sg`), row 2t-2 starts pair t-1 in `sg`
@@ -582,9 +590,13 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
           mbar_wait_sleep(bar_acc2_full + 8u * a2, a2_par);
           tc_fence_after();
           uint32_t hp[2][4];
-          b2_drain_pool<HH>(t2_base + a2 * 64, s_bias2, bar_acc2_free + 8u * a2, lane0, Ub, Vb, Wb, hp);
+          b2_drain_pool<HH>(t1_base_r + R * 32 + a2 * 64,
+                            reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_bias + 32) + grp_bytes),
+                            bar_acc2_free + 8u * a2, lane0, Ub, Vb, Wb, hp);
           a2 = (a2 + 1) & 3;
           a2_par ^= a2 == 0;
+          // (the residual-group ring advances in lockstep with the layer-2 accumulator ring: same index, same parity)
+          const uint32_t rg = (a2 + 3) & 3, rg_par = a2_par ^ (a2 == 0);
           mbar_wait_sleep(bar_res_full + 8u * rg, rg_par);
           // reference network.py:199-203 in folded form: bilinear taps in packed 16-bit arithmetic
           // (top = tl + (tr - tl) * tx, ... : the TF formula), the per-channel affine in fp32.  Which ring rows and
@@ -628,14 +640,13 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
           // the ring rows of this group are in registers: hand the group back to the producer
           __syncwarp();
           if (lane0) mbar_arrive(bar_res_done + 8u * rg);
-          rg = (rg + 1) & 3;
-          rg_par ^= rg == 0;
           // per-channel affine A * pool + B * resized + C on fp32 pairs (fma.f32x2), both rows per coefficient load
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const f32x2_t A2 = *reinterpret_cast<const f32x2_t*>(s_co + 2 * i);
-            const f32x2_t B2 = *reinterpret_cast<const f32x2_t*>(s_co + 32 + 2 * i);
-            const f32x2_t C2 = *reinterpret_cast<const f32x2_t*>(s_co + 64 + 2 * i);
+            const uint8_t* co = reinterpret_cast<const uint8_t*>(s_abc) + grp_bytes + 8 * i;  // A | +128: B | +256: C
+            const f32x2_t A2 = *reinterpret_cast<const f32x2_t*>(co);
+            const f32x2_t B2 = *reinterpret_cast<const f32x2_t*>(co + 128);
+            const f32x2_t C2 = *reinterpret_cast<const f32x2_t*>(co + 256);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
               const float2 r2 = HH::unpack(rs[k][i]);
