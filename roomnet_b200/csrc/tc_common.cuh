@@ -285,9 +285,11 @@ __device__ __forceinline__ void tc_mma_acc1(uint32_t d_tmem, uint32_t a_lo, uint
 }
 template <int N>
 __device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
-  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM load width");
+  static_assert(N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM load width");
   uint32_t r[N];
-  if constexpr (N == 4) {
+  if constexpr (N == 2) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+  } else if constexpr (N == 4) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(taddr));
@@ -316,9 +318,11 @@ __device__ __forceinline__ void tc_ld(uint32_t taddr, float* v) {
 }
 template <int N>
 __device__ __forceinline__ void tc_st(uint32_t taddr, const float* v) {
-  static_assert(N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM store width");
+  static_assert(N == 2 || N == 4 || N == 8 || N == 16 || N == 32, "unsupported TMEM store width");
 #define RN_U(i) "r"(__float_as_uint(v[i]))
-  if constexpr (N == 4) {
+  if constexpr (N == 2) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), RN_U(0), RN_U(1) : "memory");
+  } else if constexpr (N == 4) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), RN_U(0), RN_U(1), RN_U(2),
                  RN_U(3)
                  : "memory");

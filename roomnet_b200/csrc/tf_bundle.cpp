@@ -76,7 +76,8 @@ struct Slice {
 
 // Returns the block body after verifying compression tag and CRC.
 bool GetBlock(const std::vector<uint8_t>& file, uint64_t off, uint64_t size, Slice* out, std::string* err) {
-  if (off + size + 5 > file.size()) {
+  // overflow-safe: the handle is untrusted (two 64-bit varints), so never add before comparing
+  if (file.size() < 5 || size > file.size() - 5 || off > file.size() - 5 - size) {
     *err = "SSTable block handle runs past the end of the index file";
     return false;
   }
@@ -111,7 +112,8 @@ bool ForEachEntry(Slice block, Fn fn, std::string* err) {
   std::string key;
   while (c.p < c.end) {
     uint64_t shared = c.Varint(), non_shared = c.Varint(), vlen = c.Varint();
-    if (!c.ok || shared > key.size() || static_cast<uint64_t>(c.end - c.p) < non_shared + vlen) {
+    const uint64_t rem = static_cast<uint64_t>(c.end - c.p);
+    if (!c.ok || shared > key.size() || non_shared > rem || vlen > rem - non_shared) {
       *err = "corrupt SSTable entry";
       return false;
     }
@@ -288,9 +290,20 @@ BundleError ReadBundle(const std::string& prefix, TensorMap* out, std::string* e
     if (e.dtype != 1) continue;  // only DT_FLOAT variables matter on this path
     Tensor t;
     t.shape = e.shape;
-    if (e.shard != 0 || e.offset < 0 || e.size != t.numel() * 4 ||
-        static_cast<uint64_t>(e.offset + e.size) > data.size()) {
-      *err = "tensor " + kv.first + ": bad offset/size";
+    // untrusted header: reject negative / overflowing dims, offsets and sizes before any arithmetic on them
+    bool dims_ok = true;
+    uint64_t numel = 1;
+    for (int64_t d : e.shape) {
+      if (d < 0 || (d > 0 && numel > (static_cast<uint64_t>(1) << 40) / static_cast<uint64_t>(d))) {
+        dims_ok = false;
+        break;
+      }
+      numel *= static_cast<uint64_t>(d);
+    }
+    const uint64_t dsz = data.size();
+    if (!dims_ok || e.shard != 0 || e.offset < 0 || e.size < 0 || static_cast<uint64_t>(e.size) != numel * 4 ||
+        static_cast<uint64_t>(e.size) > dsz || static_cast<uint64_t>(e.offset) > dsz - static_cast<uint64_t>(e.size)) {
+      *err = "tensor " + kv.first + ": bad shape/offset/size";
       return BundleError::kFormat;
     }
     if (MaskCrc(Crc32c(&data[e.offset], static_cast<size_t>(e.size))) != e.crc) {

@@ -131,3 +131,32 @@ def test_cpp_error_codes(capi, ckpt_prefix, tmp_path):
     h300.load_tf_checkpoint(ckpt_prefix)
     with pytest.raises(capi.RoomNetError):
         h300.set_dense0(np.zeros((64, 32), np.float32))
+
+
+def _varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def test_cpp_reader_rejects_overflowing_handles(capi, ckpt_prefix, tmp_path):
+    """Untrusted 64-bit block handles / entry lengths must not wrap the bounds checks (off + size + 5)."""
+    h = _host_handle(capi)
+    for ext in (".index", ".data-00000-of-00001"):
+        shutil.copy(ckpt_prefix + ext, tmp_path / ("roomnet" + ext))
+    idx = tmp_path / "roomnet.index"
+    good = idx.read_bytes()
+    magic = good[-8:]
+    for off, size in ((1 << 40, (1 << 64) - (1 << 40) - 5), (0, (1 << 64) - 1), ((1 << 64) - 1, 0), (len(good), 1)):
+        footer = _varint(0) + _varint(0) + _varint(off) + _varint(size)
+        footer += b"\0" * (40 - len(footer)) + magic
+        idx.write_bytes(good[:-48] + footer)
+        with pytest.raises(capi.RoomNetError) as e:
+            h.load_tf_checkpoint(str(tmp_path / "roomnet"))
+        assert e.value.code == capi.RN_ERR_FORMAT, (off, size)
+    idx.write_bytes(good)
+    h.load_tf_checkpoint(str(tmp_path / "roomnet"))  # the untouched copy still loads

@@ -45,6 +45,58 @@ __global__ void k(float* out, long long* cyc, float seed) {
         asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
         asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(h[i]) : "r"(hb));
       }
+      if (OP == 12) asm volatile("min.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+      if (OP == 13) asm volatile("min.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+      if (OP == 14) asm volatile("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+      if (OP == 15) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f32.f16 %0, hi, lo, %0;}" : "+f"(a[i]) : "r"(hb));
+      if (OP == 16) asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; add.rn.f32.f16 %0, hi, %0;}" : "+f"(a[i]) : "r"(hb));
+      if (OP == 17) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(h[i]) : "r"(hb));
+      if (OP == 18) asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(h[i]) : "r"(hb));
+      if (OP == 19) {  // FADD + HADD2: one pipe or two?
+        asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+      }
+      if (OP == 20) {  // FADD2 + HADD2
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+      }
+      if (OP == 21) {  // FADD + FMNMX
+        asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+        asm volatile("min.f32 %0, %0, %1;" : "+f"(a[(i + 4) & 7]) : "f"(b));
+      }
+      if (OP == 22) {  // HADD2 + HMNMX2
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+        asm volatile("min.f16x2 %0, %0, %1;" : "+r"(h[(i + 4) & 7]) : "r"(hb));
+      }
+      if (OP == 23) {  // HADD2 + F2FP
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[(i + 4) & 7]) : "f"(a[i]), "f"(a[(i + 1) & 7]));
+      }
+      if (OP == 24) {  // FADD + F2FP
+        asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[(i + 3) & 7]), "f"(a[(i + 1) & 7]));
+      }
+      if (OP == 25) {  // HADD2 + SHFL
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+        asm volatile("shfl.sync.down.b32 %0, %0, 1, 0x1f, 0xffffffff;" : "+r"(h[(i + 4) & 7]));
+      }
+      if (OP == 26) {  // FHFMA + HADD2
+        asm volatile("{.reg .f16 lo, hi; mov.b32 {lo, hi}, %1; fma.rn.f32.f16 %0, hi, lo, %0;}" : "+f"(a[i]) : "r"(hb));
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(h[i]) : "r"(hb));
+      }
+      if (OP == 27) {  // F2FP + SHFL + HMNMX2 (none on the fma pipe?)
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[i]) : "f"(a[(i + 3) & 7]), "f"(a[(i + 1) & 7]));
+        asm volatile("min.f16x2 %0, %0, %1;" : "+r"(h[(i + 4) & 7]) : "r"(hb));
+      }
+      if (OP == 28) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(p[(i + 4) & 7]));
+      if (OP == 29) {  // FADD2 + FADD
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(p[i]) : "l"(pb));
+        asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+      }
+      if (OP == 30) {  // HFMA2 + FMNMX + F2FP : three pipes?
+        asm volatile("fma.rn.f16x2 %0, %0, %1, %1;" : "+r"(h[i]) : "r"(hb));
+        asm volatile("min.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b));
+      }
     }
   }
   long long t1 = clock64();
@@ -89,6 +141,25 @@ int main() {
     run<8>("HADD2.F32 (cvt f32.f16)", nw, 1);
     run<10>("FADD + SHFL mix", nw, 2);
     run<11>("FADD + LOP3 mix", nw, 2);
+    run<12>("FMNMX", nw, 1);
+    run<13>("HMNMX2", nw, 1);
+    run<14>("F2FP.RELU", nw, 1);
+    run<15>("FHFMA (fma.f32.f16)", nw, 1);
+    run<16>("FHADD (add.f32.f16)", nw, 1);
+    run<17>("PRMT", nw, 1);
+    run<18>("LOP3", nw, 1);
+    run<19>("FADD + HADD2 mix", nw, 2);
+    run<20>("FADD2 + HADD2 mix", nw, 2);
+    run<21>("FADD + FMNMX mix", nw, 2);
+    run<22>("HADD2 + HMNMX2 mix", nw, 2);
+    run<23>("HADD2 + F2FP mix", nw, 2);
+    run<24>("FADD + F2FP mix", nw, 2);
+    run<25>("HADD2 + SHFL mix", nw, 2);
+    run<26>("FHFMA + HADD2 mix", nw, 2);
+    run<27>("F2FP + HMNMX2 mix", nw, 2);
+    run<28>("FADD2 (reg,reg)", nw, 1);
+    run<29>("FADD2 + FADD mix", nw, 2);
+    run<30>("HFMA2 + FMNMX mix", nw, 2);
   }
   return 0;
 }
