@@ -214,7 +214,11 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
       L.bias = tc_bias_[i];
       size_t part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0, nullptr);
       std::vector<uint8_t> host(part_bytes * L.cout_parts);
-      PackTcWeights(f.conv[i].w.data(), cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0 / (6.0 * g_in), host.data());
+      std::vector<double> in_scale;  // the producer's per-channel join gain (below) is undone in this layer's weights
+      if (in_is_join && !join_gain_[i - 1].empty())
+        for (double g : join_gain_[i - 1]) in_scale.push_back(1.0 / g);
+      PackTcWeights(f.conv[i].w.data(), cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0 / (6.0 * g_in), host.data(),
+                    in_scale.empty() ? nullptr : in_scale.data());
       void* d = const_cast<void*>(L.w_packed);
       if (!d) RN_CUDA(Alloc(&d, host.size()));
       RN_CUDA(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
@@ -224,11 +228,30 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
         std::vector<double> a(f.join[i].a), b(f.join[i].b);
         for (auto& v : a) v /= act_scale_[i];
         for (auto& v : b) v /= act_scale_[cs.join_src];
+        std::vector<double> cc(f.join[i].c);
+        join_gain_[i].clear();
+        if (i == 3 && i + 1 < first_f32_layer_) {
+          // Residual block 2 (kernels_block2.cu) multiplies the resized residual by B with a mixed-precision fma whose
+          // multiplier is a 16-bit value.  Rounding B would be a coherent per-channel error of 2^-12 (measured: 1e-2 on
+          // the logits of flat images), so the whole output channel is stored with a gain g = round16(B) / B instead:
+          // g*A and g*C stay fp32, g*B is exactly representable, and conv2d_4's weights of that input channel carry 1/g.
+          join_gain_[i].assign(cs.cout, 1.0);
+          for (int k = 0; k < cs.cout; ++k) {
+            const double bh = RoundToHalfKind(b[k], half_kind_);
+            if (b[k] != 0.0 && bh != 0.0) {
+              join_gain_[i][k] = bh / b[k];
+              a[k] *= join_gain_[i][k];
+              cc[k] *= join_gain_[i][k];
+              b[k] = bh;
+            }
+          }
+        }
         RN_CUDA(UploadF32(a, &tc_ja_[i]));
         RN_CUDA(UploadF32(b, &tc_jb_[i]));
+        RN_CUDA(UploadF32(cc, &tc_jc_[i]));
         std::vector<double> abc(a);
         abc.insert(abc.end(), b.begin(), b.end());
-        abc.insert(abc.end(), f.join[i].c.begin(), f.join[i].c.end());
+        abc.insert(abc.end(), cc.begin(), cc.end());
         RN_CUDA(UploadF32(abc, &tc_abc_[i]));
         L.join_abc = tc_abc_[i];
         L.join_src_side = shape_.conv[cs.join_src].out_side;
@@ -349,7 +372,7 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
     RN_CUDA(ConvTc(tc_[i], in, cur_->act_h[i], n, half_kind_, st));
     Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
     if (cs.join_src >= 0) {
-      RN_CUDA(JoinH(cur_->act_h[i], cur_->act_h[cs.join_src], cur_->join_h[i], tc_ja_[i], tc_jb_[i], jc_[i], n, cs.out_side,
+      RN_CUDA(JoinH(cur_->act_h[i], cur_->act_h[cs.join_src], cur_->join_h[i], tc_ja_[i], tc_jb_[i], tc_jc_[i], n, cs.out_side,
                     shape_.conv[cs.join_src].out_side, cs.cout, half_kind_, st));
       Mark(("join" + std::to_string(i) + "_h").c_str(), st);
     }
@@ -646,6 +669,8 @@ cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dim
   cudaError_t e = cudaMemcpy(out->data(), src, elems * sizeof(float), cudaMemcpyDeviceToHost);
   if (tmp) cudaFree(tmp);
   RN_CUDA(e);
+  if (layer < first_f32_layer_ && !join_gain_[layer].empty())  // stored with a per-channel gain (LoadFolded)
+    for (size_t k = 0; k < elems; ++k) (*out)[k] = static_cast<float>((*out)[k] / join_gain_[layer][k % cs.cout]);
   return cudaSuccess;
 }
 

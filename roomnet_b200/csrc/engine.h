@@ -100,7 +100,9 @@ class Replica {
   void* tc0_w_[2] = {nullptr, nullptr};  // conv0 packed weights for uint8 BGR / RGB byte order
   float* tc_ja_[kNumConvs] = {};
   float* tc_jb_[kNumConvs] = {};
+  float* tc_jc_[kNumConvs] = {};
   float* tc_abc_[kNumConvs] = {};  // [3][cout] A/B/C for the join fused into the conv epilogue
+  std::vector<double> join_gain_[kNumConvs];  // per-channel gain a join output is stored with (empty = none)
   HalfKind half_kind_ = HalfKind::kF16;
 
   // Activations.  Two independent sets, each with its own stream: consecutive micro-batches alternate between

@@ -59,9 +59,12 @@ struct TcConvLayer {
 size_t ChunkedBytes(int n, int side, int channels);
 
 // Host-side weight packer: HWIO fp64 -> per-part shared-memory image of the conv_tc kernel.
-// `scale` multiplies every weight before rounding (stored-activation scale bookkeeping, see engine.cu).
+// `scale` multiplies every weight before rounding (stored-activation scale bookkeeping, see engine.cu);
+// `in_scale` (optional, [cin]) multiplies the weights of one input channel on top of that.
 size_t PackTcWeights(const double* w_hwio, int cin, int cout, int cout_parts, HalfKind kind, double scale,
-                     void* out_host);
+                     void* out_host, const double* in_scale = nullptr);
+// Round a value to the 16-bit storage type of the tensor-core path and return it as a double.
+double RoundToHalfKind(double v, HalfKind kind);
 
 // conv0 on the tensor cores: weights [3][3][3][8] (uint8-folded) split into fp16 hi + lo halves.
 size_t PackTcConv0Weights(const double* w_hwio, HalfKind kind, double scale, void* out_host);

@@ -27,6 +27,7 @@
 // Warps 4..19 = epilogue: warp (quadrant q, channel group g) owns TMEM lanes 32q..32q+31 and
 // channels 8g..8g+7 of BOTH layers and alternates between them (layer 2 runs kLagEpi row pairs behind layer 1).
 #include <cstring>
+#include <type_traits>
 
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -162,35 +163,47 @@ __device__ __forceinline__ void b2_mma_pair(uint32_t a_lo, uint32_t b_lo0, uint3
   }
 }
 
-// saturate as a volatile statement: keeps ptxas from hoisting the clip of the second row above the in-place window
-// update (it would then need a copy to get the value into the state registers)
+// saturate as a volatile statement: keeps ptxas from hoisting the clip of the second row above the last use of the
+// state register it is written into (it would then need a copy to get the value there)
 __device__ __forceinline__ float sat_here(float v) {
   float r;
   asm volatile("add.sat.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
   return r;
 }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// in-place packed add (tied operands: the sum replaces `acc` in its own register pair)
+__device__ __forceinline__ void f2_add_to(f32x2_t& acc, f32x2_t b) { asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(b)); }
 
 // Drain one accumulator row pair (8 channels of this thread's pixel), hand the slots back pre-loaded with the bias,
 // clip (saturate = ReLU6/6, the factor lives in the weights), advance the vertical 4-row window and apply the
 // horizontal 4-column window on packed 16-bit pairs with warp shuffles.
 // hp[0] = pooled row (y - 3), hp[1] = pooled row (y - 2) for conv rows (y, y + 1) of this call.
-// The vertical window lives in packed fp32 pairs (add.f32x2: one issue slot per two channels) and is updated in
-// place - U = x(y-1), V = x(y-1) + x(y-2), W = x(y-2) + x(y-3) - with the same association as conv_tc_kernel
-// ((x(y) + x(y-1)) + W, (x(y+1) + x(y)) + V), so the fused block stays bit-identical to the layer-by-layer kernels;
-// recomputing the two partial sums into the state registers costs two adds per channel pair but no register moves.
-template <typename HH>
-__device__ __forceinline__ void b2_drain_pool(uint32_t t_slot0, const float* s_bias8, uint32_t bar_free, bool lane0,
-                                              f32x2_t (&U)[4], f32x2_t (&V)[4], f32x2_t (&W)[4], uint32_t (&hp)[2][4]) {
+// The vertical window is a sum of two row-pair sums in packed fp32 (add.f32x2): with p(k) = x(k) + x(k+1),
+// pooled(y-3) = p(y-3) + p(y-1) and pooled(y-2) = p(y-2) + p(y): four adds per channel pair for two output rows.
+// State on entry: U = x(y-1), P[PH] = p(y-3), Q[PH] = p(y-2).  The call writes the new pair sums into P[PH^1] / Q[PH^1]
+// and finishes the window sums in place in P[PH] / Q[PH], so the next call runs with the opposite phase and no
+// register is ever copied (ptxas does not find this rotation by itself: ~18 moves per step otherwise).
+// SCALE: the window sums are multiplied by the fp32 per-channel factors at shared address `scale_addr` before they are
+// rounded to 16 bits (the join coefficient A of the block's last layer: exact, and the horizontal sums then run on A*x).
+template <typename HH, int PH, bool SCALE>
+__device__ __forceinline__ void b2_drain_pool(uint32_t t_slot0, uint32_t bias_addr, uint32_t bar_free, bool lane0,
+                                              f32x2_t (&U)[4], f32x2_t (&P)[2][4], f32x2_t (&Q)[2][4],
+                                              uint32_t (&hp)[2][4], uint32_t scale_addr = 0) {
   float a[8], b[8];
   tc_ld<8>(t_slot0, a);
   tc_ld<8>(t_slot0 + 32, b);
   tc_wait_ld();
   {
     float bias[8];
-    const float4 b0 = *reinterpret_cast<const float4*>(s_bias8);
-    const float4 b1 = *reinterpret_cast<const float4*>(s_bias8 + 4);
-    bias[0] = b0.x, bias[1] = b0.y, bias[2] = b0.z, bias[3] = b0.w;
-    bias[4] = b1.x, bias[5] = b1.y, bias[6] = b1.z, bias[7] = b1.w;
+    const uint4 b0 = lds128(bias_addr), b1 = lds128(bias_addr + 16);
+    bias[0] = __uint_as_float(b0.x), bias[1] = __uint_as_float(b0.y), bias[2] = __uint_as_float(b0.z);
+    bias[3] = __uint_as_float(b0.w), bias[4] = __uint_as_float(b1.x), bias[5] = __uint_as_float(b1.y);
+    bias[6] = __uint_as_float(b1.z), bias[7] = __uint_as_float(b1.w);
     tc_st<8>(t_slot0, bias);
     tc_st<8>(t_slot0 + 32, bias);
     tc_wait_st();
@@ -202,15 +215,21 @@ __device__ __forceinline__ void b2_drain_pool(uint32_t t_slot0, const float* s_b
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const f32x2_t x0 = f2_pack(__saturatef(a[2 * i]), __saturatef(a[2 * i + 1]));
-    const f32x2_t o0 = f2_add(f2_add(x0, U[i]), W[i]);
-    W[i] = f2_add_again(U[i], x0);  // operands swapped: bit-identical, but not the same expression for the compiler
+    P[PH ^ 1][i] = f2_add(U[i], x0);
+    f2_add_to(P[PH][i], P[PH ^ 1][i]);
     U[i] = f2_pack(sat_here(b[2 * i]), sat_here(b[2 * i + 1]));
-    const f32x2_t o1 = f2_add(f2_add(U[i], x0), V[i]);
-    V[i] = f2_add_again(x0, U[i]);
+    Q[PH ^ 1][i] = f2_add(x0, U[i]);
+    f2_add_to(Q[PH][i], Q[PH ^ 1][i]);
+    if constexpr (SCALE) {
+      f32x2_t a2;
+      asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a2) : "r"(scale_addr + 8 * i));
+      asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(P[PH][i]) : "l"(a2));
+      asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(Q[PH][i]) : "l"(a2));
+    }
     float lo, hi;
-    f2_unpack(o0, lo, hi);
+    f2_unpack(P[PH][i], lo, hi);
     v0[i] = HH::pack(lo, hi);
-    f2_unpack(o1, lo, hi);
+    f2_unpack(Q[PH][i], lo, hi);
     v1[i] = HH::pack(lo, hi);
   }
 #pragma unroll
@@ -258,10 +277,10 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
   uint8_t* s_st2 = s_st1 + NS1 * Cfg::kStageBytes;
   uint8_t* s_res = s_st2 + NS2 * Cfg::kStageBytes;
   float* s_bias = reinterpret_cast<float*>(s_res + kB2ResRows * kB2ResRowBytes);  // [2][32]
-  float* s_abc = s_bias + 64;                                                     // [3][32]
+  uint8_t* s_coef = reinterpret_cast<uint8_t*>(s_bias + 64);  // per channel group: {A x8 fp32 | C x8 fp32 | B x8 16-bit | pad}
   // per residual group (= one epilogue-2 step, two output rows): {ring byte offsets of the upper | lower source row,
-  // vertical interpolation weight as a packed 16-bit pair} per row, written by the producer; 0xffffffff = no such row
-  uint4* s_rdesc = reinterpret_cast<uint4*>(s_abc + 96);
+  // vertical interpolation weight as a packed 16-bit pair} per row, written by the producer; weight 0xffffffff = no such row
+  uint4* s_rdesc = reinterpret_cast<uint4*>(s_coef + 96 * 4);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_rdesc + kB2ResGroups);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + kB2Bars);
 
@@ -305,7 +324,12 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
     s_bias[i] = p.bias1[i];
     s_bias[32 + i] = p.bias2[i];
   }
-  for (int i = threadIdx.x; i < 96; i += kB2Threads) s_abc[i] = p.abc[i];
+  for (int i = threadIdx.x; i < 32; i += kB2Threads) {  // join coefficients (host layout [3][32] fp32: A | B | C)
+    uint8_t* g = s_coef + (i >> 3) * 96;
+    reinterpret_cast<float*>(g)[i & 7] = p.abc[i];
+    reinterpret_cast<float*>(g + 32)[i & 7] = p.abc[64 + i];
+    reinterpret_cast<uint16_t*>(g + 64)[i & 7] = static_cast<uint16_t>(HH::pack(p.abc[32 + i], 0.f));  // exact (engine.cu)
+  }
   // the 128-byte pad behind the last plane of every stage is read (lanes 126/127, dx taps) but never written
   for (int i = threadIdx.x; i < (NS1 + NS2) * 32; i += kB2Threads)
     reinterpret_cast<uint32_t*>(s_st1 + (i / 32) * Cfg::kStageBytes + 2 * Cfg::kRowBytes)[i % 32] = 0u;
@@ -380,8 +404,8 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
             const int row = 2 * m - 3 + k;
-            d[2 * k] = 0xffffffffu;
-            d[2 * k + 1] = 0u;
+            d[2 * k] = 16u | (16u << 16);  // a row outside the item: harmless ring offsets that match no real row,
+            d[2 * k + 1] = 0xffffffffu;    // ... marked by an impossible weight (the stores are predicated off)
             if (row >= 0 && row < it.npo) {  // reference network.py:199 (TF-1.13 legacy bilinear: src = dst * scale)
               const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
               const int y0 = static_cast<int>(fy);
@@ -464,13 +488,12 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
   } else if (warp >= 4) {
     // ============================= epilogue =============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kB2RegsEpi));
-    const int grp = (warp - 4) >> 2;  // channels [8 grp, 8 grp + 8) of both layers
-    const int quad = warp & 3;        // TMEM lane quadrant this warp may access = window of the 128-pixel tile
+    // (the warp index through a shuffle: ptxas then knows that everything derived from it is warp-uniform and keeps
+    // the TMEM / shared-memory base addresses of this warp in uniform registers)
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    const int grp = (warp_u - 4) >> 2;  // channels [8 grp, 8 grp + 8) of both layers
+    const int quad = warp_u & 3;        // TMEM lane quadrant this warp may access = window of the 128-pixel tile
     const bool lane0 = lane == 0;
-    const uint32_t t1_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * 8;
-    const uint32_t t2_base = t1_base + R * 32;
-    const float* s_bias1 = s_bias + grp * 8;
-    const float* s_bias2 = s_bias + 32 + grp * 8;
     // Layer-1 lane (window quad, column lane < 27) holds P2 column 27 quad + lane of the strip.  The layer-2 tile is
     // four windows at P2 columns {0, 27, 54, 76}: every P2 column lands in one or two of its lanes.
     const bool l1_lane_ok = lane < 27;
@@ -490,33 +513,33 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       l1_dup = l1_lane_ok && ib >= 0;
       if (l1_dup) sts_b = smem_u32(s_st2) + grp * Cfg::kPlaneBytesT + ib * 16;
     }
-    // ptxas would rather recompute these per-thread constants from %tid in every iteration (some 60 instructions) than
-    // keep them in registers: launder them through an opaque move
-    uint32_t t1_base_r = t1_base;
-    uint32_t grp_bytes = static_cast<uint32_t>(grp) * 32u;  // byte offset of this thread's 8 channels in a [32] fp32 row
-    asm volatile("mov.b32 %0, %0;" : "+r"(t1_base_r));
+    // per-lane addresses: ptxas would rather recompute them from %tid in every iteration than keep them in registers:
+    // launder them through an opaque move
     asm volatile("mov.b32 %0, %0;" : "+r"(sts_a));
     asm volatile("mov.b32 %0, %0;" : "+r"(sts_b));
-    asm volatile("mov.b32 %0, %0;" : "+r"(grp_bytes));
+    const uint32_t t1_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * 8;
+    const uint32_t bias_a = smem_u32(s_bias) + grp * 32;  // this thread's 8 biases of layer 1; layer 2: + 128
+    const uint32_t coef_a = smem_u32(s_coef) + grp * 96;  // {A x8 fp32 | C x8 fp32 | B x8 16-bit | pad}
+    const uint32_t res_ring = smem_u32(s_res) + grp * kB2ResPlaneBytes;
     // layer-2 lane -> output column of the strip
     const int rel2 = (quad == 3 ? 76 : 27 * quad) + lane;
     const bool l2_lane_ok = lane < 27 && (quad < 3 || lane >= 5);
-    const size_t out_plane_bytes = static_cast<size_t>(p.out_side) * 16;
-    const size_t out_row_bytes = 4 * out_plane_bytes;
-    const size_t out_img_bytes = out_row_bytes * p.out_side;
-    const uint32_t res_ring = smem_u32(s_res) + grp * kB2ResPlaneBytes;
+    const uint32_t out_plane_bytes = static_cast<uint32_t>(p.out_side) * 16;
+    const uint32_t out_row_bytes = 4 * out_plane_bytes;
+    const size_t out_img_bytes = static_cast<size_t>(out_row_bytes) * p.out_side;
+    const uint32_t rdesc_a = smem_u32(s_rdesc);
 
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
     {
       float b1[8], b2[8];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        b1[c] = s_bias1[c];
-        b2[c] = s_bias2[c];
+        b1[c] = s_bias[grp * 8 + c];
+        b2[c] = s_bias[32 + grp * 8 + c];
       }
       for (int s = 0; s < R; ++s) {
         tc_st<8>(t1_base + s * 32, b1);
-        tc_st<8>(t2_base + s * 32, b2);
+        tc_st<8>(t1_base + R * 32 + s * 32, b2);
       }
       tc_wait_st();
       tc_fence_before();
@@ -543,124 +566,134 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       const int jx0 = static_cast<int>(fx);
       const uint32_t jtx2 = HH::splat(fx - static_cast<float>(jx0));
       const uint32_t jl = res_ring + static_cast<uint32_t>(min(jx0 - jb, kB2ResPx - 2)) * 16;  // left tap, ring row 0
-      const uint32_t jr = jl + (jx0 + 1 < p.in_side ? 16u : 0u);                                // right tap
-      uint32_t jbot[4] = {0u, 0u, 0u, 0u};
-      uint32_t joff_prev = 0xffffffffu;  // ring offset of the source row held in jbot
+      // (right tap = jl + 16: with a resize scale > 1 the last output column still has a right neighbour)
+      uint32_t J[4] = {0u, 0u, 0u, 0u}, Jn[4];  // J: horizontally interpolated source row at ring offset `joff`
+      uint32_t joff = 0xffffffffu;
       // output row 2m - 3 of epilogue-2 step m (advanced by two rows per step; starts three rows above the item)
       uint8_t* optr = p.out + it.n * out_img_bytes + static_cast<size_t>(it.po0) * out_row_bytes + grp * out_plane_bytes +
                       static_cast<size_t>(min(col, p.out_side - 1)) * 16 - 3 * static_cast<ptrdiff_t>(out_row_bytes);
 
-      f32x2_t Ua[4], Va[4], Wa[4], Ub[4], Vb[4], Wb[4];
+      f32x2_t U1[4], P1[2][4], Q1[2][4], U2[4], P2[2][4], Q2[2][4];  // vertical windows of the two layers (b2_drain_pool)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) Ua[c] = Va[c] = Wa[c] = Ub[c] = Vb[c] = Wb[c] = 0ull;
+      for (int c = 0; c < 4; ++c) U1[c] = P1[0][c] = Q1[0][c] = U2[c] = P2[0][c] = Q2[0][c] = 0ull;
 
-      const int steps = it.n2e + kB2LagEpi;  // = max(n1e, n2e + lag): n1e = n2e + 3
-      for (int t = 0; t < steps; ++t) {
-        if (t < it.n1e) {
-          // ---------------- layer 1: conv rows (2t, 2t+1) -> P2 rows (2t-3, 2t-2) into the layer-2 stages ----
-          mbar_wait_sleep(bar_acc1_full + 8u * a1, a1_par);
-          tc_fence_after();
-          uint32_t hp[2][4];
-          b2_drain_pool<HH>(t1_base_r + a1 * 64, reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_bias) + grp_bytes),
-                            bar_acc1_free + 8u * a1, lane0, Ua, Va, Wa, hp);
-          a1 = (a1 + 1) & 3;
-          a1_par ^= a1 == 0;
-          // P2 row 2t-3 completes the stage of pair t-2 (= the stage before `sg`), row 2t-2 starts pair t-1 in `sg`
-          if (t >= 2) {
-            const uint32_t dst = ((sg + 3) & 3) * Cfg::kStageBytes + Cfg::kRowBytes;
-            sts128_if(sts_a + dst, hp[0], l1_lane_ok);
-            sts128_if(sts_b + dst, hp[0], l1_dup);
-            // generic-proxy writes -> visible to the tensor core's async-proxy reads, then signal the MMA issuer
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane0) mbar_arrive(bar_l2_full + 8u * ((sg + 3) & 3));
-          }
-          if (t >= 1 && t <= it.n2s) {  // row 2t-2 < nin2
-            mbar_wait_sleep(bar_l2_empty + 8u * sg, sg_par);  // the stage must have been consumed by the layer-2 MMAs
-            const uint32_t dst = sg * Cfg::kStageBytes;
-            sts128_if(sts_a + dst, hp[1], l1_lane_ok);
-            sts128_if(sts_b + dst, hp[1], l1_dup);
-            sg = (sg + 1) & 3;
-            sg_par ^= sg == 0;
-          }
-        }
-        const int m = t - kB2LagEpi;
-        if (m >= 0) {
-          // ---------------- layer 2: conv rows (2m, 2m+1) -> output rows (2m-3, 2m-2) + residual join ---------
-          mbar_wait_sleep(bar_acc2_full + 8u * a2, a2_par);
-          tc_fence_after();
-          uint32_t hp[2][4];
-          b2_drain_pool<HH>(t1_base_r + R * 32 + a2 * 64,
-                            reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(s_bias + 32) + grp_bytes),
-                            bar_acc2_free + 8u * a2, lane0, Ub, Vb, Wb, hp);
-          a2 = (a2 + 1) & 3;
-          a2_par ^= a2 == 0;
-          // (the residual-group ring advances in lockstep with the layer-2 accumulator ring: same index, same parity)
-          const uint32_t rg = (a2 + 3) & 3, rg_par = a2_par ^ (a2 == 0);
-          mbar_wait_sleep(bar_res_full + 8u * rg, rg_par);
-          // reference network.py:199-203 in folded form: bilinear taps in packed 16-bit arithmetic
-          // (top = tl + (tr - tl) * tx, ... : the TF formula), the per-channel affine in fp32.  Which ring rows and
-          // which vertical weight: the producer's descriptor of this group (one broadcast load).
-          const uint4 rd = s_rdesc[rg];
-          uint32_t rs[2][4];
-          bool row_ok[2];
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint32_t offs = k ? rd.z : rd.x, ty2 = k ? rd.w : rd.y;
-            row_ok[k] = offs != 0xffffffffu;
-            if (row_ok[k]) {
-              const uint32_t o0 = offs & 0xffffu, o1 = offs >> 16;
-              uint32_t top[4];
-              if (o0 == joff_prev) {  // the upper source row is the previous output row's lower one
-#pragma unroll
-                for (int i = 0; i < 4; ++i) top[i] = jbot[i];
-              } else {
-                uint4 l, r;
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(jl + o0));
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(jr + o0));
-                top[0] = HH::fma(HH::sub(r.x, l.x), jtx2, l.x);
-                top[1] = HH::fma(HH::sub(r.y, l.y), jtx2, l.y);
-                top[2] = HH::fma(HH::sub(r.z, l.z), jtx2, l.z);
-                top[3] = HH::fma(HH::sub(r.w, l.w), jtx2, l.w);
-              }
-              {
-                uint4 l, r;
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(l.x), "=r"(l.y), "=r"(l.z), "=r"(l.w) : "r"(jl + o1));
-                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(jr + o1));
-                jbot[0] = HH::fma(HH::sub(r.x, l.x), jtx2, l.x);
-                jbot[1] = HH::fma(HH::sub(r.y, l.y), jtx2, l.y);
-                jbot[2] = HH::fma(HH::sub(r.z, l.z), jtx2, l.z);
-                jbot[3] = HH::fma(HH::sub(r.w, l.w), jtx2, l.w);
-              }
-              joff_prev = o1;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) rs[k][i] = HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]);
-            }
-          }
-          // the ring rows of this group are in registers: hand the group back to the producer
+      // ---------------- layer 1: conv rows (2t, 2t+1) -> P2 rows (2t-3, 2t-2) into the layer-2 stages ----------
+      auto layer1_step = [&](auto ph, int t) {
+        mbar_wait_sleep(bar_acc1_full + 8u * a1, a1_par);
+        tc_fence_after();
+        uint32_t hp[2][4];
+        b2_drain_pool<HH, decltype(ph)::value, false>(t1_base + a1 * 64, bias_a, bar_acc1_free + 8u * a1, lane0, U1, P1, Q1,
+                                                      hp);
+        a1 = (a1 + 1) & 3;
+        a1_par ^= a1 == 0;
+        // P2 row 2t-3 completes the stage of pair t-2 (= the stage before `sg`), row 2t-2 starts pair t-1 in `sg`
+        if (t >= 2) {
+          const uint32_t dst = ((sg + 3) & 3) * Cfg::kStageBytes + Cfg::kRowBytes;
+          sts128_if(sts_a + dst, hp[0], l1_lane_ok);
+          sts128_if(sts_b + dst, hp[0], l1_dup);
+          // generic-proxy writes -> visible to the tensor core's async-proxy reads, then signal the MMA issuer
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane0) mbar_arrive(bar_res_done + 8u * rg);
-          // per-channel affine A * pool + B * resized + C on fp32 pairs (fma.f32x2), both rows per coefficient load
+          if (lane0) mbar_arrive(bar_l2_full + 8u * ((sg + 3) & 3));
+        }
+        if (t >= 1 && t <= it.n2s) {  // row 2t-2 < nin2
+          mbar_wait_sleep(bar_l2_empty + 8u * sg, sg_par);  // the stage must have been consumed by the layer-2 MMAs
+          const uint32_t dst = sg * Cfg::kStageBytes;
+          sts128_if(sts_a + dst, hp[1], l1_lane_ok);
+          sts128_if(sts_b + dst, hp[1], l1_dup);
+          sg = (sg + 1) & 3;
+          sg_par ^= sg == 0;
+        }
+      };
+      // ---------------- layer 2: conv rows (2m, 2m+1) -> output rows (2m-3, 2m-2) + residual join ---------------
+      auto layer2_step = [&](auto ph) {
+        mbar_wait_sleep(bar_acc2_full + 8u * a2, a2_par);
+        tc_fence_after();
+        uint32_t hp[2][4];
+        b2_drain_pool<HH, decltype(ph)::value, true>(t1_base + R * 32 + a2 * 64, bias_a + 128, bar_acc2_free + 8u * a2, lane0,
+                                                     U2, P2, Q2, hp, coef_a);
+        // (the residual-group ring advances in lockstep with the layer-2 accumulator ring: same index, same parity)
+        const uint32_t rg = a2, rg_par = a2_par;
+        a2 = (a2 + 1) & 3;
+        a2_par ^= a2 == 0;
+        mbar_wait_sleep(bar_res_full + 8u * rg, rg_par);
+        // reference network.py:199-203 in folded form: bilinear taps in packed 16-bit arithmetic
+        // (top = tl + (tr - tl) * tx, ... : the TF formula).  Which ring rows and which vertical weight: the
+        // producer's descriptor of this group (one broadcast load); a row outside the item has weight 0xffffffff.
+        const uint4 rd = lds128(rdesc_a + 16u * rg);
+        uint32_t rs[2][4];
+        const bool row_ok0 = rd.y != 0xffffffffu, row_ok1 = rd.w != 0xffffffffu;
+        auto hlerp = [&](uint32_t (&dst)[4], uint32_t off) {
+          const uint4 l = lds128(jl + off), r = lds128(jl + off + 16);
+          dst[0] = HH::fma(HH::sub(r.x, l.x), jtx2, l.x);
+          dst[1] = HH::fma(HH::sub(r.y, l.y), jtx2, l.y);
+          dst[2] = HH::fma(HH::sub(r.z, l.z), jtx2, l.z);
+          dst[3] = HH::fma(HH::sub(r.w, l.w), jtx2, l.w);
+        };
+        {  // first row: upper source row in J (normally left there by the previous output row), lower one -> Jn
+          const uint32_t o0 = rd.x & 0xffffu, o1 = rd.x >> 16;
+          if (o0 != joff) hlerp(J, o0);
+          hlerp(Jn, o1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint8_t* co = reinterpret_cast<const uint8_t*>(s_abc) + grp_bytes + 8 * i;  // A | +128: B | +256: C
-            const f32x2_t A2 = *reinterpret_cast<const f32x2_t*>(co);
-            const f32x2_t B2 = *reinterpret_cast<const f32x2_t*>(co + 128);
-            const f32x2_t C2 = *reinterpret_cast<const f32x2_t*>(co + 256);
+          for (int i = 0; i < 4; ++i) rs[0][i] = HH::fma(HH::sub(Jn[i], J[i]), rd.y, J[i]);
+          joff = o1;
+        }
+        {  // second row: the roles of J and Jn swap, so the lower source row ends up in J again
+          const uint32_t o0 = rd.z & 0xffffu, o1 = rd.z >> 16;
+          if (o0 != joff) hlerp(Jn, o0);
+          hlerp(J, o1);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const float2 r2 = HH::unpack(rs[k][i]);
-              const float2 h2 = HH::unpack(hp[k][i]);
-              float lo, hi;
-              f2_unpack(f2_fma(A2, f2_pack(h2.x, h2.y), f2_fma(B2, f2_pack(r2.x, r2.y), C2)), lo, hi);
+          for (int i = 0; i < 4; ++i) rs[1][i] = HH::fma(HH::sub(J[i], Jn[i]), rd.w, Jn[i]);
+          joff = o1;
+        }
+        // the ring rows of this group are in registers: hand the group back to the producer
+        __syncwarp();
+        if (lane0) mbar_arrive(bar_res_done + 8u * rg);
+        // out = A * pool + (B * resized + C): A was applied to the fp32 window sums, B is a 16-bit value by construction
+        // (engine.cu stores the channel with a gain that makes it one) and multiplies the 16-bit resized residual
+        // in a mixed-precision fma with fp32 accumulation; the pooled 16-bit value joins through a mixed-precision add
+        {
+          const uint4 C0 = lds128(coef_a + 32), C1 = lds128(coef_a + 48), Bh = lds128(coef_a + 64);
+          const uint32_t Bv[4] = {Bh.x, Bh.y, Bh.z, Bh.w};
+          const float Cv[8] = {__uint_as_float(C0.x), __uint_as_float(C0.y), __uint_as_float(C0.z), __uint_as_float(C0.w),
+                               __uint_as_float(C1.x), __uint_as_float(C1.y), __uint_as_float(C1.z), __uint_as_float(C1.w)};
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float lo = HH::fhadd_lo(hp[k][i], HH::fhfma_lo(rs[k][i], Bv[i], Cv[2 * i]));
+              const float hi = HH::fhadd_hi(hp[k][i], HH::fhfma_hi(rs[k][i], Bv[i], Cv[2 * i + 1]));
               hp[k][i] = HH::pack(lo, hi);
             }
-          }
-          stg128_if(optr, hp[0], col_ok && row_ok[0]);
-          stg128_if(optr + out_row_bytes, hp[1], col_ok && row_ok[1]);
-          optr += 2 * out_row_bytes;
         }
+        stg128_if(optr, hp[0], col_ok && row_ok0);
+        stg128_if(optr + out_row_bytes, hp[1], col_ok && row_ok1);
+        optr += 2 * out_row_bytes;
+      };
+
+      // Layer 1 runs kB2LagEpi = 5 row pairs ahead of layer 2 (n1e = n2e + 3 >= 5).  The window phases alternate
+      // per call; every item starts in phase 0 and the step sequence is arranged so that they are compile-time:
+      //   5 x L1 | pairs of {L1<1> L2<0> L1<0> L2<1>} | [L1<1>] L2<0> L2<1> [L2<0>]   (bracketed if n2e is odd)
+      constexpr std::integral_constant<int, 0> ph0{};
+      constexpr std::integral_constant<int, 1> ph1{};
+      static_assert(kB2LagEpi == 5, "the phase schedule below is written for a lag of five row pairs");
+      layer1_step(ph0, 0);
+      layer1_step(ph1, 1);
+      layer1_step(ph0, 2);
+      layer1_step(ph1, 3);
+      layer1_step(ph0, 4);
+      int t = kB2LagEpi;
+      for (; t + 2 <= it.n1e; t += 2) {  // steady state
+        layer1_step(ph1, t);
+        layer2_step(ph0);
+        layer1_step(ph0, t + 1);
+        layer2_step(ph1);
       }
+      const bool odd = t < it.n1e;
+      if (odd) layer1_step(ph1, t);
+      layer2_step(ph0);
+      layer2_step(ph1);
+      if (odd) layer2_step(ph0);
     }
   }
 
@@ -682,7 +715,7 @@ bool Block2FusedSupported(const TcConvLayer& l1, const TcConvLayer& l2) {
   if ((l2.out_side + kB2StripOut - 1) / kB2StripOut > kB2MaxStrips) return false;
   // residual window of a strip / of three consecutive row groups must fit the shared-memory ring
   const float scale = static_cast<float>(l1.in_side) / static_cast<float>(l2.out_side);
-  if (scale < 1.f || scale * (kB2StripOut - 1) + 3.f > static_cast<float>(kB2ResPx)) return false;
+  if (l1.in_side <= l2.out_side || scale * (kB2StripOut - 1) + 3.f > static_cast<float>(kB2ResPx)) return false;
   if (scale * 5.f + 2.f > static_cast<float>(kB2ResRows)) return false;
   return true;
 }

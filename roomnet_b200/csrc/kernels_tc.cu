@@ -1128,7 +1128,21 @@ size_t ChunkedBytes(int n, int side, int channels) {
   return static_cast<size_t>(n) * side * side * channels * 2 + kSlackBytes;
 }
 
-size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKind kind, double scale, void* out_host) {
+double RoundToHalfKind(double v, HalfKind kind) {
+  const uint16_t bits = to_half_bits(v, kind);
+  if (kind == HalfKind::kBF16) {
+    const uint32_t u = static_cast<uint32_t>(bits) << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return static_cast<double>(f);
+  }
+  __half_raw hr;
+  hr.x = bits;
+  return static_cast<double>(__half2float(__half(hr)));
+}
+
+size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKind kind, double scale, void* out_host,
+                     const double* in_scale) {
   const int cb = cin / 8;
   const bool paired = cb == 1;
   const int planes = paired ? 4 : 3 * cb;
@@ -1147,6 +1161,7 @@ size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKin
         for (int oc = 0; oc < cp; ++oc)
           for (int e = 0; e < 8; ++e) {
             double v = scale * w[(((dy * 3 + dx) * cin) + c0 + e) * cout + part * cp + oc];
+            if (in_scale) v *= in_scale[c0 + e];
             o[part * (part_bytes / 2) + ((static_cast<size_t>(pl) * 3 * cp + j * cp + oc) * 8) + e] =
                 to_half_bits(v, kind);
           }

@@ -243,6 +243,49 @@ struct H2 {
       return *reinterpret_cast<uint32_t*>(&r);
     }
   }
+  // mixed-precision fma (sm_100: FHFMA): fp32 acc + (16-bit x) * (16-bit y) taken from the low / high half of a packed
+  // pair - no unpack instructions, one full-rate fma-pipe slot per element
+  __device__ static __forceinline__ float fhfma_lo(uint32_t x, uint32_t y, float acc) {
+    float r;
+    if constexpr (BF16) {
+      asm("{.reg .b16 xl, xh, yl, yh; mov.b32 {xl, xh}, %1; mov.b32 {yl, yh}, %2; fma.rn.f32.bf16 %0, xl, yl, %3;}"
+          : "=f"(r) : "r"(x), "r"(y), "f"(acc));
+    } else {
+      asm("{.reg .b16 xl, xh, yl, yh; mov.b32 {xl, xh}, %1; mov.b32 {yl, yh}, %2; fma.rn.f32.f16 %0, xl, yl, %3;}"
+          : "=f"(r) : "r"(x), "r"(y), "f"(acc));
+    }
+    return r;
+  }
+  __device__ static __forceinline__ float fhfma_hi(uint32_t x, uint32_t y, float acc) {
+    float r;
+    if constexpr (BF16) {
+      asm("{.reg .b16 xl, xh, yl, yh; mov.b32 {xl, xh}, %1; mov.b32 {yl, yh}, %2; fma.rn.f32.bf16 %0, xh, yh, %3;}"
+          : "=f"(r) : "r"(x), "r"(y), "f"(acc));
+    } else {
+      asm("{.reg .b16 xl, xh, yl, yh; mov.b32 {xl, xh}, %1; mov.b32 {yl, yh}, %2; fma.rn.f32.f16 %0, xh, yh, %3;}"
+          : "=f"(r) : "r"(x), "r"(y), "f"(acc));
+    }
+    return r;
+  }
+  // mixed-precision add (FHADD): fp32 acc + 16-bit x from the low / high half of a packed pair
+  __device__ static __forceinline__ float fhadd_lo(uint32_t x, float acc) {
+    float r;
+    if constexpr (BF16) {
+      asm("{.reg .b16 xl, xh; mov.b32 {xl, xh}, %1; add.rn.f32.bf16 %0, xl, %2;}" : "=f"(r) : "r"(x), "f"(acc));
+    } else {
+      asm("{.reg .b16 xl, xh; mov.b32 {xl, xh}, %1; add.rn.f32.f16 %0, xl, %2;}" : "=f"(r) : "r"(x), "f"(acc));
+    }
+    return r;
+  }
+  __device__ static __forceinline__ float fhadd_hi(uint32_t x, float acc) {
+    float r;
+    if constexpr (BF16) {
+      asm("{.reg .b16 xl, xh; mov.b32 {xl, xh}, %1; add.rn.f32.bf16 %0, xh, %2;}" : "=f"(r) : "r"(x), "f"(acc));
+    } else {
+      asm("{.reg .b16 xl, xh; mov.b32 {xl, xh}, %1; add.rn.f32.f16 %0, xh, %2;}" : "=f"(r) : "r"(x), "f"(acc));
+    }
+    return r;
+  }
   __device__ static __forceinline__ uint32_t sixteenth(uint32_t a) {  // exact: power-of-two scale
     if constexpr (BF16) {
       __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), __floats2bfloat162_rn(0.0625f, 0.0625f));
