@@ -70,7 +70,8 @@ struct B2Params {
   const float* bias2;
   const float* abc;    // [3][32] join coefficients A, B, C
   int N, in_side, out_side;
-  int n_strips, rows_per_item, n_rowblocks, n_items;
+  int n_strips;
+  int total_rows, min_piece;  // work line of N x out_side output rows (tc_common.cuh: rn_gang_rows)
   float res_scale;     // in_side / out_side as float32 (TF computes the resize scale in float32)
   int x0[kB2MaxStrips];      // first column a strip computes (input, P2 and output columns share the origin)
   int own_lo[kB2MaxStrips];  // output columns [own_lo, own_hi) are stored by the strip
@@ -88,14 +89,13 @@ struct B2Item {
   int n1s, n1e, n2s, n2e;          // R2 stage loads, epilogue-1 steps, P2 pairs, epilogue-2 steps
 };
 
-__device__ __forceinline__ B2Item b2_decode(const B2Params& p, int item) {
+// the piece of the CTA's row range [.., hi) that starts at line position `cur`
+__device__ __forceinline__ B2Item b2_decode(const B2Params& p, int cur, int hi) {
   B2Item it;
-  const int rb = item % p.n_rowblocks;
-  const int t = item / p.n_rowblocks;
-  it.strip = t % p.n_strips;
-  it.n = t / p.n_strips;
-  it.po0 = rb * p.rows_per_item;
-  it.npo = min(p.rows_per_item, p.out_side - it.po0);
+  it.n = cur / p.out_side;
+  it.strip = blockIdx.x % p.n_strips;
+  it.po0 = cur - it.n * p.out_side;
+  it.npo = min(p.out_side - it.po0, hi - cur);
   it.nconv3 = (it.npo + 3 + 1) & ~1;  // conv rows of layer 2 (one never-stored extra row when odd)
   it.nin2 = it.nconv3 + 2;            // P2 rows layer 2 reads = pooled rows layer 1 must produce
   it.nconv2 = it.nin2 + 4;            // conv rows of layer 1 (nin2 + 3, rounded up to even)
@@ -339,7 +339,8 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   pdl_trigger();
-
+  int row_lo, row_hi;  // this CTA's share of the work line
+  rn_gang_rows(blockIdx.x / p.n_strips, gridDim.x / p.n_strips, p.total_rows, p.out_side, p.min_piece, &row_lo, &row_hi);
 
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kB2RegsCtl));
   if (warp == 0) {
@@ -354,8 +355,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       uint32_t st = 0, ph = 1;  // waiting parity 1 on a fresh "empty" barrier passes immediately
       uint32_t G1 = 0;          // global layer-1 conv-row counter (same sequence as the MMA issuer's)
       const uint32_t stage0 = smem_u32(s_st1);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const B2Item it = b2_decode(p, item);
+      for (int cur = row_lo; cur < row_hi;) {
+        const B2Item it = b2_decode(p, cur, row_hi);
+        cur += it.npo;
         const CUtensorMap* tmap = &maps.m[it.strip];
         const int row0 = it.n * p.in_side + it.po0;  // tensor-map row of R2 row 0 of the item
         for (int r = 0; r < it.nin1; r += 2) {
@@ -384,8 +386,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       pdl_wait();
       uint32_t GG = 0;  // global residual-group counter (same sequence as the epilogue's)
       const uint32_t res0 = smem_u32(s_res);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const B2Item it = b2_decode(p, item);
+      for (int cur = row_lo; cur < row_hi;) {
+        const B2Item it = b2_decode(p, cur, row_hi);
+        cur += it.npo;
         // residual window of the strip: columns [jb, jb + 112) of the source rows, one TMA box per row
         const int jb2 = 2 * static_cast<int>(static_cast<float>(p.x0[it.strip]) * p.res_scale);  // in 8-byte elements
         const int row_base = it.n * p.in_side;
@@ -438,8 +441,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       const uint32_t b_lo0 = (smem_u32(s_w1) >> 4) | (Cfg::kBLbo16 << 16);
       const uint32_t idesc0 = make_idesc(0, BF16 ? 1 : 0);
       uint32_t st = 0, ph = 0, G = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const B2Item it = b2_decode(p, item);
+      for (int cur = row_lo; cur < row_hi;) {
+        const B2Item it = b2_decode(p, cur, row_hi);
+        cur += it.npo;
         for (int r0 = 0; r0 < it.nin1; r0 += 2) {
           mbar_wait_sleep(bar_l1_full + 8u * st, ph);
           tc_fence_after();
@@ -464,8 +468,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
       const uint32_t b_lo0 = (smem_u32(s_w2) >> 4) | (Cfg::kBLbo16 << 16);
       const uint32_t idesc0 = make_idesc(0, BF16 ? 1 : 0);
       uint32_t st = 0, ph = 0, G = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const B2Item it = b2_decode(p, item);
+      for (int cur = row_lo; cur < row_hi;) {
+        const B2Item it = b2_decode(p, cur, row_hi);
+        cur += it.npo;
         for (int r0 = 0; r0 < it.nin2; r0 += 2) {
           if (r0 < it.nconv3) {  // the accumulators this input pair starts must be drained and re-initialised
             const uint32_t gy = G + r0;
@@ -555,8 +560,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
     // ring positions, advanced incrementally (all rings have four entries): accumulator pair + parity of the two
     // layers, P2 stage + parity of the stage the even row of an epilogue-1 step starts, residual group + parity
     uint32_t a1 = 0, a1_par = 0, a2 = 0, a2_par = 0, sg = 0, sg_par = 1;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const B2Item it = b2_decode(p, item);
+    for (int cur = row_lo; cur < row_hi;) {
+      const B2Item it = b2_decode(p, cur, row_hi);
+      cur += it.npo;
       const int x0 = p.x0[it.strip];
       const int col = x0 + rel2;
       const bool col_ok = l2_lane_ok && col >= p.own_lo[it.strip] && col < p.own_hi[it.strip];
@@ -741,28 +747,11 @@ cudaError_t Block2Fused(const TcConvLayer& l1, const TcConvLayer& l2, const void
     p.own_lo[k] = k * kB2StripOut;
     p.own_hi[k] = std::min((k + 1) * kB2StripOut, p.out_side);
   }
-  // Row blocks: items are dealt round-robin to the persistent CTAs; pick the split that minimises
-  // (items per CTA, rounded up) x (row pairs per item + halo rows of the two layers + pipeline fill).
-  {
-    const int ctas = std::max(1, SmCount());
-    const int max_nrb = std::max(1, p.out_side / 8);
-    long best_cost = -1;
-    int best_rows = p.out_side;
-    for (int nrb = 1; nrb <= max_nrb; ++nrb) {
-      const int rows = (p.out_side + nrb - 1) / nrb;
-      const int blocks = (p.out_side + rows - 1) / rows;
-      const long items = static_cast<long>(N) * p.n_strips * blocks;
-      const long rounds = (items + ctas - 1) / ctas;
-      const long cost = rounds * (rows + 10 + 2 * kB2LagEpi);
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best_rows = rows;
-      }
-    }
-    p.rows_per_item = best_rows;
-    p.n_rowblocks = (p.out_side + best_rows - 1) / best_rows;
-  }
-  p.n_items = N * p.n_strips * p.n_rowblocks;
+  // every gang of n_strips CTAs gets the same share of the (image x output row) line (tc_common.cuh)
+  p.total_rows = N * p.out_side;
+  int gangs = 1;
+  rn_plan_rows(p.total_rows, p.out_side, p.n_strips, std::max(p.n_strips, SmCount()), &gangs, &p.min_piece);
+  const int gx = gangs * p.n_strips;
 
   const PFN_encodeTiled encode = GetEncodeTiled();
   if (!encode) return cudaErrorNotSupported;
@@ -796,7 +785,6 @@ cudaError_t Block2Fused(const TcConvLayer& l1, const TcConvLayer& l2, const void
   auto kern = kind == HalfKind::kBF16 ? block2_fused_kernel<true> : block2_fused_kernel<false>;
   cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kB2SmemBytes);
   if (ea != cudaSuccess) return ea;
-  const int gx = std::max(1, std::min(p.n_items, SmCount()));
   cudaError_t el = LaunchPdl(kern, dim3(gx), dim3(kB2Threads), kB2SmemBytes, st, N, p, maps);
   if (el != cudaSuccess) return el;
   return cudaGetLastError();

@@ -45,9 +45,8 @@ struct TcParams {
   int strip_step_out; // output column step between strips
   int win_step_in;    // POOL != 0: input-pixel step between the four 32-lane windows of a tile
   int win_step_out;   // ... and the number of output columns each window produces
-  int rows_per_item;  // pooled (output) rows per work item
-  int n_rowblocks;
-  int n_items;
+  int total_rows;     // work line: image groups x out_side pooled rows (tc_common.cuh: rn_gang_rows)
+  int min_piece;      // ... and the snapping distance of the CTA ranges
   int w_bytes;        // packed weight bytes per part
   // fused residual join (JOIN kernels): out = A*h + B*resize_bilinear_legacy(src)[y][x] + C
   const uint8_t* res_src;  // chunked tensor [n][y][c/8][x][8], side res_side, same channel count as the output
@@ -63,19 +62,18 @@ struct Item {
   int n0, strip, x_in0, x_out0, po0, npo, c0, nconv;
 };
 
+// the piece of the CTA's row range [.., hi) that starts at line position `cur`
 template <int POOL, int SEG>
-__device__ __forceinline__ Item decode_item(const TcParams& p, int item) {
+__device__ __forceinline__ Item decode_piece(const TcParams& p, int cur, int hi) {
   Item it;
-  int rb = item % p.n_rowblocks;
-  int t = item / p.n_rowblocks;
-  int strip = t % p.n_strips;
-  int ig = t / p.n_strips;
+  const int ig = cur / p.out_side;
+  const int strip = blockIdx.x % p.n_strips;
   it.n0 = ig * SEG;
   it.strip = strip;
   it.x_in0 = strip * p.strip_step_in;
   it.x_out0 = strip * p.strip_step_out;
-  it.po0 = rb * p.rows_per_item;
-  it.npo = min(p.rows_per_item, p.out_side - it.po0);
+  it.po0 = cur - ig * p.out_side;
+  it.npo = min(p.out_side - it.po0, hi - cur);
   if (POOL == 0) {
     it.c0 = it.po0;
     it.nconv = it.npo;
@@ -199,6 +197,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 
   const size_t in_row_bytes = static_cast<size_t>(CB) * p.in_side * 16;
   const size_t in_img_bytes = in_row_bytes * p.in_side;
+  int row_lo, row_hi;  // this CTA's share of the work line
+  rn_gang_rows(blockIdx.x / p.n_strips, gridDim.x / p.n_strips, p.total_rows, p.out_side, p.min_piece, &row_lo, &row_hi);
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -220,8 +220,9 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       // a global stride of win_step pixels (< 32), i.e. the windows overlap in memory and every window arrives
       // with its own pooling halo
       if (lane == 0) {
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-          const Item it = decode_item<POOL, SEG>(p, item);
+        for (int cur = row_lo; cur < row_hi;) {
+          const Item it = decode_piece<POOL, SEG>(p, cur, row_hi);
+          cur += it.npo;
           const int nin = it.nconv + 2;  // even
           // SEG == 1: rows of all images form one dimension; SEG == 2: (image, row) are separate dimensions
           int row = SEG == 2 ? it.c0 : it.n0 * p.in_side + it.c0;
@@ -252,8 +253,9 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       }
     } else {
       constexpr int kCopies = 2 * SEG * CB;  // two input rows per stage
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const Item it = decode_item<POOL, SEG>(p, item);
+      for (int cur = row_lo; cur < row_hi;) {
+        const Item it = decode_piece<POOL, SEG>(p, cur, row_hi);
+        cur += it.npo;
         const int nin = it.nconv + 2;
         const uint8_t* src0 = p.in + it.n0 * in_img_bytes + it.c0 * in_row_bytes + static_cast<size_t>(it.x_in0) * 16;
         const uint8_t* src1 = p.in + min(it.n0 + 1, p.N - 1) * in_img_bytes + it.c0 * in_row_bytes;
@@ -299,8 +301,9 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     const uint32_t b_lo0 = (smem_u32(s_w) >> 4) | (Cfg::kBLbo16 << 16);
     const uint32_t idesc0 = make_idesc(0, BF16 ? 1 : 0);
     uint32_t st = 0, ph = 0, G = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item<POOL, SEG>(p, item);
+    for (int cur = row_lo; cur < row_hi;) {
+      const Item it = decode_piece<POOL, SEG>(p, cur, row_hi);
+      cur += it.npo;
       const int nin = it.nconv + 2;
       for (int r0 = 0; r0 < nin; r0 += 2) {
         // The accumulators of conv rows r0, r0+1 (started by this pair) are free: the producer waited for their
@@ -392,8 +395,9 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     pdl_wait();  // before the first global store / residual gather
 
     uint32_t G = 0, iter = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const Item it = decode_item<POOL, SEG>(p, item);
+    for (int cur = row_lo; cur < row_hi;) {
+      const Item it = decode_piece<POOL, SEG>(p, cur, row_hi);
+      cur += it.npo;
       int n_img, col;
       bool col_ok;
       if (POOL == 0) {
@@ -1022,31 +1026,11 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
     p.n_strips = SEG == 2 ? 1 : (p.out_side + p.strip_step_out - 1) / p.strip_step_out;
   }
   const int groups = (N + SEG - 1) / SEG;
-  // Row blocks: items are dealt round-robin to the persistent CTAs, so the kernel lasts as long as the CTA with the
-  // most items.  Pick the split that minimises (items per CTA, rounded up) x (conv rows per item + pipeline refill),
-  // keeping >= 2 pooled rows per item; a finer split evens out the last round (and, for a handful of images, is
-  // what spreads the work over the SMs at all), a coarser one saves halo rows.
-  {
-    const int ctas = std::max(1, SmCount() / L.cout_parts);
-    const int max_nrb = std::max(1, p.out_side / 2);
-    long best_cost = -1;
-    int best_rows = p.out_side;
-    for (int nrb = 1; nrb <= max_nrb; ++nrb) {
-      const int rows = (p.out_side + nrb - 1) / nrb;
-      const int blocks = (p.out_side + rows - 1) / rows;
-      const int conv_rows = POOL == 0 ? rows : (POOL == 42 ? 2 * rows + 2 : rows + (POOL == 41 ? 3 : 2));
-      const long items = static_cast<long>(groups) * p.n_strips * blocks;
-      const long rounds = (items + ctas - 1) / ctas;
-      const long cost = rounds * (conv_rows + 4);
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best_rows = rows;
-      }
-    }
-    p.rows_per_item = best_rows;
-    p.n_rowblocks = (p.out_side + best_rows - 1) / best_rows;
-  }
-  p.n_items = groups * p.n_strips * p.n_rowblocks;
+  // every gang of n_strips CTAs gets the same share of the (image group x output row) line (tc_common.cuh)
+  p.total_rows = groups * p.out_side;
+  int gangs = 1;
+  rn_plan_rows(p.total_rows, p.out_side, p.n_strips, std::max(p.n_strips, SmCount() / L.cout_parts), &gangs, &p.min_piece);
+  const int gx = gangs * p.n_strips;
   auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL, JOIN>;
   if (JOIN) {
     if (!L.join_src || !L.join_abc) return cudaErrorInvalidValue;
@@ -1058,7 +1042,6 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   // per device (replicas of several GPUs share the process), and cheap enough to repeat
   cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   if (ea != cudaSuccess) return ea;
-  const int gx = std::max(1, std::min(p.n_items, SmCount() / L.cout_parts));
   dim3 grid(gx, L.cout_parts);
   CUtensorMap tmap;
   std::memset(&tmap, 0, sizeof(tmap));
