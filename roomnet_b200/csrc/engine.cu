@@ -30,7 +30,6 @@ Replica::Replica(int device, const NetShape& shape, int precision, int max_batch
   layerwise_ = (flags & RN_FLAG_LAYERWISE) != 0;
   half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
   first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
-  fuse_join_ = std::getenv("RN_NO_FUSED_JOIN") == nullptr;
 }
 
 Replica::~Replica() {
@@ -230,11 +229,11 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
         for (auto& v : b) v /= act_scale_[cs.join_src];
         std::vector<double> cc(f.join[i].c);
         join_gain_[i].clear();
-        if (i == 3 && i + 1 < first_f32_layer_) {
-          // Residual block 2 (kernels_block2.cu) multiplies the resized residual by B with a mixed-precision fma whose
-          // multiplier is a 16-bit value.  Rounding B would be a coherent per-channel error of 2^-12 (measured: 1e-2 on
+        if (i + 1 < first_f32_layer_) {
+          // The tensor-core kernels (kernels_block2.cu, the JOIN epilogue of kernels_tc.cu) multiply the resized
+          // residual by B with a mixed-precision fma whose multiplier is a 16-bit value.  Rounding B would be a coherent per-channel error of 2^-12 (measured: 1e-2 on
           // the logits of flat images), so the whole output channel is stored with a gain g = round16(B) / B instead:
-          // g*A and g*C stay fp32, g*B is exactly representable, and conv2d_4's weights of that input channel carry 1/g.
+          // g*A and g*C stay fp32, g*B is exactly representable, and the next conv's weights of that input channel carry 1/g.
           join_gain_[i].assign(cs.cout, 1.0);
           for (int k = 0; k < cs.cout; ++k) {
             const double bh = RoundToHalfKind(b[k], half_kind_);
@@ -246,9 +245,6 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
             }
           }
         }
-        RN_CUDA(UploadF32(a, &tc_ja_[i]));
-        RN_CUDA(UploadF32(b, &tc_jb_[i]));
-        RN_CUDA(UploadF32(cc, &tc_jc_[i]));
         std::vector<double> abc(a);
         abc.insert(abc.end(), b.begin(), b.end());
         abc.insert(abc.end(), cc.begin(), cc.end());
@@ -354,7 +350,7 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const void* in = shape_.conv[i - 1].join_src >= 0 ? cur_->join_h[i - 1] : cur_->act_h[i - 1];
-    if (i == 2 && !layerwise_ && fuse_join_ && shape_.conv[3].join_src == 1 && Block2FusedSupported(tc_[2], tc_[3])) {
+    if (i == 2 && !layerwise_ && shape_.conv[3].join_src == 1 && Block2FusedSupported(tc_[2], tc_[3])) {
       // residual block 2 in one kernel: conv2d_2's output stays in shared memory (kernels_block2.cu)
       RN_CUDA(Block2Fused(tc_[2], tc_[3], cur_->act_h[1], cur_->join_h[3], n, half_kind_, st));
       Mark("block2_tc", st);
@@ -362,20 +358,14 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
       i = 3;
       continue;
     }
-    if (cs.join_src >= 0 && fuse_join_) {
+    if (cs.join_src >= 0) {  // the residual join runs in the conv epilogue
       TcConvLayer L = tc_[i];
       L.join_src = cur_->act_h[cs.join_src];
       RN_CUDA(ConvTc(L, in, cur_->join_h[i], n, half_kind_, st));
-      Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
-      continue;
+    } else {
+      RN_CUDA(ConvTc(tc_[i], in, cur_->act_h[i], n, half_kind_, st));
     }
-    RN_CUDA(ConvTc(tc_[i], in, cur_->act_h[i], n, half_kind_, st));
     Mark(("conv" + std::to_string(i) + "_tc").c_str(), st);
-    if (cs.join_src >= 0) {
-      RN_CUDA(JoinH(cur_->act_h[i], cur_->act_h[cs.join_src], cur_->join_h[i], tc_ja_[i], tc_jb_[i], tc_jc_[i], n, cs.out_side,
-                    shape_.conv[cs.join_src].out_side, cs.cout, half_kind_, st));
-      Mark(("join" + std::to_string(i) + "_h").c_str(), st);
-    }
   }
   const int last = first_f32_layer_ - 1;
   const ConvShape& cl = shape_.conv[last];
@@ -430,8 +420,7 @@ cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long l
   const int C = shape_.num_classes;
   // Two half-size micro-batches on two streams overlap better than one big one (see ActSet); while
   // profiling everything stays on `st` so that the per-kernel events measure isolated kernels.
-  static const bool no_overlap = std::getenv("RN_NO_OVERLAP") != nullptr;  // experiments
-  const bool overlap = !profiling_ && !no_overlap && n >= 64;
+  const bool overlap = !profiling_ && n >= 64;
   const int chunk = overlap ? std::min(max_batch_, std::max(32, (n + 1) / 2)) : max_batch_;
   if (overlap) RN_CUDA(cudaEventRecord(ev_fork_, st));
   int k = 0;
@@ -485,17 +474,7 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
   // micro-batch is small; the rest are as large as possible (kernel efficiency) while still alternating between
   // the two staging slots / activation sets so that copies overlap the previous micro-batch's kernels.
   std::vector<int> sizes;
-  if (const char* sched = std::getenv("RN_SCHED")) {  // experiments: explicit micro-batch sizes "a,b,c" (rest: max_batch_)
-    int rest = n;
-    for (const char* q = sched; *q && rest > 0;) {
-      const int m = std::min(rest, std::min(max_batch_, std::max(1, std::atoi(q))));
-      sizes.push_back(m);
-      rest -= m;
-      while (*q && *q != ',') ++q;
-      if (*q == ',') ++q;
-    }
-    for (; rest > 0; rest -= std::min(rest, max_batch_)) sizes.push_back(std::min(rest, max_batch_));
-  } else if (n >= 128) {
+  if (n >= 128) {
     const int first = std::min(max_batch_, std::max(32, n / 4));
     sizes.push_back(first);
     int rest = n - first;

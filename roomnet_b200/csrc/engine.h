@@ -98,9 +98,6 @@ class Replica {
   double act_scale_[kNumConvs] = {};
   float* tc_bias_[kNumConvs] = {};
   void* tc0_w_[2] = {nullptr, nullptr};  // conv0 packed weights for uint8 BGR / RGB byte order
-  float* tc_ja_[kNumConvs] = {};
-  float* tc_jb_[kNumConvs] = {};
-  float* tc_jc_[kNumConvs] = {};
   float* tc_abc_[kNumConvs] = {};  // [3][cout] A/B/C for the join fused into the conv epilogue
   std::vector<double> join_gain_[kNumConvs];  // per-channel gain a join output is stored with (empty = none)
   HalfKind half_kind_ = HalfKind::kF16;
@@ -124,8 +121,6 @@ class Replica {
   ActSet* cur_ = &sets_[0];
   cudaEvent_t ev_fork_ = nullptr;
   int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
-  bool fuse_join_ = true;    // residual joins fused into the conv epilogue (RN_NO_FUSED_JOIN=1, read once at construction,
-                             // keeps the separate join kernel: parity cross-check only)
   bool layerwise_ = false;   // RN_FLAG_LAYERWISE: no fused residual-block kernel
   bool block2_fused_last_ = false;  // the last forward pass ran residual block 2 as one kernel
 

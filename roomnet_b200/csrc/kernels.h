@@ -85,9 +85,6 @@ cudaError_t Block2Fused(const TcConvLayer& l1, const TcConvLayer& l2, const void
 template <typename TIn>
 cudaError_t Conv0PoolH(const TIn* in, const float* w, const float* b, void* out, int N, int S, HalfKind kind,
                        cudaStream_t st);
-// out = A*p + B*resize(src) + C on chunked 16-bit tensors.
-cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, const float* B, const float* C, int N,
-                  int S, int SS, int Ch, HalfKind kind, cudaStream_t st);
 // Fused tail (conv8 .. softmax) for small maps; dbg8/dbg9 (optional) receive the NHWC outputs of conv blocks 8/9.
 bool TailFusedSupported(int s7, int channels);
 cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float* w8, const float* b8, const float* w9,

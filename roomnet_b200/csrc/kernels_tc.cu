@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
   uint8_t* s_w = smem;
   uint8_t* s_stage = smem + Cfg::kWBytes;
   float* s_bias = reinterpret_cast<float*>(s_stage + NST * Cfg::kStageBytes);
-  float* s_abc = s_bias + COUT;  // [3][COUT] join coefficients (JOIN kernels)
+  float* s_abc = s_bias + COUT;  // [3][COUT] join coefficients (JOIN kernels); the B row is re-used for ...
+  uint32_t* s_bh = reinterpret_cast<uint32_t*>(s_abc + COUT);  // ... B as packed 16-bit pairs [COUT / 2]
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 4 * COUT);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NST + 1 + R);
 
@@ -179,9 +180,16 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < COUT; i += kThreadsTc) s_bias[i] = bias_g[i];
-  if (JOIN)
-    for (int i = threadIdx.x; i < 3 * COUT; i += kThreadsTc)
+  if (JOIN) {
+    for (int i = threadIdx.x; i < 3 * COUT; i += kThreadsTc) {
+      if (i / COUT == 1) continue;
       s_abc[i] = p.join_abc[(i / COUT) * (COUT * gridDim.y) + part * COUT + (i % COUT)];
+    }
+    for (int i = threadIdx.x; i < COUT / 2; i += kThreadsTc) {
+      const float* bsrc = p.join_abc + COUT * gridDim.y + part * COUT + 2 * i;
+      s_bh[i] = HH::pack(bsrc[0], bsrc[1]);  // exact: engine.cu made B a 16-bit value
+    }
+  }
   if (POOL != 0) {
     // The 128-byte pad behind the last plane of every stage is never written by the TMA box but is read (with
     // zero weights, Cin = 8 layers) by the tap shift of lane 125: it must hold finite values, so zero it once.
@@ -383,6 +391,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     for (int c = 0; c < CG; ++c) bias_r[c] = s_bias[grp * CG + c];
     // fused join: per-channel coefficients of this thread's channels and the residual tensor's strides
     constexpr bool kJoinPreload = JOIN && CG == 8 && POOL == 41;
+    constexpr bool kJoinAFirst = true;  // A on the fp32 window sums (false: after the 16-bit rounding; same accuracy, more work)
     const uint32_t jplane_bytes = static_cast<uint32_t>(p.res_side) * 16;
     const uint32_t jrow_bytes = static_cast<uint32_t>(p.cb_out_total) * jplane_bytes;
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
@@ -458,14 +467,14 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       if (POOL == 41 || POOL == 31) optr -= static_cast<ptrdiff_t>(LAG) * out_row_bytes;
       if (POOL == 42) optr -= out_row_bytes;
 
-      // vertical pooling window, fp32 registers
-      float r1[(POOL == 41 || POOL == 31) ? CG : 1], q1[POOL != 0 ? CG : 1], q2[POOL == 41 ? CG : 1];
+      // vertical pooling window: packed fp32 pairs (add.f32x2 - one issue slot per two channels)
+      f32x2_t r1[(POOL == 41 || POOL == 31) ? NP : 1], q1[POOL != 0 ? NP : 1], q2[POOL == 41 ? NP : 1];
 #pragma unroll
-      for (int c = 0; c < (POOL != 0 ? CG : 1); ++c) q1[c] = 0.f;
+      for (int c = 0; c < (POOL != 0 ? NP : 1); ++c) q1[c] = 0ull;
 #pragma unroll
-      for (int c = 0; c < ((POOL == 41 || POOL == 31) ? CG : 1); ++c) r1[c] = 0.f;
+      for (int c = 0; c < ((POOL == 41 || POOL == 31) ? NP : 1); ++c) r1[c] = 0ull;
 #pragma unroll
-      for (int c = 0; c < (POOL == 41 ? CG : 1); ++c) q2[c] = 0.f;
+      for (int c = 0; c < (POOL == 41 ? NP : 1); ++c) q2[c] = 0ull;
 
       // it.nconv is even: two conv rows per iteration (row slots gy, gy+1)
 #pragma unroll 2
@@ -501,36 +510,42 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         uint32_t vp[2][NP];
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
-          float o0[2], o1[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int c = 2 * i + e;
-            // weights and bias carry a factor 1/6: relu6(z)/6 == saturate(z/6), one FADD.SAT
-            const float x0 = __saturatef(a[c]), x1 = __saturatef(b[c]);
-            if (POOL == 0) {
-              o0[e] = x0;
-              o1[e] = x1;
-            } else if (POOL == 42) {
-              const float q0 = x0 + x1;
-              o0[e] = q0 + q1[c];
-              o1[e] = 0.f;
-              q1[c] = q0;
-            } else if (POOL == 41) {
-              const float qa = x0 + r1[c], qb = x1 + x0;
-              o0[e] = qa + q2[c];
-              o1[e] = qb + q1[c];
-              q2[c] = qa;
-              q1[c] = qb;
-              r1[c] = x1;
-            } else {  // 31: q1 = r(y-1) + r(y-2), r1 = r(y-1)
-              o0[e] = x0 + q1[c];
-              o1[e] = x1 + (x0 + r1[c]);
-              q1[c] = x1 + x0;
-              r1[c] = x1;
-            }
+          // weights and bias carry a factor 1/6: relu6(z)/6 == saturate(z/6), one FADD.SAT
+          const f32x2_t x0 = f2_pack(__saturatef(a[2 * i]), __saturatef(a[2 * i + 1]));
+          const f32x2_t x1 = f2_pack(__saturatef(b[2 * i]), __saturatef(b[2 * i + 1]));
+          f32x2_t o0, o1 = 0ull;
+          if (POOL == 0) {
+            o0 = x0;
+            o1 = x1;
+          } else if (POOL == 42) {
+            const f32x2_t q0 = f2_add(x0, x1);
+            o0 = f2_add(q0, q1[i]);
+            q1[i] = q0;
+          } else if (POOL == 41) {  // sums of row pairs: q2 = p(y-3), q1 = p(y-2), r1 = x(y-1)
+            const f32x2_t qa = f2_add(x0, r1[i]), qb = f2_add(x1, x0);
+            o0 = f2_add(qa, q2[i]);
+            o1 = f2_add(qb, q1[i]);
+            q2[i] = qa;
+            q1[i] = qb;
+            r1[i] = x1;
+          } else {  // 31: q1 = r(y-1) + r(y-2), r1 = r(y-1)
+            o0 = f2_add(x0, q1[i]);
+            o1 = f2_add(x1, f2_add(x0, r1[i]));
+            q1[i] = f2_add(x1, x0);
+            r1[i] = x1;
           }
-          vp[0][i] = HH::pack(o0[0], o0[1]);
-          if (POOL != 42) vp[1][i] = HH::pack(o1[0], o1[1]);
+          if constexpr (JOIN && kJoinAFirst) {  // join coefficient A on the fp32 window sums (exact; the 16-bit sums then run on A*x)
+            const f32x2_t a2 = *reinterpret_cast<const f32x2_t*>(s_abc + grp * CG + 2 * i);
+            o0 = f2_mul(o0, a2);
+            if (POOL != 42) o1 = f2_mul(o1, a2);
+          }
+          float lo, hi;
+          f2_unpack(o0, lo, hi);
+          vp[0][i] = HH::pack(lo, hi);
+          if (POOL != 42) {
+            f2_unpack(o1, lo, hi);
+            vp[1][i] = HH::pack(lo, hi);
+          }
         }
 
         // ---- horizontal window with warp shuffles (every window owns its halo, see kWindows)
@@ -564,7 +579,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
               if (row >= 0 && row < it.npo) {
                 uint8_t* orow = optr + static_cast<size_t>(k) * out_row_bytes;
                 if constexpr (JOIN) {
-                  // reference network.py:199-203 in folded form; same arithmetic as join_h_kernel: bilinear taps in
+                  // reference network.py:199-203 in folded form; bilinear taps in
                   // packed 16-bit arithmetic (top = tl + (tr-tl)*tx, ...: the TF formula), the per-channel affine in
                   // fp32 (CPU emulation, DESIGN.md §2: the 16-bit lerp costs nothing measurable, a 16-bit affine
                   // would cost 4x the error budget)
@@ -596,14 +611,23 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
                   jy_prev = y1;
 #pragma unroll
                   for (int i = 0; i < NP; ++i) {
-                    const float2 rs = HH::unpack(HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]));
-                    const float2 hv = HH::unpack(hp[k][i]);
-                    // per-channel coefficients from shared memory (registers are worth more as in-flight taps)
-                    const float* co = s_abc + grp * CG + 2 * i;
-                    const float2 a2 = *reinterpret_cast<const float2*>(co);
-                    const float2 b2 = *reinterpret_cast<const float2*>(co + COUT);
-                    const float2 c2 = *reinterpret_cast<const float2*>(co + 2 * COUT);
-                    hp[k][i] = HH::pack(fmaf(a2.x, hv.x, fmaf(b2.x, rs.x, c2.x)), fmaf(a2.y, hv.y, fmaf(b2.y, rs.y, c2.y)));
+                    // out = A*pool (A already applied above) + (B * resized + C): B is a 16-bit value by construction
+                    // (engine.cu stores the channel with a gain that makes it one), mixed-precision fma / add with
+                    // fp32 accumulation straight from the packed 16-bit pairs
+                    const uint32_t rs = HH::fma(HH::sub(jbot[i], top[i]), ty2, top[i]);
+                    const uint32_t b2 = s_bh[(grp * CG) / 2 + i];
+                    const float2 c2 = *reinterpret_cast<const float2*>(s_abc + 2 * COUT + grp * CG + 2 * i);
+                    float lo = HH::fhfma_lo(rs, b2, c2.x), hi = HH::fhfma_hi(rs, b2, c2.y);
+                    if constexpr (kJoinAFirst) {
+                      lo = HH::fhadd_lo(hp[k][i], lo);
+                      hi = HH::fhadd_hi(hp[k][i], hi);
+                    } else {
+                      const float2 hv = HH::unpack(hp[k][i]);
+                      const float2 a2 = *reinterpret_cast<const float2*>(s_abc + grp * CG + 2 * i);
+                      lo = fmaf(a2.x, hv.x, lo);
+                      hi = fmaf(a2.y, hv.y, hi);
+                    }
+                    hp[k][i] = HH::pack(lo, hi);
                   }
                 }
 #pragma unroll
@@ -697,65 +721,6 @@ __global__ void __launch_bounds__(256) conv0_pool_kernel(const TIn* __restrict__
   }
 }
 
-// out = A*p + B*resize_bilinear_legacy(src) + C on chunked tensors (reference network.py:199-203 folded).
-// One block = one output row (n, y); one warp = one 8-channel plane of that row, lanes walk x, so every
-// global access is a contiguous 512-byte segment and the per-channel coefficients live in registers.
-__global__ void __launch_bounds__(256) join_h_kernel(const uint4* __restrict__ p, const uint4* __restrict__ src,
-                                                     uint4* __restrict__ out, const float* __restrict__ A,
-                                                     const float* __restrict__ B, const float* __restrict__ Cc, int S,
-                                                     int SS, int CBn, int bf16) {
-  const int n = blockIdx.x / S, y = blockIdx.x % S;
-  const int lane = threadIdx.x & 31;
-  const float scale = static_cast<float>(SS) / static_cast<float>(S);
-  const float fy = static_cast<float>(y) * scale;
-  const int y0 = static_cast<int>(floorf(fy));
-  const int y1 = min(y0 + 1, SS - 1);
-  const float ty = fy - static_cast<float>(y0);
-  for (int cb = threadIdx.x >> 5; cb < CBn; cb += blockDim.x >> 5) {
-    float a[8], b[8], c[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      a[e] = A[cb * 8 + e];
-      b[e] = B[cb * 8 + e];
-      c[e] = Cc[cb * 8 + e];
-    }
-    const uint4* row_p = p + ((static_cast<size_t>(n) * S + y) * CBn + cb) * S;
-    uint4* row_o = out + ((static_cast<size_t>(n) * S + y) * CBn + cb) * S;
-    const uint4* s0 = src + ((static_cast<size_t>(n) * SS + y0) * CBn + cb) * SS;
-    const uint4* s1 = src + ((static_cast<size_t>(n) * SS + y1) * CBn + cb) * SS;
-    for (int x = lane; x < S; x += 32) {
-      const float fx = static_cast<float>(x) * scale;
-      const int x0 = static_cast<int>(floorf(fx));
-      const int x1 = min(x0 + 1, SS - 1);
-      const float tx = fx - static_cast<float>(x0);
-      const uint4 tl = s0[x0], tr = s0[x1], bl = s1[x0], br = s1[x1];
-      const uint4 pv = row_p[x];
-      const uint32_t* ptl = &tl.x;
-      const uint32_t* ptr = &tr.x;
-      const uint32_t* pbl = &bl.x;
-      const uint32_t* pbr = &br.x;
-      const uint32_t* ppv = &pv.x;
-      uint4 o;
-      uint32_t* po = &o.x;
-#pragma unroll
-      for (int e2 = 0; e2 < 4; ++e2) {
-        float res[2];
-#pragma unroll
-        for (int hl = 0; hl < 2; ++hl) {
-          auto get = [&](const uint32_t* q) { return hl ? unpack_hi(q[e2], bf16) : unpack_lo(q[e2], bf16); };
-          const int e = e2 * 2 + hl;
-          const float va = get(ptl), vb = get(ptr), vc = get(pbl), vd = get(pbr);
-          const float top = va + (vb - va) * tx;
-          const float bot = vc + (vd - vc) * tx;
-          const float rs = top + (bot - top) * ty;
-          res[hl] = fmaf(a[e], get(ppv), fmaf(b[e], rs, c[e]));
-        }
-        po[e2] = pack2(res[0], res[1], bf16);
-      }
-      row_o[x] = o;
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // Fused tail for small maps (im_side 224: 21x21x16 in): conv 16->16 + ReLU6 + pool4/2, conv 16->16 + ReLU6 +
@@ -1229,14 +1194,6 @@ template cudaError_t Conv0PoolH<float>(const float*, const float*, const float*,
 template cudaError_t Conv0PoolH<uint8_t>(const uint8_t*, const float*, const float*, void*, int, int, HalfKind,
                                          cudaStream_t);
 
-cudaError_t JoinH(const void* p, const void* src, void* out, const float* A, const float* B, const float* C, int N,
-                  int S, int SS, int Ch, HalfKind kind, cudaStream_t st) {
-  const int cbn = Ch / 8;
-  join_h_kernel<<<N * S, std::min(256, 32 * cbn), 0, st>>>(static_cast<const uint4*>(p), static_cast<const uint4*>(src),
-                                                           static_cast<uint4*>(out), A, B, C, S, SS, cbn,
-                                                           kind == HalfKind::kBF16);
-  return cudaGetLastError();
-}
 
 bool TailFusedSupported(int s7, int channels) { return channels == kTailC && s7 <= kTailMaxSide && s7 >= 11; }
 
