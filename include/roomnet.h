@@ -99,6 +99,17 @@ int rn_set_dense0(rn_handle* h, const float* kernel /* [flat_len,32] */, int32_t
  * logits f32[n,C] (= out_op, ReLU6-clipped, network.py:43/214). */
 int rn_infer_u8_bgr(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits);
 
+/* Asynchronous form of rn_infer_u8_bgr for callers that stream batches (classify_im_dir, infer.py:65-100, feeds
+ * one image after the other; the batch scheduler here keeps two calls in flight).  rn_submit_u8_bgr enqueues the
+ * host->device copies, the kernels and the device->host result copies of one call and returns a ticket; it blocks
+ * only while both staging slots of a replica are still busy.  The output buffers (and, when `nhwc` is page-locked
+ * memory, the input) must stay valid until rn_wait(h, ticket) has returned: results are written by a later
+ * rn_submit_u8_bgr / rn_wait on the calling thread.  rn_wait(h, 0) waits for everything submitted so far; the
+ * synchronous entry points wait for earlier submissions first.  Same arithmetic, same results as rn_infer_u8_bgr. */
+int rn_submit_u8_bgr(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits,
+                     uint64_t* ticket);
+int rn_wait(rn_handle* h, uint64_t ticket);
+
 /* sess.run(outs_final, {x_tensor: im})                  network.py:131-134, :155
  * and Interpreter.run(imgData, labelProbArray)          ClassifierFloatMobileNet.java:97
  * Raw feed: NHWC float32 RGB in [-1,1], [n, S, S, 3]. */

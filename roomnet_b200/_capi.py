@@ -59,6 +59,8 @@ def _load():
         "rn_infer_f32_rgb": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_argb8888": ([vp, vp, i32, vp, vp, vp], C.c_int),
         "rn_infer_u8_bgr_device": ([vp, vp, i32, vp, vp, vp, vp], C.c_int),
+        "rn_submit_u8_bgr": ([vp, vp, i32, vp, vp, vp, C.POINTER(C.c_uint64)], C.c_int),
+        "rn_wait": ([vp, C.c_uint64], C.c_int),
         "rn_preprocess_u8": ([vp, vp, i32, i32, vp], C.c_int),
         "rn_infer_image_u8_bgr": ([vp, vp, i32, i32, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
@@ -83,6 +85,7 @@ def _load():
 lib = _load()
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
+            "rn_submit_u8_bgr", "rn_wait",
             "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
@@ -200,6 +203,16 @@ class Handle:
     def infer_raw(self, fn_name, in_ptr, n, top1_ptr, probs_ptr, logits_ptr):
         """Pointer-level call (pinned host buffers owned by the caller)."""
         self._check(getattr(lib, fn_name)(self._h, in_ptr, n, top1_ptr, probs_ptr, logits_ptr))
+
+    def submit_raw(self, in_ptr, n, top1_ptr, probs_ptr, logits_ptr):
+        """rn_submit_u8_bgr on caller-owned (ideally pinned) buffers; returns the ticket for wait()."""
+        ticket = C.c_uint64()
+        self._check(lib.rn_submit_u8_bgr(self._h, in_ptr, n, top1_ptr, probs_ptr, logits_ptr, C.byref(ticket)))
+        return ticket.value
+
+    def wait(self, ticket=0):
+        """Block until every call up to `ticket` (0 = all) has delivered its results."""
+        self._check(lib.rn_wait(self._h, ticket))
 
     def infer_u8_bgr_device(self, d_in, n, d_top1, d_probs, d_logits, stream=None):
         self._check(lib.rn_infer_u8_bgr_device(self._h, d_in, n, d_top1, d_probs, d_logits, stream))

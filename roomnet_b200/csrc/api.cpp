@@ -82,6 +82,8 @@ struct rn_handle {
   int last_launches = 0;
   std::vector<double> lat_ms;
   int64_t calls = 0, images = 0;
+  uint64_t next_ticket = 1;                 // rn_submit_*: tickets are handed out in submission order
+  std::vector<cudaError_t> async_status;    // per replica: first error of a submitted call (reported by rn_wait)
 };
 
 namespace {
@@ -91,6 +93,19 @@ thread_local std::string g_create_error;
 int Fail(rn_handle* h, int code, const std::string& msg) {
   if (h) h->err = msg;
   return code;
+}
+
+// No exception crosses the C boundary (std::bad_alloc from the vectors, std::system_error from the worker threads):
+// every entry point that allocates runs its body through this.
+template <typename Fn>
+int Guarded(rn_handle* h, Fn&& fn) {
+  try {
+    return fn();
+  } catch (const std::exception& e) {
+    return Fail(h, RN_ERR_INTERNAL, std::string("internal error: ") + e.what());
+  } catch (...) {
+    return Fail(h, RN_ERR_INTERNAL, "internal error");
+  }
 }
 
 int LoadCommon(rn_handle* h, const rn::TensorMap& vars) {
@@ -104,7 +119,7 @@ int LoadCommon(rn_handle* h, const rn::TensorMap& vars) {
   return RN_OK;
 }
 
-int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1, float* probs, float* logits) {
+int InferImpl(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1, float* probs, float* logits) {
   if (!h) return RN_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(h->mu);
   if (!in || n < 0) return Fail(h, RN_ERR_INVALID_ARG, "null input or negative batch size");
@@ -129,7 +144,10 @@ int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1
   if (g == 1) {
     run(0);
   } else {
-    for (int r = 0; r < g; ++r) h->workers[r]->Submit([&run, r] { run(r); });
+    for (int r = 0; r < g; ++r) {
+      h->workers[r]->Wait();  // a shard submitted through rn_submit_* may still be enqueuing
+      h->workers[r]->Submit([&run, r] { run(r); });
+    }
     for (int r = 0; r < g; ++r) h->workers[r]->Wait();
   }
   h->last_launches = 0;
@@ -144,15 +162,90 @@ int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1
   return RN_OK;
 }
 
+// rn_submit_*: the shards of one call are enqueued by the replicas' workers (one replica: by the caller); nothing waits
+// for the GPU here unless a replica's two staging slots are both still in flight.
+int SubmitImpl(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1, float* probs, float* logits,
+               uint64_t* ticket) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (!in || n < 0 || !ticket) return Fail(h, RN_ERR_INVALID_ARG, "null input / ticket or negative batch size");
+  if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+  if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+  const uint64_t tk = h->next_ticket++;
+  *ticket = tk;
+  if (n == 0) return RN_OK;
+  const int g = static_cast<int>(h->replicas.size());
+  const int C = h->shape.num_classes;
+  const size_t per = static_cast<size_t>(h->shape.im_side) * h->shape.im_side * rn::InputBytesPerPixel(kind);
+  h->async_status.resize(g, cudaSuccess);
+  int b = 0;
+  for (int r = 0; r < g; ++r) {
+    const int m = n / g + (r < n % g ? 1 : 0);
+    if (m == 0) continue;
+    rn::Replica* rep = h->replicas[r].get();
+    cudaError_t* status = &h->async_status[r];
+    auto task = [=] {
+      cudaError_t e = rep->SubmitHost(static_cast<const char*>(in) + per * b, kind, m, top1 ? top1 + b : nullptr,
+                                      probs ? probs + static_cast<size_t>(b) * C : nullptr,
+                                      logits ? logits + static_cast<size_t>(b) * C : nullptr, tk);
+      if (e != cudaSuccess && *status == cudaSuccess) *status = e;
+    };
+    if (g == 1) {
+      task();
+    } else {
+      h->workers[r]->Wait();  // the previous call's shard has been enqueued
+      h->workers[r]->Submit(task);
+    }
+    b += m;
+  }
+  h->calls += 1;
+  h->images += n;
+  if (g == 1 && h->async_status[0] != cudaSuccess) {
+    h->async_status[0] = cudaSuccess;
+    return Fail(h, RN_ERR_CUDA, h->replicas[0]->error());
+  }
+  return RN_OK;
+}
+
+int WaitImpl(rn_handle* h, uint64_t ticket) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (ticket == 0) ticket = ~0ull;
+  const int g = static_cast<int>(h->replicas.size());
+  int rc = RN_OK;
+  for (int r = 0; r < g; ++r) {
+    if (g > 1) h->workers[r]->Wait();
+    cudaError_t e = h->replicas[r]->WaitHost(ticket);
+    if (r < static_cast<int>(h->async_status.size()) && h->async_status[r] != cudaSuccess) {
+      e = h->async_status[r];
+      h->async_status[r] = cudaSuccess;
+    }
+    if (e != cudaSuccess && rc == RN_OK) rc = Fail(h, RN_ERR_CUDA, h->replicas[r]->error());
+  }
+  return rc;
+}
+
+int Infer(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1, float* probs, float* logits) {
+  return Guarded(h, [&] { return InferImpl(h, in, kind, n, top1, probs, logits); });
+}
+
 }  // namespace
 
 extern "C" {
+
+int rn_submit_u8_bgr(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits,
+                     uint64_t* ticket) {
+  return Guarded(h, [&] { return SubmitImpl(h, nhwc, InputKind::kU8Bgr, n, top1, probs, logits, ticket); });
+}
+int rn_wait(rn_handle* h, uint64_t ticket) {
+  return Guarded(h, [&] { return WaitImpl(h, ticket); });
+}
 
 const char* rn_version(void) { return "roomnet_b200 0.1 (sm_100a)"; }
 
 const char* rn_last_error(const rn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
-int rn_create(const rn_config* cfg, rn_handle** out) {
+static int CreateImpl(const rn_config* cfg, rn_handle** out) {
   g_create_error.clear();
   if (!cfg || !out) {
     g_create_error = "null config or output pointer";
@@ -218,7 +311,7 @@ int rn_destroy(rn_handle* h) {
   return RN_OK;
 }
 
-int rn_load_tf_checkpoint(rn_handle* h, const char* prefix) {
+static int LoadCheckpointImpl(rn_handle* h, const char* prefix) {
   if (!h) return RN_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(h->mu);
   if (!prefix) return Fail(h, RN_ERR_INVALID_ARG, "null checkpoint prefix");
@@ -230,8 +323,8 @@ int rn_load_tf_checkpoint(rn_handle* h, const char* prefix) {
   return LoadCommon(h, vars);
 }
 
-int rn_load_tensors(rn_handle* h, int32_t n, const char* const* names, const float* const* data,
-                    const int64_t* const* shapes, const int32_t* ranks) {
+static int LoadTensorsImpl(rn_handle* h, int32_t n, const char* const* names, const float* const* data,
+                           const int64_t* const* shapes, const int32_t* ranks) {
   if (!h) return RN_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lock(h->mu);
   if (n < 0 || !names || !data || !shapes || !ranks) return Fail(h, RN_ERR_INVALID_ARG, "null argument");
@@ -247,6 +340,25 @@ int rn_load_tensors(rn_handle* h, int32_t n, const char* const* names, const flo
     vars[names[i]] = std::move(t);
   }
   return LoadCommon(h, vars);
+}
+
+int rn_create(const rn_config* cfg, rn_handle** out) {
+  try {
+    return CreateImpl(cfg, out);
+  } catch (const std::exception& e) {
+    g_create_error = std::string("internal error: ") + e.what();
+  } catch (...) {
+    g_create_error = "internal error";
+  }
+  if (out) *out = nullptr;
+  return RN_ERR_INTERNAL;
+}
+int rn_load_tf_checkpoint(rn_handle* h, const char* prefix) {
+  return Guarded(h, [&] { return LoadCheckpointImpl(h, prefix); });
+}
+int rn_load_tensors(rn_handle* h, int32_t n, const char* const* names, const float* const* data,
+                    const int64_t* const* shapes, const int32_t* ranks) {
+  return Guarded(h, [&] { return LoadTensorsImpl(h, n, names, data, shapes, ranks); });
 }
 
 int rn_set_dense0(rn_handle* h, const float* kernel, int32_t flat_len) {

@@ -38,8 +38,9 @@ Replica::~Replica() {
   for (void* p : allocs_) cudaFree(p);
   if (d_raw_) cudaFree(d_raw_);
   for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 2; ++i)
     if (h_in_[i]) cudaFreeHost(h_in_[i]);
+  for (int i = 0; i < kSlots; ++i) {
     if (h_out_[i]) cudaFreeHost(h_out_[i]);
     if (ev_h2d_[i]) cudaEventDestroy(ev_h2d_[i]);
     if (ev_done_[i]) cudaEventDestroy(ev_done_[i]);
@@ -76,7 +77,7 @@ cudaError_t Replica::Init() {
   }
   RN_CUDA(cudaStreamCreateWithFlags(&compute_, cudaStreamNonBlocking));
   RN_CUDA(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < kSlots; ++i) {
     RN_CUDA(cudaEventCreateWithFlags(&ev_h2d_[i], cudaEventDisableTiming));
     RN_CUDA(cudaEventCreateWithFlags(&ev_done_[i], cudaEventDisableTiming));
   }
@@ -116,9 +117,9 @@ cudaError_t Replica::Init() {
   }
   cur_ = &sets_[0];
   const size_t in_bytes = InputBytesPerImage(shape_, InputKind::kF32Rgb) * B;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 2; ++i) RN_CUDA(cudaMallocHost(&h_in_[i], in_bytes));
+  for (int i = 0; i < kSlots; ++i) {
     RN_CUDA(Alloc(&d_in_[i], in_bytes));
-    RN_CUDA(cudaMallocHost(&h_in_[i], in_bytes));
     RN_CUDA(Alloc(reinterpret_cast<void**>(&d_top1_[i]), B * sizeof(long long)));
     RN_CUDA(Alloc(reinterpret_cast<void**>(&d_probs_[i]), B * C * sizeof(float)));
     RN_CUDA(Alloc(reinterpret_cast<void**>(&d_logits_[i]), B * C * sizeof(float)));
@@ -422,6 +423,12 @@ cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long l
   // profiling everything stays on `st` so that the per-kernel events measure isolated kernels.
   const bool overlap = !profiling_ && n >= 64;
   const int chunk = overlap ? std::min(max_batch_, std::max(32, (n + 1) / 2)) : max_batch_;
+  // the activation sets are shared with the host entry points, whose work runs on the sets' own streams: order this
+  // call after whatever they still have in flight (and, below, later host calls after this one)
+  for (int si = 0; si < 2; ++si) {
+    RN_CUDA(cudaEventRecord(sets_[si].ev_done, sets_[si].stream));
+    RN_CUDA(cudaStreamWaitEvent(st, sets_[si].ev_done, 0));
+  }
   if (overlap) RN_CUDA(cudaEventRecord(ev_fork_, st));
   int k = 0;
   for (int off = 0; off < n; off += chunk, ++k) {
@@ -439,11 +446,59 @@ cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long l
       RN_CUDA(cudaEventRecord(sets_[si].ev_done, sets_[si].stream));
       RN_CUDA(cudaStreamWaitEvent(st, sets_[si].ev_done, 0));
     }
+  } else {
+    RN_CUDA(cudaEventRecord(ev_fork_, st));
+    RN_CUDA(cudaStreamWaitEvent(sets_[0].stream, ev_fork_, 0));
+  }
+  return cudaSuccess;
+}
+
+cudaError_t Replica::DrainSlot(int slot) {
+  PendingOut& q = pend_[slot];
+  if (!q.active) return cudaSuccess;
+  q.active = false;
+  RN_CUDA(cudaEventSynchronize(ev_done_[slot]));
+  const int C = shape_.num_classes;
+  const char* base = h_out_[slot];
+  if (q.top1) std::memcpy(q.top1, base, q.m * sizeof(long long));
+  if (q.probs) std::memcpy(q.probs, base + max_batch_ * sizeof(long long), static_cast<size_t>(q.m) * C * sizeof(float));
+  if (q.logits)
+    std::memcpy(q.logits, base + max_batch_ * (sizeof(long long) + C * sizeof(float)),
+                static_cast<size_t>(q.m) * C * sizeof(float));
+  return cudaSuccess;
+}
+
+// error path: nothing of this replica may still be running (or be delivered) when the failing call returns
+void Replica::AbortPending() {
+  cudaDeviceSynchronize();
+  for (auto& q : pend_) q.active = false;
+}
+
+cudaError_t Replica::WaitHost(uint64_t ticket) {
+  RN_CUDA(cudaSetDevice(device_));
+  for (int s = 0; s < kSlots; ++s) {  // oldest slot first
+    const int slot = (slot_seq_ + s) % kSlots;
+    if (pend_[slot].active && pend_[slot].ticket <= ticket) {
+      cudaError_t e = DrainSlot(slot);
+      if (e != cudaSuccess) {
+        AbortPending();
+        return e;
+      }
+    }
   }
   return cudaSuccess;
 }
 
 cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits) {
+  cudaError_t e = WaitHost(~0ull);  // a synchronous call comes after everything submitted before it
+  if (e != cudaSuccess) return e;
+  e = SubmitHost(h_in, kind, n, top1, probs, logits, 0);
+  if (e != cudaSuccess) return e;
+  return WaitHost(~0ull);
+}
+
+cudaError_t Replica::SubmitHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits,
+                                uint64_t ticket) {
   RN_CUDA(cudaSetDevice(device_));
   last_launches_ = 0;
   const size_t per = InputBytesPerImage(shape_, kind);
@@ -451,33 +506,19 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
   cudaPointerAttributes attr;
   bool pinned_in = cudaPointerGetAttributes(&attr, h_in) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may set a sticky-less error
-  const size_t out_stride = sizeof(long long) + 2 * C * sizeof(float);
-  struct Pending {
-    int off = 0, m = 0;
-    bool active = false;
-  } pend[2];
-  auto drain = [&](int slot) -> cudaError_t {
-    if (!pend[slot].active) return cudaSuccess;
-    RN_CUDA(cudaEventSynchronize(ev_done_[slot]));
-    const int off = pend[slot].off, m = pend[slot].m;
-    const char* base = h_out_[slot];
-    if (top1) std::memcpy(top1 + off, base, m * sizeof(long long));
-    if (probs) std::memcpy(probs + static_cast<size_t>(off) * C, base + max_batch_ * sizeof(long long), m * C * sizeof(float));
-    if (logits)
-      std::memcpy(logits + static_cast<size_t>(off) * C, base + max_batch_ * (sizeof(long long) + C * sizeof(float)),
-                  m * C * sizeof(float));
-    pend[slot].active = false;
-    return cudaSuccess;
-  };
-  (void)out_stride;
-  // Micro-batch schedule of one call: the first H2D copy is exposed (nothing to overlap with), so the first
+  // Micro-batch schedule of one call: the first H2D copy is exposed when nothing is in flight, so the first
   // micro-batch is small; the rest are as large as possible (kernel efficiency) while still alternating between
   // the two staging slots / activation sets so that copies overlap the previous micro-batch's kernels.
   std::vector<int> sizes;
+  bool idle = true;
+  for (const auto& q : pend_) idle = idle && !q.active;
   if (n >= 128) {
-    const int first = std::min(max_batch_, std::max(32, n / 4));
-    sizes.push_back(first);
-    int rest = n - first;
+    int rest = n;
+    if (idle) {
+      const int first = std::min(max_batch_, std::max(32, n / 4));
+      sizes.push_back(first);
+      rest -= first;
+    }
     const int parts = std::max(2, (rest + max_batch_ - 1) / max_batch_);
     for (int i = 0; i < parts; ++i) {
       const int m = rest / (parts - i);
@@ -487,40 +528,54 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
   } else {
     for (int off = 0; off < n; off += max_batch_) sizes.push_back(std::min(max_batch_, n - off));
   }
-  int k = 0, off = 0;
-  for (size_t si = 0; si < sizes.size(); off += sizes[si], ++si, ++k) {
-    const int slot = k & 1;
+  auto fail = [&](cudaError_t e) {
+    err_ = std::string("SubmitHost: ") + cudaGetErrorString(e) + " (device " + std::to_string(device_) + ")";
+    AbortPending();
+    return e;
+  };
+  int off = 0;
+  for (size_t si = 0; si < sizes.size(); off += sizes[si], ++si, ++slot_seq_) {
+    const int slot = slot_seq_ % kSlots;
     const int m = sizes[si];
-    cudaError_t e = drain(slot);  // slot buffers (d_in_, h_in_, outputs) are free after this
-    if (e != cudaSuccess) return e;
+    cudaError_t e = DrainSlot(slot);  // the slot's device / host buffers are free after this
+    if (e != cudaSuccess) return fail(e);
     const char* src = static_cast<const char*>(h_in) + per * off;
-    if (!pinned_in) {
-      std::memcpy(h_in_[slot], src, per * m);
-      src = static_cast<const char*>(h_in_[slot]);
+    if (!pinned_in) {  // pageable caller memory: through a pinned bounce buffer, reusable once its last copy is done
+      const int hb = slot_seq_ & 1;
+      if (slot_seq_ >= 2 && (e = cudaEventSynchronize(ev_h2d_[(slot_seq_ - 2) % kSlots])) != cudaSuccess) return fail(e);
+      std::memcpy(h_in_[hb], src, per * m);
+      src = static_cast<const char*>(h_in_[hb]);
     }
-    RN_CUDA(cudaMemcpyAsync(d_in_[slot], src, per * m, cudaMemcpyHostToDevice, copy_));
-    RN_CUDA(cudaEventRecord(ev_h2d_[slot], copy_));
-    cur_ = &sets_[profiling_ ? 0 : slot];
+    if ((e = cudaMemcpyAsync(d_in_[slot], src, per * m, cudaMemcpyHostToDevice, copy_)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventRecord(ev_h2d_[slot], copy_)) != cudaSuccess) return fail(e);
+    cur_ = &sets_[profiling_ ? 0 : (slot_seq_ & 1)];
     cudaStream_t cs = profiling_ ? compute_ : cur_->stream;
-    RN_CUDA(cudaStreamWaitEvent(cs, ev_h2d_[slot], 0));
+    if ((e = cudaStreamWaitEvent(cs, ev_h2d_[slot], 0)) != cudaSuccess) return fail(e);
     e = ForwardDevice(d_in_[slot], kind, m, d_top1_[slot], d_probs_[slot], d_logits_[slot], cs);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess) {
+      AbortPending();
+      return e;
+    }
     char* base = h_out_[slot];
-    RN_CUDA(cudaMemcpyAsync(base, d_top1_[slot], m * sizeof(long long), cudaMemcpyDeviceToHost, cs));
-    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[slot], m * C * sizeof(float),
-                            cudaMemcpyDeviceToHost, cs));
-    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[slot],
-                            m * C * sizeof(float), cudaMemcpyDeviceToHost, cs));
-    RN_CUDA(cudaEventRecord(ev_done_[slot], cs));
-    pend[slot].off = off;
-    pend[slot].m = m;
-    pend[slot].active = true;
+    if ((e = cudaMemcpyAsync(base, d_top1_[slot], m * sizeof(long long), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+      return fail(e);
+    if ((e = cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[slot], m * C * sizeof(float),
+                             cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+      return fail(e);
+    if ((e = cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[slot],
+                             m * C * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+      return fail(e);
+    if ((e = cudaEventRecord(ev_done_[slot], cs)) != cudaSuccess) return fail(e);
+    PendingOut& q = pend_[slot];
+    q.m = m;
+    q.active = true;
+    q.ticket = ticket;
+    q.top1 = top1 ? top1 + off : nullptr;
+    q.probs = probs ? probs + static_cast<size_t>(off) * C : nullptr;
+    q.logits = logits ? logits + static_cast<size_t>(off) * C : nullptr;
   }
-  for (int s = 0; s < 2; ++s) {
-    cudaError_t e = drain((k + s) & 1);
-    if (e != cudaSuccess) return e;
-  }
-  RN_CUDA(cudaGetLastError());
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(e);
   return cudaSuccess;
 }
 
@@ -557,6 +612,10 @@ void ResizeTaps(int dst, int src, bool vertical, int* s0, int* s1, int* w0, int*
 }  // namespace
 
 cudaError_t Replica::Preprocess(const uint8_t* h_img, int H, int W, uint8_t* h_out) {
+  {
+    cudaError_t ew = WaitHost(~0ull);  // staging slot 0 is used below: nothing submitted earlier may still own it
+    if (ew != cudaSuccess) return ew;
+  }
   RN_CUDA(cudaSetDevice(device_));
   const int S = shape_.im_side;
   // reference network.py:139: offset = abs((w - h) // 2) with Python floor division

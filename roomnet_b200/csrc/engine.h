@@ -35,6 +35,12 @@ class Replica {
                             float* d_logits, cudaStream_t st);
   // Arbitrary n from host memory (pinned or pageable), double-buffered micro-batches; synchronous.
   cudaError_t InferHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits);
+  // Asynchronous form: SubmitHost enqueues the copies and kernels of one call and returns (it blocks only when both
+  // staging slots are still in flight); the results are delivered to the caller's buffers by a later SubmitHost that
+  // needs the slot, or by WaitHost(ticket), which returns once every call up to `ticket` has been delivered.
+  cudaError_t SubmitHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits,
+                         uint64_t ticket);
+  cudaError_t WaitHost(uint64_t ticket);
   // Arbitrary n, device-resident input/outputs, micro-batched on `st` (nullptr = own stream); no sync.
   cudaError_t InferDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
                           float* d_logits, cudaStream_t st);
@@ -79,7 +85,23 @@ class Replica {
   void Mark(const char* name, cudaStream_t st);
 
   cudaStream_t compute_ = nullptr, copy_ = nullptr;
-  cudaEvent_t ev_h2d_[2] = {nullptr, nullptr}, ev_done_[2] = {nullptr, nullptr};
+  // Host entry points: a ring of kSlots staging slots (device input buffer, device/host result buffers, events) feeds
+  // the two activation sets (micro-batch j: slot j % kSlots, set j & 1).  With more slots than sets the host->device
+  // copies run up to kSlots - 1 micro-batches ahead of the kernels, so a stream of calls is bound by
+  // max(PCIe time, kernel time) instead of their partial sum.
+  static constexpr int kSlots = 4;
+  cudaEvent_t ev_h2d_[kSlots] = {}, ev_done_[kSlots] = {};
+  struct PendingOut {  // a micro-batch in flight in staging slot s: where its results go once ev_done_[s] has fired
+    int m = 0;
+    bool active = false;
+    int64_t* top1 = nullptr;
+    float* probs = nullptr;
+    float* logits = nullptr;
+    uint64_t ticket = 0;
+  } pend_[kSlots];
+  unsigned slot_seq_ = 0;  // micro-batches submitted so far
+  cudaError_t DrainSlot(int slot);
+  void AbortPending();
   std::vector<void*> allocs_;
 
   // weights (fp32, HWIO folded)
@@ -129,12 +151,12 @@ class Replica {
   size_t d_raw_cap_ = 0;
   int* d_taps_ = nullptr;
   // staging
-  void* d_in_[2] = {nullptr, nullptr};
-  void* h_in_[2] = {nullptr, nullptr};
-  long long* d_top1_[2] = {nullptr, nullptr};
-  float* d_probs_[2] = {nullptr, nullptr};
-  float* d_logits_[2] = {nullptr, nullptr};
-  char* h_out_[2] = {nullptr, nullptr};
+  void* d_in_[kSlots] = {};
+  void* h_in_[2] = {nullptr, nullptr};  // pinned bounce buffers for pageable caller memory (micro-batch j: j & 1)
+  long long* d_top1_[kSlots] = {};
+  float* d_probs_[kSlots] = {};
+  float* d_logits_[kSlots] = {};
+  char* h_out_[kSlots] = {};
 };
 
 }  // namespace rn

@@ -244,3 +244,38 @@ def test_bf16_operand_mode_runs_but_is_not_the_parity_path(capi, ckpt_prefix, su
     assert (top1 == golden["argmax"]).mean() >= 0.95
     assert err <= 0.3
     np.testing.assert_allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_submit_wait_delivers_the_same_results_as_the_synchronous_call(capi, ckpt_prefix, suite64):
+    """rn_submit_u8_bgr / rn_wait (two calls in flight, results delivered by a later submit or by wait) against
+    rn_infer_u8_bgr on the same images: bit-identical, for pageable and for pinned buffers, small and large calls."""
+    import torch
+    h = _handle(capi, ckpt_prefix, "fp16", max_batch=64)
+    batches = [suite64[:5], suite64[5:64], np.concatenate([suite64, suite64[:37]]), suite64[10:11], suite64[::-1].copy()]
+    want = [h.infer_u8_bgr(b, want_logits=True) for b in batches]
+    for pinned in (False, True):
+        bufs, tickets = [], []
+        for b in batches:
+            n = len(b)
+            x = torch.from_numpy(np.ascontiguousarray(b))
+            t1, pr, lg = torch.empty(n, dtype=torch.int64), torch.empty(n, 6), torch.empty(n, 6)
+            if pinned:
+                x, t1, pr, lg = x.pin_memory(), t1.pin_memory(), pr.pin_memory(), lg.pin_memory()
+            bufs.append((x, t1, pr, lg))
+            tickets.append(h.submit_raw(x.data_ptr(), n, t1.data_ptr(), pr.data_ptr(), lg.data_ptr()))
+            if len(tickets) == 2:
+                h.wait(tickets[0])  # the first call is complete, later ones may still be in flight
+                assert np.array_equal(bufs[0][1].numpy(), want[0][0])
+        assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+        h.wait(0)
+        for (x, t1, pr, lg), (w1, wp, wl) in zip(bufs, want):
+            assert np.array_equal(t1.numpy(), w1)
+            assert np.array_equal(pr.numpy(), wp)
+            assert np.array_equal(lg.numpy(), wl)
+    # a synchronous call after pending submissions waits for them first
+    x, t1, pr, lg = bufs[2]
+    t1.zero_()
+    tk = h.submit_raw(x.data_ptr(), len(batches[2]), t1.data_ptr(), pr.data_ptr(), lg.data_ptr())
+    again = h.infer_u8_bgr(batches[0], want_logits=True)
+    assert np.array_equal(t1.numpy(), want[2][0]) and np.array_equal(again[2], want[0][2])
+    h.wait(tk)
