@@ -144,6 +144,14 @@ int rn_preprocess_u8(rn_handle* h, const uint8_t* img, int32_t H, int32_t W, uin
 int rn_infer_image_u8_bgr(rn_handle* h, const uint8_t* img, int32_t H, int32_t W, int64_t* top1, float* probs,
                           float* logits);
 
+/* The loop of classify_im_dir                            infer.py:79-82
+ * n BGR uint8 photos of arbitrary sizes (imgs[i] is heights[i] x widths[i] x 3, packed rows): the centre crop and the
+ * cv2-identical resize of a whole micro-batch run as ONE kernel that writes the network's input tensor, followed by the
+ * forward pass - nothing returns to the host between preprocessing and inference.  The list is split over the handle's
+ * devices like any other batch.  Per image the result is bit-identical to rn_infer_image_u8_bgr. */
+int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths,
+                           int32_t n, int64_t* top1, float* probs, float* logits);
+
 /* Host-side geometry helper: writes the crop rectangle the reference would take (network.py:137-146). */
 int rn_center_crop_rect(int32_t h, int32_t w, int32_t* y0, int32_t* x0, int32_t* side);
 

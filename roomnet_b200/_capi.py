@@ -63,6 +63,7 @@ def _load():
         "rn_wait": ([vp, C.c_uint64], C.c_int),
         "rn_preprocess_u8": ([vp, vp, i32, i32, vp], C.c_int),
         "rn_infer_image_u8_bgr": ([vp, vp, i32, i32, vp, vp, vp], C.c_int),
+        "rn_infer_images_u8_bgr": ([vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), i32, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
         "rn_flat_len": ([vp], C.c_int),
         "rn_num_kernel_launches": ([vp], C.c_int),
@@ -86,7 +87,7 @@ lib = _load()
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
             "rn_submit_u8_bgr", "rn_wait",
-            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
 
@@ -198,6 +199,25 @@ class Handle:
         logits = np.empty((1, self.num_classes), np.float32)
         self._check(lib.rn_infer_image_u8_bgr(self._h, img.ctypes.data, img.shape[0], img.shape[1], top1.ctypes.data,
                                               probs.ctypes.data, logits.ctypes.data))
+        return (top1, probs, logits) if want_logits else (top1, probs)
+
+    def infer_images_u8_bgr(self, imgs, want_logits=False):
+        """List of BGR uint8 images of any size: crop + resize + forward pass on the device, one call."""
+        arrs = []
+        for img in imgs:
+            a = np.ascontiguousarray(img, dtype=np.uint8)
+            if a.ndim != 3 or a.shape[2] != 3:
+                raise RoomNetError(RN_ERR_INVALID_ARG, "image must be [H, W, 3] uint8, got %s" % (a.shape,))
+            arrs.append(a)
+        n = len(arrs)
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        hs = (C.c_int32 * n)(*[a.shape[0] for a in arrs])
+        ws = (C.c_int32 * n)(*[a.shape[1] for a in arrs])
+        top1 = np.empty((n,), np.int64)
+        probs = np.empty((n, self.num_classes), np.float32)
+        logits = np.empty((n, self.num_classes), np.float32)
+        self._check(lib.rn_infer_images_u8_bgr(self._h, ptrs, hs, ws, n, top1.ctypes.data, probs.ctypes.data,
+                                               logits.ctypes.data))
         return (top1, probs, logits) if want_logits else (top1, probs)
 
     def infer_raw(self, fn_name, in_ptr, n, top1_ptr, probs_ptr, logits_ptr):

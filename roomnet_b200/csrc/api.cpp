@@ -432,6 +432,53 @@ int rn_infer_image_u8_bgr(rn_handle* h, const uint8_t* img, int32_t hgt, int32_t
   return RN_OK;
 }
 
+int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths,
+                           int32_t n, int64_t* top1, float* probs, float* logits) {
+  return Guarded(h, [&]() -> int {
+    if (!h) return RN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!imgs || !heights || !widths || n < 0) return Fail(h, RN_ERR_INVALID_ARG, "null argument or negative count");
+    for (int i = 0; i < n; ++i)
+      if (!imgs[i] || heights[i] < 2 || widths[i] < 2)
+        return Fail(h, RN_ERR_INVALID_ARG, "image " + std::to_string(i) + ": null pointer or degenerate size");
+    if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+    if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+    if (n == 0) return RN_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    const int g = static_cast<int>(h->replicas.size());
+    const int C = h->shape.num_classes;
+    std::vector<int> begin(g + 1, 0);
+    for (int r = 0; r < g; ++r) begin[r + 1] = begin[r] + n / g + (r < n % g ? 1 : 0);
+    std::vector<cudaError_t> status(g, cudaSuccess);
+    auto run = [&](int r) {
+      const int b = begin[r], m = begin[r + 1] - begin[r];
+      if (m == 0) return;
+      status[r] = h->replicas[r]->InferImages(imgs + b, heights + b, widths + b, m, top1 ? top1 + b : nullptr,
+                                              probs ? probs + static_cast<size_t>(b) * C : nullptr,
+                                              logits ? logits + static_cast<size_t>(b) * C : nullptr);
+    };
+    if (g == 1) {
+      run(0);
+    } else {
+      for (int r = 0; r < g; ++r) {
+        h->workers[r]->Wait();
+        h->workers[r]->Submit([&run, r] { run(r); });
+      }
+      for (int r = 0; r < g; ++r) h->workers[r]->Wait();
+    }
+    h->last_launches = 0;
+    for (int r = 0; r < g; ++r) {
+      if (status[r] != cudaSuccess) return Fail(h, RN_ERR_CUDA, h->replicas[r]->error());
+      h->last_launches += h->replicas[r]->last_launches();
+    }
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (h->lat_ms.size() < (1u << 20)) h->lat_ms.push_back(ms);
+    h->calls += 1;
+    h->images += n;
+    return RN_OK;
+  });
+}
+
 int rn_center_crop_rect(int32_t hgt, int32_t wid, int32_t* y0, int32_t* x0, int32_t* side) {
   if (hgt <= 0 || wid <= 0 || !y0 || !x0 || !side) return RN_ERR_INVALID_ARG;
   // reference network.py:139: offset = abs((w - h) // 2) with Python floor division

@@ -651,6 +651,72 @@ cudaError_t Replica::Preprocess(const uint8_t* h_img, int H, int W, uint8_t* h_o
   return cudaSuccess;
 }
 
+cudaError_t Replica::InferImages(const uint8_t* const* imgs, const int* H, const int* W, int n, int64_t* top1,
+                                 float* probs, float* logits) {
+  {
+    cudaError_t ew = WaitHost(~0ull);  // uses staging slot 0 and activation set 0 on the replica's own stream
+    if (ew != cudaSuccess) return ew;
+  }
+  RN_CUDA(cudaSetDevice(device_));
+  last_launches_ = 0;
+  const int S = shape_.im_side, C = shape_.num_classes;
+  if (!d_descs_) RN_CUDA(Alloc(&d_descs_, static_cast<size_t>(max_batch_) * sizeof(CropDesc)));
+  std::vector<CropDesc> descs;
+  for (int off = 0; off < n; off += max_batch_) {
+    const int m = std::min(max_batch_, n - off);
+    descs.assign(m, CropDesc{});
+    size_t total = 0;
+    for (int i = 0; i < m; ++i) {
+      const int h = H[off + i], w = W[off + i];
+      if (!imgs[off + i] || h <= 0 || w <= 0) {
+        err_ = "image " + std::to_string(off + i) + ": null pointer or empty size";
+        return cudaErrorInvalidValue;
+      }
+      // reference network.py:139: offset = abs((w - h) // 2) with Python floor division
+      const int d = w - h;
+      const int fl = d >= 0 ? d / 2 : -((-d + 1) / 2);
+      const int o = fl < 0 ? -fl : fl;
+      descs[i].offset = total;
+      descs[i].W = w;
+      descs[i].side = std::min(h, w);
+      descs[i].cy = h > w ? o : 0;
+      descs[i].cx = w > h ? o : 0;
+      total += (static_cast<size_t>(h) * w * 3 + 255) & ~static_cast<size_t>(255);
+    }
+    if (total > d_raw_cap_) {
+      RN_CUDA(cudaStreamSynchronize(compute_));
+      if (d_raw_) cudaFree(d_raw_);
+      d_raw_ = nullptr;
+      d_raw_cap_ = 0;
+      RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_raw_), total));
+      d_raw_cap_ = total;
+    }
+    for (int i = 0; i < m; ++i)
+      RN_CUDA(cudaMemcpyAsync(d_raw_ + descs[i].offset, imgs[off + i], static_cast<size_t>(H[off + i]) * W[off + i] * 3,
+                              cudaMemcpyHostToDevice, compute_));
+    RN_CUDA(cudaMemcpyAsync(d_descs_, descs.data(), m * sizeof(CropDesc), cudaMemcpyHostToDevice, compute_));
+    RN_CUDA(CropResizeBatchU8(d_raw_, static_cast<const CropDesc*>(d_descs_), m, static_cast<uint8_t*>(d_in_[0]), S,
+                              compute_));
+    ++last_launches_;
+    cur_ = &sets_[0];
+    cudaError_t e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, m, d_top1_[0], d_probs_[0], d_logits_[0], compute_);
+    if (e != cudaSuccess) return e;
+    char* base = h_out_[0];
+    RN_CUDA(cudaMemcpyAsync(base, d_top1_[0], m * sizeof(long long), cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[0], m * C * sizeof(float),
+                            cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[0],
+                            m * C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
+    RN_CUDA(cudaStreamSynchronize(compute_));  // `descs` and the caller's images are pageable host memory
+    if (top1) std::memcpy(top1 + off, base, m * sizeof(long long));
+    if (probs) std::memcpy(probs + static_cast<size_t>(off) * C, base + max_batch_ * sizeof(long long), m * C * sizeof(float));
+    if (logits)
+      std::memcpy(logits + static_cast<size_t>(off) * C, base + max_batch_ * (sizeof(long long) + C * sizeof(float)),
+                  m * C * sizeof(float));
+  }
+  return cudaSuccess;
+}
+
 cudaError_t Replica::InferImage(const uint8_t* h_img, int H, int W, int64_t* top1, float* probs, float* logits) {
   cudaError_t e = Preprocess(h_img, H, W, nullptr);
   if (e != cudaSuccess) return e;

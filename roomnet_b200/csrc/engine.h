@@ -35,6 +35,10 @@ class Replica {
                             float* d_logits, cudaStream_t st);
   // Arbitrary n from host memory (pinned or pageable), double-buffered micro-batches; synchronous.
   cudaError_t InferHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits);
+  // n BGR uint8 photos of arbitrary sizes (imgs[i] = H[i] x W[i] x 3): centre crop + cv2-identical resize of a whole
+  // micro-batch in one launch, straight into the network input - no host round trip between the two.
+  cudaError_t InferImages(const uint8_t* const* imgs, const int* H, const int* W, int n, int64_t* top1, float* probs,
+                          float* logits);
   // Asynchronous form: SubmitHost enqueues the copies and kernels of one call and returns (it blocks only when both
   // staging slots are still in flight); the results are delivered to the caller's buffers by a later SubmitHost that
   // needs the slot, or by WaitHost(ticket), which returns once every call up to `ticket` has been delivered.
@@ -150,6 +154,7 @@ class Replica {
   uint8_t* d_raw_ = nullptr;
   size_t d_raw_cap_ = 0;
   int* d_taps_ = nullptr;
+  void* d_descs_ = nullptr;  // CropDesc[max_batch] of the batched preprocess
   // staging
   void* d_in_[kSlots] = {};
   void* h_in_[2] = {nullptr, nullptr};  // pinned bounce buffers for pageable caller memory (micro-batch j: j & 1)

@@ -31,6 +31,13 @@ cudaError_t DenseTailF32(const float* flat, int N, int flat_len, const DensePara
 // Centre crop + cv2.resize-compatible (INTER_LINEAR, uint8 fixed point) bilinear resize; `taps` = 8*S int32 on the device.
 cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst, int S, const int* taps, int area2x,
                          cudaStream_t st);
+// One image of a batched crop + resize: raw HxWx3 bytes at arena + offset, row pitch W pixels, crop origin (cy, cx),
+// crop side `side`.
+struct CropDesc {
+  unsigned long long offset;
+  int W, cy, cx, side;
+};
+cudaError_t CropResizeBatchU8(const uint8_t* arena, const CropDesc* descs, int n, uint8_t* dst, int S, cudaStream_t st);
 
 // ---- 16-bit tensor-core path (kernels_tc.cu) --------------------------------
 // Activation layout between tensor-core layers ("chunked rows"):

@@ -238,6 +238,61 @@ __global__ void crop_resize_u8_kernel(const uint8_t* __restrict__ src, int W, in
   }
 }
 
+// Batched form for a list of photos of different sizes (classify_im_dir, reference infer.py:79-82): one launch crops and
+// resizes every image of the micro-batch from a device arena straight into the network's input tensor.  The tap tables
+// of crop_resize_u8_kernel are evaluated in place with OpenCV's own expressions (resize.cpp, double / float steps as
+// in engine.cu: ResizeTaps), so the result is the same bit pattern: fx = float((d + 0.5) * scale - 0.5), floor,
+// 11-bit weights by round-half-even; columns clamp the fraction at the borders, rows only clamp the indices.
+__global__ void crop_resize_batch_kernel(const uint8_t* __restrict__ arena, const CropDesc* __restrict__ descs,
+                                         uint8_t* __restrict__ dst, int S) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+  if (dx >= S) return;
+  const CropDesc d = descs[blockIdx.z];
+  const uint8_t* src = arena + d.offset;
+  uint8_t* o = dst + ((static_cast<size_t>(blockIdx.z) * S + dy) * S + dx) * 3;
+  const int W = d.W, cy = d.cy, cx = d.cx, side = d.side;
+  if (side == S) {  // already the right size: plain crop (network.py:151 skips the resize)
+    const uint8_t* p0 = src + (static_cast<size_t>(cy + dy) * W + cx + dx) * 3;
+    o[0] = p0[0], o[1] = p0[1], o[2] = p0[2];
+    return;
+  }
+  if (side == 2 * S) {  // exact 2x shrink: 2x2 box
+    const uint8_t* p0 = src + (static_cast<size_t>(cy + 2 * dy) * W + cx + 2 * dx) * 3;
+    const uint8_t* p1 = p0 + static_cast<size_t>(W) * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<uint8_t>((p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2);
+    return;
+  }
+  const double scale = static_cast<double>(side) / static_cast<double>(S);
+  float fx = static_cast<float>((dx + 0.5) * scale - 0.5);
+  int sx = static_cast<int>(floorf(fx));
+  fx -= static_cast<float>(sx);
+  if (sx < 0) {
+    fx = 0.f;
+    sx = 0;
+  }
+  if (sx >= side - 1) {
+    fx = 0.f;
+    sx = side - 1;
+  }
+  const int x0 = sx, x1 = min(sx + 1, side - 1);
+  const int a1 = static_cast<int>(rintf(fx * 2048.0f)), a0 = static_cast<int>(rintf((1.0f - fx) * 2048.0f));
+  float fy = static_cast<float>((dy + 0.5) * scale - 0.5);
+  const int sy = static_cast<int>(floorf(fy));
+  fy -= static_cast<float>(sy);
+  const int y0 = min(max(sy, 0), side - 1), y1 = min(max(sy + 1, 0), side - 1);
+  const int b1 = static_cast<int>(rintf(fy * 2048.0f)), b0 = static_cast<int>(rintf((1.0f - fy) * 2048.0f));
+  const uint8_t* r0 = src + (static_cast<size_t>(cy + y0) * W + cx) * 3;
+  const uint8_t* r1 = src + (static_cast<size_t>(cy + y1) * W + cx) * 3;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int h0 = r0[x0 * 3 + c] * a0 + r0[x1 * 3 + c] * a1;
+    const int h1 = r1[x0 * 3 + c] * a0 + r1[x1 * 3 + c] * a1;
+    const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+    o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+  }
+}
+
 template <int CC, int COG, typename TIn>
 void launch_conv(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin, int Cout,
                  int px_stride, cudaStream_t st) {
@@ -270,6 +325,12 @@ cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst
                          cudaStream_t st) {
   dim3 grid((S + 127) / 128, S);
   crop_resize_u8_kernel<<<grid, 128, 0, st>>>(src, W, cy, cx, dst, S, taps, area2x);
+  return cudaGetLastError();
+}
+
+cudaError_t CropResizeBatchU8(const uint8_t* arena, const CropDesc* descs, int n, uint8_t* dst, int S, cudaStream_t st) {
+  dim3 grid((S + 127) / 128, S, n);
+  crop_resize_batch_kernel<<<grid, 128, 0, st>>>(arena, descs, dst, S);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,7 @@ from __future__ import annotations
 import os
 import shutil
 import struct
+from collections import deque
 from concurrent.futures import ThreadPoolExecutor
 from glob import glob
 
@@ -30,7 +31,10 @@ INPUT_MODEL_PATH = './final_model/roomnet'       # reference infer.py:24
 INPUT_IMAGES_DIR = './test_images/set2/images'   # reference infer.py:25
 IMG_SIDE = 224                                   # reference infer.py:26
 BATCH = 256
+BATCH_BYTES = 512 << 20           # decoded pixels per device call (bounds host memory on large photos)
 IO_THREADS = min(32, os.cpu_count() or 1)
+DECODE_AHEAD = 2 * IO_THREADS     # files being decoded ahead of the device
+MAX_PENDING_WRITES = 64           # overlay / copy writes in flight
 
 
 class _Biff2Sheet:
@@ -107,24 +111,55 @@ def classify_im_dir(nn, imgs_dir, overlay=True):
     sheet.write(0, 0, 'IMAGE_NAME')
     sheet.write(0, 1, 'PREDICTED_LABEL')
     row = 1
-    chunks = [paths[start:start + BATCH] for start in range(0, len(paths), BATCH)]
     with ThreadPoolExecutor(max_workers=IO_THREADS) as pool:
-        writes = []
-        decoding = [pool.submit(_read_image, path) for path in chunks[0]] if chunks else []
-        for ci, chunk in enumerate(chunks):
-            images = [f.result() for f in decoding]
-            if ci + 1 < len(chunks):  # decode the next batch while this one is on the GPU
-                decoding = [pool.submit(_read_image, path) for path in chunks[ci + 1]]
-            top1, probs = nn.infer_optimized_batch(images)
-            for path, image, cls, prob in zip(chunk, images, top1, probs):
+        writes = deque()
+
+        def flush(batch):
+            """One device call for the images collected so far, then their output side on the pool."""
+            nonlocal row
+            if not batch:
+                return
+            top1, probs = nn.infer_optimized_batch([image for _, image in batch])
+            for (path, image), cls, prob in zip(batch, top1, probs):
                 label, confidence = CLASS_LABELS[cls], prob[cls]
                 name = path.split(os.sep)[-1]
                 print(path, '--->', label, confidence)
-                writes.append(pool.submit(_emit, path, image, out_dir + os.sep + label, name, label, confidence, overlay))
+                # a plain copy does not need the pixels: do not keep them alive in the write queue
+                writes.append(pool.submit(_emit, path, image if overlay else None, out_dir + os.sep + label, name,
+                                          label, confidence, overlay))
                 sheet.write(row, 0, name)
                 sheet.write(row, 1, label)
                 sheet.write(row, 2, str(confidence))
                 row += 1
+            while len(writes) > MAX_PENDING_WRITES:  # bounded: finished images are released as they are written
+                writes.popleft().result()
+
+        # decode a bounded window ahead of the device; a batch is closed at BATCH images or BATCH_BYTES of pixels,
+        # whichever comes first (a directory of multi-megapixel photos must not hold hundreds of them in memory)
+        decoding = deque()
+        nxt = 0
+        batch, batch_bytes = [], 0
+        try:
+            while nxt < len(paths) or decoding:
+                while nxt < len(paths) and len(decoding) < DECODE_AHEAD:
+                    decoding.append((paths[nxt], pool.submit(_read_image, paths[nxt])))
+                    nxt += 1
+                path, fut = decoding.popleft()
+                image = fut.result()
+                batch.append((path, image))
+                batch_bytes += image.nbytes
+                if len(batch) >= BATCH or batch_bytes >= BATCH_BYTES:
+                    flush(batch)
+                    batch, batch_bytes = [], 0
+        except AttributeError:
+            # unreadable file: like the reference (which processes file by file), everything before it is still
+            # classified and written, then the error surfaces
+            flush(batch)
+            for w in writes:
+                w.result()
+            workbook.save(xl_fpath)
+            raise
+        flush(batch)
         for w in writes:
             w.result()  # surface I/O errors before the table is saved
     workbook.save(xl_fpath)

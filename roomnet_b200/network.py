@@ -123,10 +123,10 @@ class RoomNet:
     def infer_optimized_batch(self, ims):
         """Batched form of infer_optimized used by classify_im_dir: list of BGR images of any size."""
         self._require()
-        if self.gpu_preprocess:
-            batch = np.stack([self.sess.preprocess_u8(im) for im in ims])
-        else:
-            batch = np.stack([self.preprocess(im) for im in ims])
+        if self.gpu_preprocess and all(im.dtype == np.uint8 for im in ims):
+            # crop + resize of the whole list in one launch, straight into the network input (rn_infer_images_u8_bgr)
+            return self.sess.infer_images_u8_bgr(ims)
+        batch = np.stack([self.preprocess(im) for im in ims])
         return self.sess.infer_u8_bgr(batch)
 
     def train_step(self, x_in, y):
