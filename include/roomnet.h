@@ -152,6 +152,19 @@ int rn_infer_image_u8_bgr(rn_handle* h, const uint8_t* img, int32_t H, int32_t W
 int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths,
                            int32_t n, int64_t* top1, float* probs, float* logits);
 
+/* CameraActivity.onImageAvailable -> ImageUtils.convertYUV420ToARGB8888 -> ClassifierActivity.processImage
+ *   mobile/.../env/ImageUtils.java:131-151 (+ YUV2RGB :100-129), getTransformationMatrix :168-225,
+ *   ClassifierActivity.java:89-106 (frameToCropTransform, canvas.drawBitmap), Classifier.java:226-243
+ * One YUV_420_888 camera frame (the three android.media.Image planes with their strides) -> class probabilities: the
+ * colour conversion (the reference's integer arithmetic, bit-exact), the frame-to-crop transform (rotation by a
+ * multiple of 90 degrees, uniform scale max(S/w, S/h), nearest frame pixel as an unfiltered drawBitmap samples it) and
+ * the network run in one device call; `rgb_out` (optional) receives the S*S*3 R,G,B bytes the network saw (what
+ * croppedBitmap would hold).  Same results as rn_infer_u8_rgb on those bytes. */
+int rn_infer_yuv420(rn_handle* h, const uint8_t* y, const uint8_t* u, const uint8_t* v, int32_t y_size, int32_t u_size,
+                    int32_t v_size, int32_t width, int32_t height, int32_t y_row_stride, int32_t uv_row_stride,
+                    int32_t uv_pixel_stride, int32_t rotation_degrees, int64_t* top1, float* probs, float* logits,
+                    uint8_t* rgb_out);
+
 /* Host-side geometry helper: writes the crop rectangle the reference would take (network.py:137-146). */
 int rn_center_crop_rect(int32_t h, int32_t w, int32_t* y0, int32_t* x0, int32_t* side);
 

@@ -64,6 +64,7 @@ def _load():
         "rn_preprocess_u8": ([vp, vp, i32, i32, vp], C.c_int),
         "rn_infer_image_u8_bgr": ([vp, vp, i32, i32, vp, vp, vp], C.c_int),
         "rn_infer_images_u8_bgr": ([vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), i32, vp, vp, vp], C.c_int),
+        "rn_infer_yuv420": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
         "rn_flat_len": ([vp], C.c_int),
         "rn_num_kernel_launches": ([vp], C.c_int),
@@ -87,7 +88,7 @@ lib = _load()
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
             "rn_submit_u8_bgr", "rn_wait",
-            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
 
@@ -219,6 +220,18 @@ class Handle:
         self._check(lib.rn_infer_images_u8_bgr(self._h, ptrs, hs, ws, n, top1.ctypes.data, probs.ctypes.data,
                                                logits.ctypes.data))
         return (top1, probs, logits) if want_logits else (top1, probs)
+
+    def infer_yuv420(self, y, u, v, width, height, y_row_stride, uv_row_stride, uv_pixel_stride, rotation=0):
+        """One YUV_420_888 camera frame (planes as uint8 arrays) -> (top1, probs, logits, rgb the network saw)."""
+        y, u, v = (np.ascontiguousarray(a, dtype=np.uint8).ravel() for a in (y, u, v))
+        top1 = np.empty((1,), np.int64)
+        probs = np.empty((1, self.num_classes), np.float32)
+        logits = np.empty((1, self.num_classes), np.float32)
+        rgb = np.empty((self.im_side, self.im_side, 3), np.uint8)
+        self._check(lib.rn_infer_yuv420(self._h, y.ctypes.data, u.ctypes.data, v.ctypes.data, y.size, u.size, v.size,
+                                        width, height, y_row_stride, uv_row_stride, uv_pixel_stride, rotation,
+                                        top1.ctypes.data, probs.ctypes.data, logits.ctypes.data, rgb.ctypes.data))
+        return top1, probs, logits, rgb
 
     def infer_raw(self, fn_name, in_ptr, n, top1_ptr, probs_ptr, logits_ptr):
         """Pointer-level call (pinned host buffers owned by the caller)."""

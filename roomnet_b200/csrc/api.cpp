@@ -479,6 +479,40 @@ int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32
   });
 }
 
+int rn_infer_yuv420(rn_handle* h, const uint8_t* y, const uint8_t* u, const uint8_t* v, int32_t y_size, int32_t u_size,
+                    int32_t v_size, int32_t width, int32_t height, int32_t y_row_stride, int32_t uv_row_stride,
+                    int32_t uv_pixel_stride, int32_t rotation, int64_t* top1, float* probs, float* logits,
+                    uint8_t* rgb_out) {
+  return Guarded(h, [&]() -> int {
+    if (!h) return RN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!y || !u || !v || width < 2 || height < 2 || y_row_stride < width || uv_row_stride < 1 || uv_pixel_stride < 1)
+      return Fail(h, RN_ERR_INVALID_ARG, "null plane or bad frame geometry");
+    rotation %= 360;
+    if (rotation < 0) rotation += 360;
+    if (rotation % 90 != 0) return Fail(h, RN_ERR_INVALID_ARG, "rotation must be a multiple of 90 degrees");
+    // every (row, column) the kernel can touch must lie inside the planes the caller handed over
+    const long long y_need = static_cast<long long>(y_row_stride) * (height - 1) + width;
+    const long long uv_need = static_cast<long long>(uv_row_stride) * ((height - 1) >> 1) +
+                              static_cast<long long>((width - 1) >> 1) * uv_pixel_stride + 1;
+    if (y_size < y_need || u_size < uv_need || v_size < uv_need)
+      return Fail(h, RN_ERR_INVALID_ARG, "plane buffers are smaller than the frame geometry requires");
+    if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+    if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+    auto t0 = std::chrono::steady_clock::now();
+    rn::Replica* r = h->replicas[0].get();
+    rn::YuvFrame f{width, height, y_row_stride, uv_row_stride, uv_pixel_stride, rotation};
+    if (r->InferYuv420(y, u, v, y_size, u_size, v_size, f, top1, probs, logits, rgb_out) != cudaSuccess)
+      return Fail(h, RN_ERR_CUDA, r->error());
+    h->last_launches = r->last_launches();
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (h->lat_ms.size() < (1u << 20)) h->lat_ms.push_back(ms);
+    h->calls += 1;
+    h->images += 1;
+    return RN_OK;
+  });
+}
+
 int rn_center_crop_rect(int32_t hgt, int32_t wid, int32_t* y0, int32_t* x0, int32_t* side) {
   if (hgt <= 0 || wid <= 0 || !y0 || !x0 || !side) return RN_ERR_INVALID_ARG;
   // reference network.py:139: offset = abs((w - h) // 2) with Python floor division

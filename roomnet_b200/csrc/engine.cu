@@ -717,6 +717,47 @@ cudaError_t Replica::InferImages(const uint8_t* const* imgs, const int* H, const
   return cudaSuccess;
 }
 
+cudaError_t Replica::InferYuv420(const uint8_t* y, const uint8_t* u, const uint8_t* v, size_t y_size, size_t u_size,
+                                 size_t v_size, const YuvFrame& f, int64_t* top1, float* probs, float* logits,
+                                 uint8_t* rgb_out) {
+  {
+    cudaError_t ew = WaitHost(~0ull);
+    if (ew != cudaSuccess) return ew;
+  }
+  RN_CUDA(cudaSetDevice(device_));
+  const int S = shape_.im_side, C = shape_.num_classes;
+  const size_t oy = 0, ou = (y_size + 255) & ~static_cast<size_t>(255), ov = ou + ((u_size + 255) & ~static_cast<size_t>(255));
+  const size_t total = ov + v_size;
+  if (total > d_raw_cap_) {
+    RN_CUDA(cudaStreamSynchronize(compute_));
+    if (d_raw_) cudaFree(d_raw_);
+    d_raw_ = nullptr;
+    d_raw_cap_ = 0;
+    RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_raw_), total));
+    d_raw_cap_ = total;
+  }
+  RN_CUDA(cudaMemcpyAsync(d_raw_ + oy, y, y_size, cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemcpyAsync(d_raw_ + ou, u, u_size, cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemcpyAsync(d_raw_ + ov, v, v_size, cudaMemcpyHostToDevice, compute_));
+  uint8_t* dst = static_cast<uint8_t*>(d_in_[0]);
+  RN_CUDA(Yuv420CropU8(d_raw_ + oy, d_raw_ + ou, d_raw_ + ov, f, dst, S, compute_));
+  last_launches_ = 1;
+  if (rgb_out) RN_CUDA(cudaMemcpyAsync(rgb_out, dst, static_cast<size_t>(S) * S * 3, cudaMemcpyDeviceToHost, compute_));
+  cur_ = &sets_[0];
+  cudaError_t e = ForwardDevice(dst, InputKind::kU8Rgb, 1, d_top1_[0], d_probs_[0], d_logits_[0], compute_);
+  if (e != cudaSuccess) return e;
+  long long t1 = 0;
+  std::vector<float> buf(2 * C);
+  RN_CUDA(cudaMemcpyAsync(&t1, d_top1_[0], sizeof(long long), cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaMemcpyAsync(buf.data(), d_probs_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaMemcpyAsync(buf.data() + C, d_logits_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaStreamSynchronize(compute_));
+  if (top1) *top1 = t1;
+  if (probs) std::memcpy(probs, buf.data(), C * sizeof(float));
+  if (logits) std::memcpy(logits, buf.data() + C, C * sizeof(float));
+  return cudaSuccess;
+}
+
 cudaError_t Replica::InferImage(const uint8_t* h_img, int H, int W, int64_t* top1, float* probs, float* logits) {
   cudaError_t e = Preprocess(h_img, H, W, nullptr);
   if (e != cudaSuccess) return e;

@@ -37,6 +37,10 @@ class Replica {
   cudaError_t InferHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits);
   // n BGR uint8 photos of arbitrary sizes (imgs[i] = H[i] x W[i] x 3): centre crop + cv2-identical resize of a whole
   // micro-batch in one launch, straight into the network input - no host round trip between the two.
+  // One YUV_420_888 camera frame: colour conversion + frame-to-crop transform + forward pass on the device.
+  cudaError_t InferYuv420(const uint8_t* y, const uint8_t* u, const uint8_t* v, size_t y_size, size_t u_size,
+                          size_t v_size, const YuvFrame& f, int64_t* top1, float* probs, float* logits,
+                          uint8_t* rgb_out);
   cudaError_t InferImages(const uint8_t* const* imgs, const int* H, const int* W, int n, int64_t* top1, float* probs,
                           float* logits);
   // Asynchronous form: SubmitHost enqueues the copies and kernels of one call and returns (it blocks only when both

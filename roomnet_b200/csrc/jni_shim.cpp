@@ -11,6 +11,8 @@
 //     static native long create(String checkpointPrefix, int device, int imSide, int precision);
 //     static native int run(long handle, java.nio.ByteBuffer imgData, float[][] labelProbArray);
 //     static native int runArgb(long handle, int[] intValues, float[][] labelProbArray);
+//     static native int runYuv(long handle, ByteBuffer y, ByteBuffer u, ByteBuffer v, int width, int height,
+//                              int yRowStride, int uvRowStride, int uvPixelStride, int rotation, float[][] labelProbArray);
 //     static native void close(long handle);
 //   }
 #include <cstring>
@@ -165,6 +167,58 @@ jint RN_JNI(runArgb)(JNIEnv* env, jclass, jlong handle, jintArray int_values, jo
     Slot<JniSetFloatArrayRegionFn>(env, kJniSetFloatArrayRegion)(env, row, 0, m->num_classes, probs);
   else
     Throw(env, "java/lang/IllegalStateException", std::string("RoomNet: ") + rn_last_error(m->h));
+  Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
+  return rc;
+}
+
+// The camera front end folded into the native call: the three planes of the android.media.Image the camera hands
+// to CameraActivity.onImageAvailable (direct ByteBuffers, Image.Plane.getBuffer()) with their strides and the
+// sensor-to-screen rotation of ClassifierActivity.java:80.  Replaces ImageUtils.convertYUV420ToARGB8888
+// (ImageUtils.java:131-151), rgbFrameBitmap.setPixels + canvas.drawBitmap(..., frameToCropTransform, ...)
+// (ClassifierActivity.java:101-103) and convertBitmapToByteBuffer (Classifier.java:226-243).
+jint RN_JNI(runYuv)(JNIEnv* env, jclass, jlong handle, jobject y_buf, jobject u_buf, jobject v_buf, jint width,
+                    jint height, jint y_row_stride, jint uv_row_stride, jint uv_pixel_stride, jint rotation,
+                    jobjectArray label_prob_array) {
+  JniModel* m = reinterpret_cast<JniModel*>(handle);
+  if (!m || !m->h) {
+    Throw(env, "java/lang/IllegalStateException", "RoomNet: classifier is closed");
+    return RN_ERR_INVALID_ARG;
+  }
+  jobject bufs[3] = {y_buf, u_buf, v_buf};
+  void* ptr[3] = {nullptr, nullptr, nullptr};
+  jlong cap[3] = {0, 0, 0};
+  for (int k = 0; k < 3; ++k) {
+    ptr[k] = bufs[k] ? Slot<JniGetDirectBufferAddressFn>(env, kJniGetDirectBufferAddress)(env, bufs[k]) : nullptr;
+    if (!ptr[k]) {
+      Throw(env, "java/lang/IllegalArgumentException", "RoomNet: the image planes must be direct ByteBuffers");
+      return RN_ERR_INVALID_ARG;
+    }
+    cap[k] = Slot<JniGetDirectBufferCapacityFn>(env, kJniGetDirectBufferCapacity)(env, bufs[k]);
+    if (cap[k] <= 0 || cap[k] > 0x7fffffff) {
+      Throw(env, "java/lang/IllegalArgumentException", "RoomNet: bad plane capacity");
+      return RN_ERR_INVALID_ARG;
+    }
+  }
+  if (!label_prob_array || Slot<JniGetArrayLengthFn>(env, kJniGetArrayLength)(env, label_prob_array) < 1) {
+    Throw(env, "java/lang/IllegalArgumentException", "RoomNet: labelProbArray must be float[1][numLabels]");
+    return RN_ERR_INVALID_ARG;
+  }
+  jobject row = Slot<JniGetObjectArrayElementFn>(env, kJniGetObjectArrayElement)(env, label_prob_array, 0);
+  if (!row || Slot<JniGetArrayLengthFn>(env, kJniGetArrayLength)(env, row) < m->num_classes) {
+    if (row) Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
+    Throw(env, "java/lang/IllegalArgumentException", "RoomNet: labelProbArray[0] is shorter than the label count");
+    return RN_ERR_INVALID_ARG;
+  }
+  float probs[32];
+  const int rc = rn_infer_yuv420(m->h, static_cast<const uint8_t*>(ptr[0]), static_cast<const uint8_t*>(ptr[1]),
+                                 static_cast<const uint8_t*>(ptr[2]), static_cast<int32_t>(cap[0]),
+                                 static_cast<int32_t>(cap[1]), static_cast<int32_t>(cap[2]), width, height, y_row_stride,
+                                 uv_row_stride, uv_pixel_stride, rotation, nullptr, probs, nullptr, nullptr);
+  if (rc == RN_OK)
+    Slot<JniSetFloatArrayRegionFn>(env, kJniSetFloatArrayRegion)(env, row, 0, m->num_classes, probs);
+  else
+    Throw(env, rc == RN_ERR_INVALID_ARG ? "java/lang/IllegalArgumentException" : "java/lang/IllegalStateException",
+          std::string("RoomNet: ") + rn_last_error(m->h));
   Slot<JniDeleteLocalRefFn>(env, kJniDeleteLocalRef)(env, row);
   return rc;
 }

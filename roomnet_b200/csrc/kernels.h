@@ -37,6 +37,12 @@ struct CropDesc {
   unsigned long long offset;
   int W, cy, cx, side;
 };
+// One YUV_420_888 camera frame (android.media.Image planes) and the rotation of the frame-to-crop transform.
+struct YuvFrame {
+  int width, height, y_row_stride, uv_row_stride, uv_pixel_stride, rotation;
+};
+cudaError_t Yuv420CropU8(const uint8_t* y, const uint8_t* u, const uint8_t* v, const YuvFrame& f, uint8_t* dst, int S,
+                         cudaStream_t st);
 cudaError_t CropResizeBatchU8(const uint8_t* arena, const CropDesc* descs, int n, uint8_t* dst, int S, cudaStream_t st);
 
 // ---- 16-bit tensor-core path (kernels_tc.cu) --------------------------------

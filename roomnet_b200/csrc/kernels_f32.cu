@@ -293,6 +293,66 @@ __global__ void crop_resize_batch_kernel(const uint8_t* __restrict__ arena, cons
   }
 }
 
+// Camera front end of the mobile module folded into the device call (reference ImageUtils.java:131-151
+// convertYUV420ToARGB8888 + :88-129 YUV2RGB, ClassifierActivity.java:89-106 frameToCropTransform + drawBitmap):
+// one thread per network input pixel maps its centre back through the frame-to-crop transform (rotation by a multiple
+// of 90 degrees about the frame centre, uniform scale max(S/inW, S/inH), see getTransformationMatrix :168-225),
+// takes the nearest frame pixel (an unfiltered Canvas.drawBitmap), converts it with the reference's integer YUV -> RGB
+// arithmetic and writes the R,G,B bytes of the uint8 RGB feed.  The coordinate arithmetic is fp64 with a fixed
+// operation order (oracle/yuv_front.py restates it with the same order).
+__global__ void yuv420_crop_kernel(const uint8_t* __restrict__ yp, const uint8_t* __restrict__ up,
+                                   const uint8_t* __restrict__ vp, YuvFrame f, uint8_t* __restrict__ dst, int S) {
+  const int dx = blockIdx.x * blockDim.x + threadIdx.x, dy = blockIdx.y;
+  if (dx >= S) return;
+  const bool transpose = (f.rotation + 90) % 180 == 0;
+  const int in_w = transpose ? f.height : f.width, in_h = transpose ? f.width : f.height;
+  double sx = 1.0, sy = 1.0;
+  if (in_w != S || in_h != S) {
+    const double fx = static_cast<double>(S) / in_w, fy = static_cast<double>(S) / in_h;
+    sx = sy = fx > fy ? fx : fy;  // MAINTAIN_ASPECT (ClassifierActivity.java:40)
+  }
+  // inverse of  T(S/2) * Scale * R(rotation) * T(-frame/2)   (without the translations when rotation == 0)
+  double px = dx + 0.5, py = dy + 0.5;
+  if (f.rotation != 0) {
+    px -= S / 2.0;
+    py -= S / 2.0;
+  }
+  px /= sx;
+  py /= sy;
+  double qx = px, qy = py;
+  if (f.rotation == 90) {  // forward: (x, y) -> (-y, x)
+    qx = py;
+    qy = -px;
+  } else if (f.rotation == 180) {
+    qx = -px;
+    qy = -py;
+  } else if (f.rotation == 270) {  // forward: (x, y) -> (y, -x)
+    qx = -py;
+    qy = px;
+  }
+  if (f.rotation != 0) {
+    qx += f.width / 2.0;
+    qy += f.height / 2.0;
+  }
+  const int i = min(max(static_cast<int>(floor(qx)), 0), f.width - 1);
+  const int j = min(max(static_cast<int>(floor(qy)), 0), f.height - 1);
+  int y = yp[f.y_row_stride * j + i];
+  const int uv = f.uv_row_stride * (j >> 1) + (i >> 1) * f.uv_pixel_stride;
+  int u = up[uv], v = vp[uv];
+  y = (y - 16) < 0 ? 0 : (y - 16);
+  u -= 128;
+  v -= 128;
+  const int y1192 = 1192 * y;
+  int r = y1192 + 1634 * v, g = y1192 - 833 * v - 400 * u, b = y1192 + 2066 * u;
+  r = min(max(r, 0), 262143);
+  g = min(max(g, 0), 262143);
+  b = min(max(b, 0), 262143);
+  uint8_t* o = dst + (static_cast<size_t>(dy) * S + dx) * 3;
+  o[0] = static_cast<uint8_t>(r >> 10);  // 0xff000000 | ((r << 6) & 0xff0000) | ((g >> 2) & 0xff00) | ((b >> 10) & 0xff)
+  o[1] = static_cast<uint8_t>(g >> 10);
+  o[2] = static_cast<uint8_t>(b >> 10);
+}
+
 template <int CC, int COG, typename TIn>
 void launch_conv(const TIn* in, const float* w, const float* b, float* out, int N, int H, int W, int Cin, int Cout,
                  int px_stride, cudaStream_t st) {
@@ -331,6 +391,13 @@ cudaError_t CropResizeU8(const uint8_t* src, int W, int cy, int cx, uint8_t* dst
 cudaError_t CropResizeBatchU8(const uint8_t* arena, const CropDesc* descs, int n, uint8_t* dst, int S, cudaStream_t st) {
   dim3 grid((S + 127) / 128, S, n);
   crop_resize_batch_kernel<<<grid, 128, 0, st>>>(arena, descs, dst, S);
+  return cudaGetLastError();
+}
+
+cudaError_t Yuv420CropU8(const uint8_t* y, const uint8_t* u, const uint8_t* v, const YuvFrame& f, uint8_t* dst, int S,
+                         cudaStream_t st) {
+  dim3 grid((S + 127) / 128, S);
+  yuv420_crop_kernel<<<grid, 128, 0, st>>>(y, u, v, f, dst, S);
   return cudaGetLastError();
 }
 

@@ -116,9 +116,11 @@ int main(int argc, char** argv) {
   auto create = reinterpret_cast<jlong (*)(JNIEnv*, jclass, jstring, jint, jint, jint)>(SYM("create"));
   auto run = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jobject, jobjectArray)>(SYM("run"));
   auto run_argb = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jintArray, jobjectArray)>(SYM("runArgb"));
+  auto run_yuv = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jobject, jobject, jobject, jint, jint, jint, jint, jint,
+                                           jint, jobjectArray)>(SYM("runYuv"));
   auto close_fn = reinterpret_cast<void (*)(JNIEnv*, jclass, jlong)>(SYM("close"));
   auto stats = reinterpret_cast<jint (*)(JNIEnv*, jclass, jlong, jfloatArray)>(SYM("stats"));
-  CHECK(create && run && run_argb && close_fn && stats, "JNI symbols");
+  CHECK(create && run && run_argb && run_yuv && close_fn && stats, "JNI symbols");
 
   const std::string mode = argv[3];
   FakeObject prefix{FakeObject::kString};
@@ -195,6 +197,32 @@ int main(int argc, char** argv) {
   for (int i = 0; i < 6; ++i) maxdiff_a = std::max(maxdiff_a, std::abs(pa[i] - pb[i]));
   std::printf("probs_argb %.6f %.6f %.6f %.6f %.6f %.6f\n", pa[0], pa[1], pa[2], pa[3], pa[4], pa[5]);
   CHECK(maxdiff_a < 1e-3f, "int[] (Bitmap.getPixels) and uint8 ByteBuffer feeds agree");
+  {
+    // a 640x480 NV21-style camera frame (pixel stride 2: U and V are two views of one interleaved buffer), rotation 90
+    const int W = 640, H = 480;
+    std::vector<unsigned char> yplane(static_cast<size_t>(W) * H), uv(static_cast<size_t>(W) * (H / 2) + 1);
+    for (size_t i = 0; i < yplane.size(); ++i) yplane[i] = static_cast<unsigned char>((i * 2246822519u) >> 24);
+    for (size_t i = 0; i < uv.size(); ++i) uv[i] = static_cast<unsigned char>((i * 3266489917u) >> 24);
+    FakeObject yb{FakeObject::kDirectBuffer}, ub{FakeObject::kDirectBuffer}, vb{FakeObject::kDirectBuffer};
+    yb.buf = yplane.data();
+    yb.cap = static_cast<long long>(yplane.size());
+    vb.buf = uv.data();
+    vb.cap = static_cast<long long>(uv.size() - 1);
+    ub.buf = uv.data() + 1;
+    ub.cap = static_cast<long long>(uv.size() - 1);
+    rc = run_yuv(&env, nullptr, h, reinterpret_cast<jobject>(&yb), reinterpret_cast<jobject>(&ub),
+                 reinterpret_cast<jobject>(&vb), W, H, W, W, 2, 90, reinterpret_cast<jobjectArray>(&out));
+    CHECK(rc == 0, "yuv run");
+    std::vector<float> py = row.floats;
+    float sy = 0;
+    for (int i = 0; i < 6; ++i) sy += py[i];
+    std::printf("probs_yuv %.6f %.6f %.6f %.6f %.6f %.6f\n", py[0], py[1], py[2], py[3], py[4], py[5]);
+    CHECK(std::abs(sy - 1.f) < 1e-4f, "yuv probabilities sum to 1");
+    g_thrown_class.clear();
+    rc = run_yuv(&env, nullptr, h, reinterpret_cast<jobject>(&yb), reinterpret_cast<jobject>(&ub),
+                 reinterpret_cast<jobject>(&vb), W, H, W, W, 2, 45, reinterpret_cast<jobjectArray>(&out));
+    CHECK(rc != 0 && g_thrown_class == "java/lang/IllegalArgumentException", "rotation check");
+  }
   FakeObject short_ints{FakeObject::kIntArray};
   short_ints.ints.assign(10, 0);
   g_thrown_class.clear();

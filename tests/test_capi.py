@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_jni_library_exports_entry_points():
     lib = ctypes.CDLL(os.path.join(ROOT, "roomnet_b200", "libroomnet_jni.so"))
-    for fn in ("create", "run", "close", "stats"):
+    for fn in ("create", "run", "runArgb", "runYuv", "close", "stats"):
         assert hasattr(lib, "Java_org_tensorflow_lite_examples_classification_tflite_RoomNetNative_" + fn)
 
 

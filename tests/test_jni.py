@@ -40,3 +40,10 @@ def test_jni_run_matches_python_path(harness, ckpt_prefix, capi):
     h.load_tf_checkpoint(ckpt_prefix)
     _, p = h.infer_f32_rgb(((img.astype(np.float32) - 127.5) / 127.5))
     assert np.abs(np.array(probs) - p[0]).max() < 1e-5
+    # the camera frame of the harness (640x480, NV21 layout, rotation 90) through the ctypes path
+    W, H = 640, 480
+    yplane = (((np.arange(W * H, dtype=np.uint64) * 2246822519) & 0xFFFFFFFF) >> 24).astype(np.uint8)
+    uv = (((np.arange(W * (H // 2) + 1, dtype=np.uint64) * 3266489917) & 0xFFFFFFFF) >> 24).astype(np.uint8)
+    py = [list(map(float, l.split()[1:])) for l in out.stdout.splitlines() if l.startswith("probs_yuv")][0]
+    _, p2, _, _ = h.infer_yuv420(yplane, uv[1:], uv[:-1], W, H, W, W, 2, 90)
+    assert np.abs(np.array(py) - p2[0]).max() < 1e-5
