@@ -8,6 +8,15 @@
 
 namespace rn {
 
+// NVTX ranges around the host-side phases (visible in Nsight Systems; a few nanoseconds when no tool is attached)
+#include <nvtx3/nvToolsExt.h>
+namespace {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
+
 #define RN_CUDA(expr)                                                                                   \
   do {                                                                                                  \
     cudaError_t _e = (expr);                                                                            \
@@ -137,6 +146,7 @@ cudaError_t Replica::UploadF32(const std::vector<double>& v, float** dptr) {
 }
 
 cudaError_t Replica::Upload(const FoldedNet& f) {
+  NvtxRange nvtx_range("rn::Upload (pack + upload folded weights)");
   RN_CUDA(cudaSetDevice(device_));
   RN_CUDA(cudaDeviceSynchronize());
   const FoldedConv* c0[3] = {&f.conv0_u8bgr, &f.conv0_u8rgb, &f.conv0_f32rgb};
@@ -414,6 +424,7 @@ cudaError_t Replica::ForwardDevice(const void* d_in, InputKind kind, int n, long
 
 cudaError_t Replica::InferDevice(const void* d_in, InputKind kind, int n, long long* d_top1, float* d_probs,
                                  float* d_logits, cudaStream_t st) {
+  NvtxRange nvtx_range("rn::InferDevice");
   RN_CUDA(cudaSetDevice(device_));
   if (!st) st = compute_;
   last_launches_ = 0;
@@ -475,6 +486,7 @@ void Replica::AbortPending() {
 }
 
 cudaError_t Replica::WaitHost(uint64_t ticket) {
+  NvtxRange nvtx_range("rn::WaitHost (deliver results)");
   RN_CUDA(cudaSetDevice(device_));
   for (int s = 0; s < kSlots; ++s) {  // oldest slot first
     const int slot = (slot_seq_ + s) % kSlots;
@@ -499,6 +511,7 @@ cudaError_t Replica::InferHost(const void* h_in, InputKind kind, int n, int64_t*
 
 cudaError_t Replica::SubmitHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits,
                                 uint64_t ticket) {
+  NvtxRange nvtx_range("rn::SubmitHost (copies + kernels of one call)");
   RN_CUDA(cudaSetDevice(device_));
   last_launches_ = 0;
   const size_t per = InputBytesPerImage(shape_, kind);
@@ -653,6 +666,7 @@ cudaError_t Replica::Preprocess(const uint8_t* h_img, int H, int W, uint8_t* h_o
 
 cudaError_t Replica::InferImages(const uint8_t* const* imgs, const int* H, const int* W, int n, int64_t* top1,
                                  float* probs, float* logits) {
+  NvtxRange nvtx_range("rn::InferImages (batched crop + resize + forward)");
   {
     cudaError_t ew = WaitHost(~0ull);  // uses staging slot 0 and activation set 0 on the replica's own stream
     if (ew != cudaSuccess) return ew;

@@ -43,3 +43,17 @@ def test_product_arm_line_has_roofline_and_launch_count():
     assert roof["bound"] in ("tensor", "hbm") and 0 < roof["frac"] < 1 and roof["unit"] == "TFLOP/s"
     assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-9
     assert set(line["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_reference_arm_does_not_map_the_product_library():
+    """the reference arm must not load libroomnet.so (it times the CPU restatement only)."""
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1']\n"
+        "try:\n"
+        "    runpy.run_path(%r, run_name='__main__')\n"
+        "except SystemExit:\n"
+        "    pass\n"
+        "print('MAPPED', 'libroomnet' in open('/proc/self/maps').read())\n" % os.path.join(ROOT, "bench.py"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=600)
+    assert "MAPPED False" in out.stdout, out.stdout[-300:] + out.stderr[-300:]
