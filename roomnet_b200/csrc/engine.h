@@ -97,7 +97,7 @@ class Replica {
   // the two activation sets (micro-batch j: slot j % kSlots, set j & 1).  With more slots than sets the host->device
   // copies run up to kSlots - 1 micro-batches ahead of the kernels, so a stream of calls is bound by
   // max(PCIe time, kernel time) instead of their partial sum.
-  static constexpr int kSlots = 4;
+  static constexpr int kSlots = 8;
   cudaEvent_t ev_h2d_[kSlots] = {}, ev_done_[kSlots] = {};
   struct PendingOut {  // a micro-batch in flight in staging slot s: where its results go once ev_done_[s] has fired
     int m = 0;

@@ -432,6 +432,9 @@ __global__ void __launch_bounds__(kB2Threads, 1) block2_fused_kernel(const B2Par
         }
         GG += it.n2e;
       }
+      // consume the last "group done" phases as well: nothing of this CTA is then left un-waited at exit
+      for (uint32_t g = GG > 4 ? GG - 4 : 0; g < GG; ++g)
+        mbar_wait_sleep(bar_res_done + 8u * (g & (kB2ResGroups - 1)), (g >> 2) & 1);
     }
   } else if (warp == 1) {
     // ========================= MMA issuer, layer 1 (R2 -> conv2d_2) =========================

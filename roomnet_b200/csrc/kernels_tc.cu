@@ -751,24 +751,51 @@ __device__ __forceinline__ void tail_conv_pool(const float* __restrict__ in, int
   // [9][16][16] weights, already in shared memory (`w` unused: kept for the signature of the callers' tables)
   (void)w;
   const int CS = S - 2, P = (CS - 4) / 2 + 1;
-  for (int item = threadIdx.x; item < CS * CS * 4; item += blockDim.x) {
-    const int g = item / (CS * CS), px = item % (CS * CS);
-    const int y = px / CS, x = px % CS;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int c = 0; c < 16; ++c) {
-      const float* ip = in + (c * S + y) * S + x;
+  // One item = two horizontally adjacent pixels x eight output channels: the four input values of a kernel row serve
+  // both pixels, the weights of a tap come in as two 128-bit loads, and the 16 accumulators advance as packed fp32 pairs
+  // (fma.f32x2).  Per accumulator the products are added in the same order as before (channel, then dy, dx).
+  const int XP = (CS + 1) / 2;
+  for (int item = threadIdx.x; item < CS * XP * 2; item += blockDim.x) {
+    const int g = item / (CS * XP), r = item % (CS * XP);
+    const int y = r / XP, x = (r % XP) * 2;
+    const bool two = x + 1 < CS;
+    f32x2_t acc[2][4];
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const float a = ip[(tap / 3) * S + (tap % 3)];
-        const float4 wv = *reinterpret_cast<const float4*>(&s_w[(tap * 16 + c) * 16 + g * 4]);
-        acc[0] = fmaf(a, wv.x, acc[0]);
-        acc[1] = fmaf(a, wv.y, acc[1]);
-        acc[2] = fmaf(a, wv.z, acc[2]);
-        acc[3] = fmaf(a, wv.w, acc[3]);
+    for (int k = 0; k < 4; ++k) acc[0][k] = acc[1][k] = 0ull;
+    const int x1 = min(x + 1, S - 1), x2 = min(x + 2, S - 1), x3 = min(x + 3, S - 1);
+    for (int c = 0; c < 16; ++c) {
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const float* ip = in + (c * S + y + dy) * S;
+        const float a0 = ip[x], a1 = ip[x1], a2 = ip[x2], a3 = ip[x3];
+        const f32x2_t av[4] = {f2_pack(a0, a0), f2_pack(a1, a1), f2_pack(a2, a2), f2_pack(a3, a3)};
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float* wp = &s_w[((dy * 3 + dx) * 16 + c) * 16 + g * 8];
+          const ulonglong2 w01 = *reinterpret_cast<const ulonglong2*>(wp);
+          const ulonglong2 w23 = *reinterpret_cast<const ulonglong2*>(wp + 4);
+          acc[0][0] = f2_fma(av[dx], w01.x, acc[0][0]);
+          acc[0][1] = f2_fma(av[dx], w01.y, acc[0][1]);
+          acc[0][2] = f2_fma(av[dx], w23.x, acc[0][2]);
+          acc[0][3] = f2_fma(av[dx], w23.y, acc[0][3]);
+          acc[1][0] = f2_fma(av[dx + 1], w01.x, acc[1][0]);
+          acc[1][1] = f2_fma(av[dx + 1], w01.y, acc[1][1]);
+          acc[1][2] = f2_fma(av[dx + 1], w23.x, acc[1][2]);
+          acc[1][3] = f2_fma(av[dx + 1], w23.y, acc[1][3]);
+        }
       }
     }
 #pragma unroll
-    for (int o = 0; o < 4; ++o) conv[((g * 4 + o) * CS + y) * CS + x] = relu6f(acc[o] + bias[g * 4 + o]);
+    for (int px = 0; px < 2; ++px) {
+      if (px == 1 && !two) break;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float lo, hi;
+        f2_unpack(acc[px][k], lo, hi);
+        conv[((g * 8 + 2 * k) * CS + y) * CS + x + px] = relu6f(lo + bias[g * 8 + 2 * k]);
+        conv[((g * 8 + 2 * k + 1) * CS + y) * CS + x + px] = relu6f(hi + bias[g * 8 + 2 * k + 1]);
+      }
+    }
   }
   __syncthreads();
   for (int item = threadIdx.x; item < 16 * P * P; item += blockDim.x) {

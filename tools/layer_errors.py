@@ -1,5 +1,5 @@
 """Per-layer activation error of the 16-bit path against the folded fp64 oracle (test infrastructure import, tools only).
-Usage: python tools/layer_errors.py [n_images]   (env RN_NO_FUSED_JOIN=1 for the stand-alone join kernels)"""
+Usage: python tools/layer_errors.py [n_images] [fp16|bf16|fp32]"""
 import os
 import sys
 
@@ -13,11 +13,12 @@ from roomnet_b200 import _capi  # noqa: E402
 from roomnet_b200.workload import default_checkpoint_prefix, synthetic_suite  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+precision = sys.argv[2] if len(sys.argv) > 2 else "fp16"
 imgs = synthetic_suite(64)[:n]
 weights = tf_bundle.load_checkpoint(default_checkpoint_prefix())
 ref = folded_forward(fold(weights), imgs, dtype=np.float64, conv_backend="torch", collect=True)
 for lw in (True, False):
-    h = _capi.Handle(precision="fp16", layerwise=lw, max_batch=max(n, 1))
+    h = _capi.Handle(precision=precision, layerwise=lw, max_batch=max(n, 1))
     h.load_tf_checkpoint(default_checkpoint_prefix())
     t, p, l = h.infer_u8_bgr(imgs, want_logits=True)
     errs = []
