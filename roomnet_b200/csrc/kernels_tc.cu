@@ -988,6 +988,33 @@ __global__ void prep_u8_kernel(const uint8_t* __restrict__ in, uint4* __restrict
   }
 }
 
+// Fast form for packed 3-byte pixels, fp16 and a 4-byte aligned image pointer with S * 3 % 4 == 0: one thread per output
+// chunk as above (coalesced 16-byte stores), but the six bytes come from three aligned 32-bit loads + funnel shifts and
+// are converted with byte permutes and packed fp16 math instead of six byte loads and float conversions.
+// 0x6400 | b is the fp16 number 1024 + b, so (0x6400 | b) * 2^-8 - 4 = b / 256 exactly.
+__global__ void prep_u8w_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, size_t total_px, int S) {
+  pdl_trigger();
+  const uint32_t kBias = 0x64006400u;  // bytes {0x00, 0x64, 0x00, 0x64}: selector 4 = 0x00, 5 = 0x64
+  const __half2 scale = __floats2half2_rn(1.f / 256.f, 1.f / 256.f), minus4 = __floats2half2_rn(-4.f, -4.f);
+  auto cvt = [&](uint32_t q, uint32_t sel) {
+    const uint32_t v = __byte_perm(q, kBias, sel);
+    const __half2 r = __hfma2(*reinterpret_cast<const __half2*>(&v), scale, minus4);
+    return *reinterpret_cast<const uint32_t*>(&r);
+  };
+  const size_t last_word = (total_px * 3 + 3) / 4 - 1;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total_px;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t o = 3 * i, k = o >> 2;
+    const uint32_t sh = static_cast<uint32_t>(o & 3) * 8;
+    const uint32_t w0 = in[k], w1 = in[min(k + 1, last_word)], w2 = in[min(k + 2, last_word)];
+    const uint32_t a = __funnelshift_r(w0, w1, sh);  // bytes o .. o+3
+    const uint32_t b = __funnelshift_r(w1, w2, sh);  // bytes o+4 .. o+7
+    uint32_t q1 = __byte_perm(a, b, 0x0543);         // pixel x+1 = bytes o+3 .. o+5
+    if (static_cast<int>(i % S) + 1 >= S) q1 = 0u;   // the row ends here: no right neighbour
+    out[i] = make_uint4(cvt(a, 0x5150), cvt(a, 0x5452), cvt(q1, 0x5150), cvt(q1, 0x5452));
+  }
+}
+
 template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
 cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
   using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
@@ -1183,6 +1210,11 @@ size_t PackTcConv0Weights(const double* w, HalfKind kind, double scale, void* ou
 
 cudaError_t PrepU8(const uint8_t* in, void* out, int N, int S, HalfKind kind, cudaStream_t st, int px_bytes) {
   size_t total = static_cast<size_t>(N) * S * S;
+  if (px_bytes == 3 && kind == HalfKind::kF16 && (total * 3) % 4 == 0 && reinterpret_cast<uintptr_t>(in) % 4 == 0) {
+    int blocksw = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
+    prep_u8w_kernel<<<blocksw, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(in), static_cast<uint4*>(out), total, S);
+    return cudaGetLastError();
+  }
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   prep_u8_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint4*>(out), N, S, kind == HalfKind::kBF16, px_bytes);
   return cudaGetLastError();
