@@ -228,11 +228,11 @@ def default_checkpoint_prefix() -> str:
     """Location of the shipped ``final_model`` weights.
 
     ``/root/reference`` exists only in the build container; the GPU box uses the
-    byte-identical fixture copy under tests/golden/final_model (the weights are
+    byte-identical copy under final_model/ at the repository root (the weights are
     data, not source; sha256 pinned in tests/test_bundle.py).
     """
     here = os.path.dirname(os.path.abspath(__file__))
-    fixture = os.path.join(here, "..", "tests", "golden", "final_model", "roomnet")
+    fixture = os.path.join(here, "..", "final_model", "roomnet")
     if os.path.exists(fixture + ".index"):
         return os.path.normpath(fixture)
     return "/root/reference/final_model/roomnet"

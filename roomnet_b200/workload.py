@@ -88,10 +88,11 @@ def synthetic_dense0(im_side: int) -> np.ndarray:
 
 
 def default_checkpoint_prefix() -> str:
-    """The shipped ``final_model`` weights: the byte-identical fixture copy under tests/golden (the GPU box has no
-    /root/reference), else the reference tree of the build container."""
+    """The shipped ``final_model`` weights: the byte-identical copy under final_model/ at the repository root (the
+    reference's own layout, infer.py:24; the GPU box has no /root/reference), else the reference tree of the build
+    container."""
     here = os.path.dirname(os.path.abspath(__file__))
-    fixture = os.path.join(here, "..", "tests", "golden", "final_model", "roomnet")
+    fixture = os.path.join(here, "..", "final_model", "roomnet")
     if os.path.exists(fixture + ".index"):
         return os.path.normpath(fixture)
     return "/root/reference/final_model/roomnet"

@@ -165,7 +165,8 @@ def test_other_resolutions(capi, ckpt_prefix, weights, precision, side):
     """README's alternate resolutions with a synthesised dense/kernel (BASELINE config 4)."""
     from oracle.roomnet_oracle import RoomNetOracle, synthetic_dense0, synthetic_suite
     d0 = synthetic_dense0(side)
-    imgs = synthetic_suite(4 if side <= 300 else 2, side)
+    # all four image families incl. the flat-colour ones (the worst case of the 16-bit path), both micro-batch paths
+    imgs = synthetic_suite(12 if side <= 300 else 6, side)
     orc = RoomNetOracle(im_side=side, dtype=np.float32, weights=weights, dense0_kernel=d0, conv_backend="torch")
     ref = orc.forward(orc.normalise(imgs))
     h = capi.Handle(im_side=side, precision=precision)
@@ -176,6 +177,14 @@ def test_other_resolutions(capi, ckpt_prefix, weights, precision, side):
     print("side %d %s: max|dlogit| %.3e" % (side, precision, err))
     assert np.array_equal(top1, ref["argmax"])
     assert err <= TOL[precision]
+    if precision == "fp16":
+        # BASELINE config 4 at its full batch of 512 through a size-independent property: a batch that tiles these
+        # images must reproduce their logits bit for bit at every position (several micro-batches, both streams)
+        reps = 512 // len(imgs) + 1
+        big = np.concatenate([imgs] * reps)[:512]
+        t512, _, l512 = h.infer_u8_bgr(big, want_logits=True)
+        assert np.array_equal(l512, np.concatenate([logits] * reps)[:512])
+        assert np.array_equal(t512, np.concatenate([top1] * reps)[:512])
 
 
 @pytest.mark.parametrize("precision", ["fp16"])
