@@ -109,13 +109,6 @@ __device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// volatile twin: ptxas must not merge it with an identical f2_add (used to recompute a sum INTO a state register
-// instead of copying it there)
-__device__ __forceinline__ f32x2_t f2_add_again(f32x2_t a, f32x2_t b) {
-  f32x2_t r;
-  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
 __device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
   f32x2_t r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
@@ -186,15 +179,6 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float unpack_lo(uint32_t v, int bf16) {
-  if (bf16) return __bfloat162float(reinterpret_cast<__nv_bfloat162*>(&v)->x);
-  return __half2float(reinterpret_cast<__half2*>(&v)->x);
-}
-__device__ __forceinline__ float unpack_hi(uint32_t v, int bf16) {
-  if (bf16) return __bfloat162float(reinterpret_cast<__nv_bfloat162*>(&v)->y);
-  return __half2float(reinterpret_cast<__half2*>(&v)->y);
-}
-
 // POOL modes: 0 = none, 31 = 3x3/1, 41 = 4x4/1, 42 = 4x4/2.  The kernel stores the window SUM of
 // saturate(conv/6): the factors k*k and 6 are folded into the consumer's weights by the host.
 // AMODE: 0 = channel-chunk planes (Cin >= 16), 1 = Cin 8: pixel pairs form a K=16 step (LBO = 16 B),
@@ -323,15 +307,6 @@ struct H2 {
       asm("{.reg .b16 xl, xh; mov.b32 {xl, xh}, %1; add.rn.f32.f16 %0, xh, %2;}" : "=f"(r) : "r"(x), "f"(acc));
     }
     return r;
-  }
-  __device__ static __forceinline__ uint32_t sixteenth(uint32_t a) {  // exact: power-of-two scale
-    if constexpr (BF16) {
-      __nv_bfloat162 r = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&a), __floats2bfloat162_rn(0.0625f, 0.0625f));
-      return *reinterpret_cast<uint32_t*>(&r);
-    } else {
-      __half2 r = __hmul2(*reinterpret_cast<__half2*>(&a), __floats2half2_rn(0.0625f, 0.0625f));
-      return *reinterpret_cast<uint32_t*>(&r);
-    }
   }
 };
 
