@@ -38,7 +38,11 @@ Replica::Replica(int device, const NetShape& shape, int precision, int max_batch
     : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
   layerwise_ = (flags & RN_FLAG_LAYERWISE) != 0;
   half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
-  first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
+  // RN_PREC_FP32_TC: conv0..conv6 as three-product split-fp16 tensor-core layers (hi + lo activations, [Wh | Wl]
+  // weights, fp32 epilogues); conv7 (K = 1152: both operand halves of a row pair do not fit in shared memory) and the
+  // small tail run on the fp32 CUDA-core kernels
+  split_ = precision == RN_PREC_FP32_TC;
+  first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : (split_ ? 7 : 8);
 }
 
 Replica::~Replica() {
@@ -102,17 +106,21 @@ cudaError_t Replica::Init() {
     const ConvShape& cs = shape_.conv[i];
     scratch = std::max(scratch, static_cast<size_t>(cs.conv_side) * cs.conv_side * cs.cout);
   }
+  if (split_)  // float feed: conv0 runs on the fp32 kernels and is split into hi + lo planes afterwards
+    scratch = std::max(scratch, static_cast<size_t>(shape_.conv[0].conv_side) * shape_.conv[0].conv_side * shape_.conv[0].cout);
   RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->conv_scratch), scratch * B * sizeof(float)));
   for (int i = 0; i < kNumConvs; ++i) {
     const ConvShape& cs = shape_.conv[i];
     size_t elems = static_cast<size_t>(cs.out_side) * cs.out_side * cs.cout * B;
-    bool f32_needed = i >= first_f32_layer_ || i == first_f32_layer_ - 1;
+    bool f32_needed = i >= first_f32_layer_ || i == first_f32_layer_ - 1 || (split_ && i == 0);
     if (f32_needed) {
       RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->pooled[i]), elems * sizeof(float)));
       if (cs.join_src >= 0) RN_CUDA(Alloc(reinterpret_cast<void**>(&cur_->joined[i]), elems * sizeof(float)));
     }
     if (i < first_f32_layer_) {
-      size_t bytes = ChunkedBytes(max_batch_, cs.out_side, cs.cout);
+      // split tensors carry hi and lo planes; conv0's eight channels travel padded to sixteen there (conv2d_1 then has
+      // the even number of channel chunks per half that the K = 16 MMA steps need)
+      size_t bytes = ChunkedBytes(max_batch_, cs.out_side, split_ ? 2 * std::max(cs.cout, 16) : cs.cout);
       RN_CUDA(Alloc(&cur_->act_h[i], bytes));
       RN_CUDA(cudaMemset(cur_->act_h[i], 0, bytes));
       if (cs.join_src >= 0) {
@@ -190,6 +198,7 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
       L.out_side = c0.out_side;
       L.cout_parts = 1;
       L.amode = 2;
+      L.split = split_;
       std::vector<double> b6(16, 0.0);
       for (int k = 0; k < 8; ++k) b6[k] = f.conv0_u8bgr.b[k] / 6.0;  // identical for BGR and RGB byte order
       RN_CUDA(UploadF32(b6, &tc_bias_[0]));
@@ -211,24 +220,40 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
       // the kernel computes saturate(conv(stored_in, W') + b') == relu6(z)/6 and stores the pool-window SUM
       act_scale_[i] = (cs.pool_k ? cs.pool_k * cs.pool_k : 1) / 6.0;
       TcConvLayer& L = tc_[i];
-      L.cin = cs.cin;
+      const int cin_l = split_ ? std::max(cs.cin, 16) : cs.cin;  // logical input channels (conv2d_1: 8 real + 8 zero)
+      L.split = split_;
+      L.cin = split_ ? 2 * cin_l : cs.cin;
       L.cout = cs.cout;
       L.in_side = cs.in_side;
       L.pool_k = cs.pool_k;
       L.pool_s = cs.pool_s;
       L.out_side = cs.out_side;
-      L.cout_parts = cs.cout > 64 ? cs.cout / 64 : 1;
+      // split layers keep [Wh | Wl] and hi + lo stages in shared memory: 64-channel inputs leave room for 32 outputs
+      L.cout_parts = split_ ? (cin_l >= 64 ? cs.cout / 32 : 1) : (cs.cout > 64 ? cs.cout / 64 : 1);
       std::vector<double> b6(f.conv[i].b.size());
       for (size_t k = 0; k < b6.size(); ++k) b6[k] = f.conv[i].b[k] / 6.0;
       RN_CUDA(UploadF32(b6, &tc_bias_[i]));
       L.bias = tc_bias_[i];
-      size_t part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0, nullptr);
-      std::vector<uint8_t> host(part_bytes * L.cout_parts);
+      size_t part_bytes = 0;
+      std::vector<uint8_t> host;
+      if (split_) {
+        std::vector<double> wpad(static_cast<size_t>(9) * cin_l * cs.cout, 0.0);
+        for (int t = 0; t < 9; ++t)
+          for (int c = 0; c < cs.cin; ++c)
+            for (int o = 0; o < cs.cout; ++o)
+              wpad[(static_cast<size_t>(t) * cin_l + c) * cs.cout + o] = f.conv[i].w[(static_cast<size_t>(t) * cs.cin + c) * cs.cout + o];
+        part_bytes = PackTcWeightsSplit(nullptr, cin_l, cs.cout, L.cout_parts, 1.0, nullptr);
+        host.resize(part_bytes * L.cout_parts);
+        PackTcWeightsSplit(wpad.data(), cin_l, cs.cout, L.cout_parts, 1.0 / (6.0 * g_in), host.data());
+      } else {
+      part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0, nullptr);
+      host.resize(part_bytes * L.cout_parts);
       std::vector<double> in_scale;  // the producer's per-channel join gain (below) is undone in this layer's weights
       if (in_is_join && !join_gain_[i - 1].empty())
         for (double g : join_gain_[i - 1]) in_scale.push_back(1.0 / g);
       PackTcWeights(f.conv[i].w.data(), cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0 / (6.0 * g_in), host.data(),
                     in_scale.empty() ? nullptr : in_scale.data());
+      }
       void* d = const_cast<void*>(L.w_packed);
       if (!d) RN_CUDA(Alloc(&d, host.size()));
       RN_CUDA(cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
@@ -240,7 +265,7 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
         for (auto& v : b) v /= act_scale_[cs.join_src];
         std::vector<double> cc(f.join[i].c);
         join_gain_[i].clear();
-        if (i + 1 < first_f32_layer_) {
+        if (i + 1 < first_f32_layer_ && !split_) {  // (split layers join in fp32: no gain needed)
           // The tensor-core kernels (kernels_block2.cu, the JOIN epilogue of kernels_tc.cu) multiply the resized
           // residual by B with a mixed-precision fma whose multiplier is a 16-bit value.  Rounding B would be a coherent per-channel error of 2^-12 (measured: 1e-2 on
           // the logits of flat images), so the whole output channel is stored with a gain g = round16(B) / B instead:
@@ -346,7 +371,17 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   const bool argb = kind == InputKind::kArgb8888;
   const int k = static_cast<int>(argb ? InputKind::kU8Bgr : kind);
   Mark(nullptr, st);
-  if (kind == InputKind::kF32Rgb) {
+  if (kind == InputKind::kF32Rgb && split_) {
+    // raw float feed on the fp32-class path: conv0 + pool on the fp32 kernels, then the split into hi + lo planes
+    RN_CUDA(Conv3x3Relu6F32<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], cur_->conv_scratch, n, c0.in_side,
+                                   c0.in_side, 3, c0.cout, st));
+    Mark("conv0_f32", st);
+    RN_CUDA(AvgPoolF32(cur_->conv_scratch, cur_->pooled[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
+    Mark("pool0_f32", st);
+    RN_CUDA(F32ToSplitChunked(cur_->pooled[0], cur_->act_h[0], n, c0.out_side, c0.cout, 16,
+                              static_cast<float>(act_scale_[0]), st));
+    Mark("f32_to_split", st);
+  } else if (kind == InputKind::kF32Rgb) {
     // raw float feed: operands need more than 11 bits, keep conv0 in fp32 on the CUDA cores
     RN_CUDA(Conv0PoolH<float>(static_cast<const float*>(d_in), w0_[k], b0_[k], cur_->act_h[0], n, c0.in_side, half_kind_, st));
     Mark("conv0_pool_h", st);
@@ -361,7 +396,7 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
   for (int i = 1; i < first_f32_layer_; ++i) {
     const ConvShape& cs = shape_.conv[i];
     const void* in = shape_.conv[i - 1].join_src >= 0 ? cur_->join_h[i - 1] : cur_->act_h[i - 1];
-    if (i == 2 && !layerwise_ && shape_.conv[3].join_src == 1 && Block2FusedSupported(tc_[2], tc_[3])) {
+    if (i == 2 && !layerwise_ && !split_ && shape_.conv[3].join_src == 1 && Block2FusedSupported(tc_[2], tc_[3])) {
       // residual block 2 in one kernel: conv2d_2's output stays in shared memory (kernels_block2.cu)
       RN_CUDA(Block2Fused(tc_[2], tc_[3], cur_->act_h[1], cur_->join_h[3], n, half_kind_, st));
       Mark("block2_tc", st);
@@ -389,7 +424,7 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
     return cudaSuccess;
   }
   RN_CUDA(ChunkedToF32(cur_->act_h[last], cur_->pooled[last], n, cl.out_side, cl.cout, half_kind_,
-                       static_cast<float>(1.0 / act_scale_[last]), st));
+                       static_cast<float>(1.0 / act_scale_[last]), st, split_));
   Mark("chunked_to_f32", st);
   cudaError_t e = TailF32(first_f32_layer_, n, st);
   if (e != cudaSuccess) return e;
@@ -814,14 +849,26 @@ cudaError_t Replica::DebugActivation(int layer, std::vector<float>* out, int dim
   if (layer >= first_f32_layer_) {
     src = cs.join_src >= 0 ? cur_->joined[layer] : cur_->pooled[layer];
   } else {
-    RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), elems * sizeof(float)));
+    // split tensors: conv0's eight channels are stored padded to sixteen (see Init)
+    const int stored_ch = split_ ? std::max(cs.cout, 16) : cs.cout;
+    const size_t stored_elems = elems / cs.cout * stored_ch;
+    RN_CUDA(cudaMalloc(reinterpret_cast<void**>(&tmp), stored_elems * sizeof(float)));
     const void* h = cs.join_src >= 0 ? cur_->join_h[layer] : cur_->act_h[layer];
     const float sc = cs.join_src >= 0 ? 1.f : static_cast<float>(1.0 / act_scale_[layer]);
-    cudaError_t e = ChunkedToF32(h, tmp, cur_->last_n, cs.out_side, cs.cout, half_kind_, sc, compute_);
+    cudaError_t e = ChunkedToF32(h, tmp, cur_->last_n, cs.out_side, stored_ch, half_kind_, sc, compute_, split_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(compute_);
     if (e != cudaSuccess) {
       cudaFree(tmp);
       RN_CUDA(e);
+    }
+    if (stored_ch != cs.cout) {
+      std::vector<float> wide(stored_elems);
+      e = cudaMemcpy(wide.data(), tmp, stored_elems * sizeof(float), cudaMemcpyDeviceToHost);
+      cudaFree(tmp);
+      RN_CUDA(e);
+      for (size_t px = 0; px < elems / cs.cout; ++px)
+        for (int c = 0; c < cs.cout; ++c) (*out)[px * cs.cout + c] = wide[px * stored_ch + c];
+      return cudaSuccess;
     }
     src = tmp;
   }

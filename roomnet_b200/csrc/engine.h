@@ -151,6 +151,7 @@ class Replica {
   ActSet* cur_ = &sets_[0];
   cudaEvent_t ev_fork_ = nullptr;
   int first_f32_layer_ = 0;  // layers >= this run on the fp32 kernels
+  bool split_ = false;       // RN_PREC_FP32_TC: three-product split-fp16 tensor-core layers, fp32 epilogues
   bool layerwise_ = false;   // RN_FLAG_LAYERWISE: no fused residual-block kernel
   bool block2_fused_last_ = false;  // the last forward pass ran residual block 2 as one kernel
 

@@ -118,9 +118,14 @@ __device__ __forceinline__ void join_hlerp(const uint8_t* row, uint32_t dx_bytes
 #define RN_TC_DBG_BIT(p, bit) false
 #endif
 
-template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
+// SPLIT: the fp32-class path (RN_PREC_FP32_TC).  Activations travel as hi + lo 16-bit pairs (planes [hi | lo], CB counts
+// the physical planes), every input row takes the three products xh*Wh + xl*Wh + xh*Wl into the same fp32 accumulators
+// (TcCfg), and the epilogue keeps everything in fp32 - pooling windows, residual join - until it splits the result into
+// hi = round16(v), lo = round16(v - hi) for the store.
+template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false, bool SPLIT = false>
 __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
-  using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
+  using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0, SPLIT && AMODE == 0>;
+  static_assert(!SPLIT || (CREAL % 8 == 0 && (CREAL / tc_groups(CREAL)) % 8 == 0), "split stores write whole 16-byte chunks");
   static_assert(POOL == 0 || SEG == 1 || POOL == 42, "two-image windowed tiles exist for 4x4/2 pooling only");
   using HH = H2<BF16>;
   constexpr int R = Cfg::kSlots;
@@ -182,13 +187,14 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
   for (int i = threadIdx.x; i < COUT; i += kThreadsTc) s_bias[i] = bias_g[i];
   if (JOIN) {
     for (int i = threadIdx.x; i < 3 * COUT; i += kThreadsTc) {
-      if (i / COUT == 1) continue;
+      if (!SPLIT && i / COUT == 1) continue;  // (split layers keep B in fp32)
       s_abc[i] = p.join_abc[(i / COUT) * (COUT * gridDim.y) + part * COUT + (i % COUT)];
     }
-    for (int i = threadIdx.x; i < COUT / 2; i += kThreadsTc) {
-      const float* bsrc = p.join_abc + COUT * gridDim.y + part * COUT + 2 * i;
-      s_bh[i] = HH::pack(bsrc[0], bsrc[1]);  // exact: engine.cu made B a 16-bit value
-    }
+    if (!SPLIT)
+      for (int i = threadIdx.x; i < COUT / 2; i += kThreadsTc) {
+        const float* bsrc = p.join_abc + COUT * gridDim.y + part * COUT + 2 * i;
+        s_bh[i] = HH::pack(bsrc[0], bsrc[1]);  // exact: engine.cu made B a 16-bit value
+      }
   }
   if (POOL != 0) {
     // The 128-byte pad behind the last plane of every stage is never written by the TMA box but is read (with
@@ -380,7 +386,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
     const int pix = quad * 32 + lane;             // pixel (UMMA row) owned by this thread
     const int seg = pix / SEGW, xs = pix % SEGW;
     const uint32_t t_base = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + grp * CG;
-    const size_t out_row_bytes = static_cast<size_t>(p.cb_out_total) * p.out_side * 16;
+    const int out_planes = (SPLIT ? 2 : 1) * p.cb_out_total;  // split tensors: hi planes, then lo planes
+    const size_t out_row_bytes = static_cast<size_t>(out_planes) * p.out_side * 16;
     const size_t out_img_bytes = out_row_bytes * p.out_side;
     const size_t out_plane_bytes = static_cast<size_t>(p.out_side) * 16;
     constexpr int KW = POOL == 31 ? 3 : 4;        // pooling window
@@ -390,10 +397,10 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
 #pragma unroll
     for (int c = 0; c < CG; ++c) bias_r[c] = s_bias[grp * CG + c];
     // fused join: per-channel coefficients of this thread's channels and the residual tensor's strides
-    constexpr bool kJoinPreload = JOIN && CG == 8 && POOL == 41;
+    constexpr bool kJoinPreload = JOIN && CG == 8 && POOL == 41 && !SPLIT;
     constexpr bool kJoinAFirst = true;  // A on the fp32 window sums (false: after the 16-bit rounding; same accuracy, more work)
     const uint32_t jplane_bytes = static_cast<uint32_t>(p.res_side) * 16;
-    const uint32_t jrow_bytes = static_cast<uint32_t>(p.cb_out_total) * jplane_bytes;
+    const uint32_t jrow_bytes = static_cast<uint32_t>(out_planes) * jplane_bytes;
     // every accumulator slot starts out holding the bias: the MMAs then always accumulate
     for (int s = 0; s < R; ++s) tc_st<CG>(t_base + s * COUT, bias_r);
     tc_wait_st();
@@ -430,12 +437,14 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       uint32_t jdx = 0, jtx2 = 0, jbot[JOIN ? NP : 1];
       int jy_prev = -1;
       uint4 jpl[2], jpr[2];  // kJoinPreload: left/right taps of the lower source row of the next two output rows
+      float jtxf = 0.f;
       if (JOIN) {
         const float fx = static_cast<float>(col) * p.res_scale;
         const int jx0 = static_cast<int>(fx);
         jdx = jx0 + 1 < p.res_side ? 16u : 0u;
         jtx2 = HH::splat(fx - static_cast<float>(jx0));
-        jsrc = p.res_src + static_cast<size_t>(n_img) * p.res_side * p.cb_out_total * p.res_side * 16 +
+        jtxf = fx - static_cast<float>(jx0);
+        jsrc = p.res_src + static_cast<size_t>(n_img) * p.res_side * out_planes * p.res_side * 16 +
                (static_cast<size_t>(part) * (CREAL / 8) + grp * (CG / 8)) * p.res_side * 16 + jx0 * 16;
       }
       // issue the gathers for output rows first_row, first_row + 1 (relative to the item); they are consumed one
@@ -508,6 +517,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
         // ---- saturate (= ReLU6/6) + vertical window -> packed 16-bit pairs vp[k][i] for output slot k
         // output slot 0 is pooled row (y - LAG) [41/31] or (y - 2)/2 [42] or conv row y [0]; slot 1 the next one
         uint32_t vp[2][NP];
+        float vf[2][SPLIT ? CG : 1];  // split layers: the window sums stay fp32
 #pragma unroll
         for (int i = 0; i < NP; ++i) {
           // weights and bias carry a factor 1/6: relu6(z)/6 == saturate(z/6), one FADD.SAT
@@ -534,25 +544,55 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
             q1[i] = f2_add(x1, x0);
             r1[i] = x1;
           }
-          if constexpr (JOIN && kJoinAFirst) {  // join coefficient A on the fp32 window sums (exact; the 16-bit sums then run on A*x)
+          if constexpr (JOIN && kJoinAFirst && !SPLIT) {  // join coefficient A on the fp32 window sums (exact; the 16-bit sums then run on A*x)
+            const f32x2_t a2 = *reinterpret_cast<const f32x2_t*>(s_abc + grp * CG + 2 * i);
+            o0 = f2_mul(o0, a2);
+            if (POOL != 42) o1 = f2_mul(o1, a2);
+          }
+          if constexpr (JOIN && SPLIT) {  // (kJoinAFirst applies to the 16-bit path only)
             const f32x2_t a2 = *reinterpret_cast<const f32x2_t*>(s_abc + grp * CG + 2 * i);
             o0 = f2_mul(o0, a2);
             if (POOL != 42) o1 = f2_mul(o1, a2);
           }
           float lo, hi;
           f2_unpack(o0, lo, hi);
-          vp[0][i] = HH::pack(lo, hi);
+          if constexpr (SPLIT) {
+            vf[0][2 * i] = lo;
+            vf[0][2 * i + 1] = hi;
+          } else {
+            vp[0][i] = HH::pack(lo, hi);
+          }
           if (POOL != 42) {
             f2_unpack(o1, lo, hi);
-            vp[1][i] = HH::pack(lo, hi);
+            if constexpr (SPLIT) {
+              vf[1][2 * i] = lo;
+              vf[1][2 * i + 1] = hi;
+            } else {
+              vp[1][i] = HH::pack(lo, hi);
+            }
           }
         }
 
         // ---- horizontal window with warp shuffles (every window owns its halo, see kWindows)
         uint32_t hp[2][NP];
         constexpr int NK = (POOL == 42) ? 1 : 2;
+        if constexpr (SPLIT) {
 #pragma unroll
-        for (int k = 0; k < NK; ++k)
+          for (int k = 0; k < NK; ++k)
+#pragma unroll
+            for (int c = 0; c < CG; ++c) {
+              const float v = vf[k][c];
+              if (POOL == 42) {
+                const float u = v + __shfl_xor_sync(0xffffffffu, v, 1);
+                vf[k][c] = u + __shfl_down_sync(0xffffffffu, u, 2);
+              } else if (POOL != 0) {
+                const float t = v + __shfl_down_sync(0xffffffffu, v, 1);
+                vf[k][c] = t + __shfl_down_sync(0xffffffffu, POOL == 41 ? t : v, 2);
+              }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < (SPLIT ? 0 : NK); ++k)
 #pragma unroll
           for (int i = 0; i < NP; ++i) {
             const uint32_t v = vp[k][i];
@@ -578,6 +618,63 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
               const int row = first + k;
               if (row >= 0 && row < it.npo) {
                 uint8_t* orow = optr + static_cast<size_t>(k) * out_row_bytes;
+                if constexpr (SPLIT) {
+                  // fp32-class path: residual join in fp32 from the hi + lo planes of the source tensor (reference
+                  // network.py:199-203, TF-1.13 legacy bilinear: top = tl + (tr - tl) * tx, ...), then the hi / lo split
+                  float ty = 0.f;
+                  const uint8_t* r0 = nullptr;
+                  const uint8_t* r1p = nullptr;
+                  if constexpr (JOIN) {
+                    const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
+                    const int y0 = static_cast<int>(fy);
+                    const int y1 = min(y0 + 1, p.res_side - 1);
+                    ty = fy - static_cast<float>(y0);
+                    r0 = jsrc + static_cast<uint32_t>(y0) * jrow_bytes;
+                    r1p = jsrc + static_cast<uint32_t>(y1) * jrow_bytes;
+                  }
+                  const size_t lo_off = static_cast<size_t>(p.cb_out_total) * out_plane_bytes;  // hi plane -> lo plane
+                  const uint32_t jlo_off = static_cast<uint32_t>(p.cb_out_total) * jplane_bytes;
+#pragma unroll
+                  for (int cb = 0; cb < CG / 8; ++cb) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = vf[k][8 * cb + e];
+                    if constexpr (JOIN) {
+                      auto tap = [&](const uint8_t* rowp, uint32_t dxb, float* out8) {
+                        const uint4 h = *reinterpret_cast<const uint4*>(rowp + cb * jplane_bytes + dxb);
+                        const uint4 l = *reinterpret_cast<const uint4*>(rowp + cb * jplane_bytes + jlo_off + dxb);
+                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                          const float2 a = HH::unpack(hw[q]), b = HH::unpack(lw[q]);
+                          out8[2 * q] = a.x + b.x;
+                          out8[2 * q + 1] = a.y + b.y;
+                        }
+                      };
+                      float tl[8], tr[8], bl[8], br[8];
+                      tap(r0, 0, tl);
+                      tap(r0, jdx, tr);
+                      tap(r1p, 0, bl);
+                      tap(r1p, jdx, br);
+#pragma unroll
+                      for (int e = 0; e < 8; ++e) {
+                        const float top = tl[e] + (tr[e] - tl[e]) * jtxf, bot = bl[e] + (br[e] - bl[e]) * jtxf;
+                        const float rs = top + (bot - top) * ty;
+                        const int ch = grp * CG + 8 * cb + e;
+                        v[e] = v[e] + fmaf(s_abc[COUT + ch], rs, s_abc[2 * COUT + ch]);  // A was applied to the window sums
+                      }
+                    }
+                    uint32_t hi4[4], lo4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      hi4[q] = HH::pack(v[2 * q], v[2 * q + 1]);
+                      const float2 back = HH::unpack(hi4[q]);
+                      lo4[q] = HH::pack(v[2 * q] - back.x, v[2 * q + 1] - back.y);
+                    }
+                    *reinterpret_cast<uint4*>(orow + cb * out_plane_bytes) = make_uint4(hi4[0], hi4[1], hi4[2], hi4[3]);
+                    *reinterpret_cast<uint4*>(orow + cb * out_plane_bytes + lo_off) = make_uint4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                  }
+                } else {
                 if constexpr (JOIN) {
                   // reference network.py:199-203 in folded form; bilinear taps in
                   // packed 16-bit arithmetic (top = tl + (tr-tl)*tx, ...: the TF formula), the per-channel affine in
@@ -635,6 +732,7 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
                   *reinterpret_cast<uint4*>(orow + cb * out_plane_bytes) =
                       make_uint4(hp[k][4 * cb], hp[k][4 * cb + 1], hp[k][4 * cb + 2], hp[k][4 * cb + 3]);
                 if (CG == 4) *reinterpret_cast<uint2*>(orow) = make_uint2(hp[k][0], hp[k][1]);
+                }
               }
             }
           }
@@ -937,10 +1035,11 @@ __global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __rest
   if (lane == 0 && top1) top1[n] = bi;
 }
 
+// `split`: the tensor carries hi planes followed by lo planes (fp32-class path); the value is hi + lo
 __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, int N, int S, int C,
-                                      int bf16, float scale) {
+                                      int bf16, float scale, int split) {
   const size_t total = static_cast<size_t>(N) * S * S * C;
-  const int CBn = C / 8;
+  const int CBl = C / 8, CBn = split ? 2 * CBl : CBl;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     int c = static_cast<int>(i % C);
@@ -949,13 +1048,18 @@ __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __
     r /= S;
     int y = static_cast<int>(r % S);
     int n = static_cast<int>(r / S);
-    uint16_t raw = in[((((static_cast<size_t>(n) * S + y) * CBn + c / 8) * S) + x) * 8 + (c % 8)];
+    const size_t at = ((((static_cast<size_t>(n) * S + y) * CBn + c / 8) * S) + x) * 8 + (c % 8);
+    uint16_t raw = in[at];
     float f;
     if (bf16) {
       f = __uint_as_float(static_cast<uint32_t>(raw) << 16);
     } else {
       __half h = *reinterpret_cast<__half*>(&raw);
       f = __half2float(h);
+    }
+    if (split) {
+      uint16_t raw_lo = in[at + static_cast<size_t>(CBl) * S * 8];
+      f += __half2float(*reinterpret_cast<__half*>(&raw_lo));
     }
     out[i] = f * scale;
   }
@@ -1015,9 +1119,9 @@ __global__ void prep_u8w_kernel(const uint32_t* __restrict__ in, uint4* __restri
   }
 }
 
-template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false>
+template <int CB, int COUT, int POOL, int SEG, int AMODE, bool BF16, int CREAL = COUT, bool JOIN = false, bool SPLIT = false>
 cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
-  using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0>;
+  using Cfg = TcCfg<CB, COUT, AMODE, POOL != 0, SPLIT && AMODE == 0>;
   TcParams p{};
   p.in = static_cast<const uint8_t*>(in);
   p.out = static_cast<uint8_t*>(out);
@@ -1050,7 +1154,7 @@ cudaError_t launch_tc_impl(const TcConvLayer& L, const void* in, void* out, int 
   int gangs = 1;
   rn_plan_rows(p.total_rows, p.out_side, p.n_strips, std::max(p.n_strips, SmCount() / L.cout_parts), &gangs, &p.min_piece);
   const int gx = gangs * p.n_strips;
-  auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL, JOIN>;
+  auto kern = conv_tc_kernel<CB, COUT, POOL, SEG, AMODE, BF16, CREAL, JOIN, SPLIT>;
   if (JOIN) {
     if (!L.join_src || !L.join_abc) return cudaErrorInvalidValue;
     p.res_src = static_cast<const uint8_t*>(L.join_src);
@@ -1108,6 +1212,11 @@ template <int CB, int COUT, int POOL, int SEG, int AMODE, int CREAL = COUT, bool
 cudaError_t launch_tc(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
   return kind == HalfKind::kBF16 ? launch_tc_impl<CB, COUT, POOL, SEG, AMODE, true, CREAL, JOIN>(L, in, out, N, st)
                                  : launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL, JOIN>(L, in, out, N, st);
+}
+// split (fp32-class) layers exist with fp16 halves only
+template <int CB, int COUT, int POOL, int SEG, int AMODE, int CREAL = COUT, bool JOIN = false>
+cudaError_t launch_tc_split(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
+  return launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL, JOIN, true>(L, in, out, N, st);
 }
 
 uint16_t to_half_bits(double v, HalfKind kind) {
@@ -1172,6 +1281,28 @@ size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKin
   return part_bytes;
 }
 
+size_t PackTcWeightsSplit(const double* w, int cin, int cout, int cout_parts, double scale, void* out_host) {
+  // per part: [Wh image | Wl image], each laid out as PackTcWeights does; wh = round16(scale * w), wl = round16(rest)
+  const size_t pb = PackTcWeights(nullptr, cin, cout, cout_parts, HalfKind::kF16, 1.0, nullptr);
+  if (!out_host) return 2 * pb;
+  const size_t n = static_cast<size_t>(9) * cin * cout;
+  std::vector<double> wh(n), wl(n);
+  for (size_t i = 0; i < n; ++i) {
+    const double v = scale * w[i];
+    wh[i] = RoundToHalfKind(v, HalfKind::kF16);
+    wl[i] = RoundToHalfKind(v - wh[i], HalfKind::kF16);
+  }
+  std::vector<uint8_t> hi(pb * cout_parts), lo(pb * cout_parts);
+  PackTcWeights(wh.data(), cin, cout, cout_parts, HalfKind::kF16, 1.0, hi.data());
+  PackTcWeights(wl.data(), cin, cout, cout_parts, HalfKind::kF16, 1.0, lo.data());
+  uint8_t* o = static_cast<uint8_t*>(out_host);
+  for (int part = 0; part < cout_parts; ++part) {
+    std::memcpy(o + 2 * pb * part, hi.data() + pb * part, pb);
+    std::memcpy(o + 2 * pb * part + pb, lo.data() + pb * part, pb);
+  }
+  return 2 * pb;
+}
+
 size_t PackTcConv0Weights(const double* w, HalfKind kind, double scale, void* out_host) {
   // planes: 0/1 = hi halves for pixel pairs (x,x+1)/(x+2,x+3), 2/3 = lo halves; rows [dy=2|dy=1|dy=0] x 16 (8 real)
   constexpr int kCout = 16, kReal = 8;
@@ -1225,6 +1356,19 @@ cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfK
   // two images per tile: 2 x 64 lanes (no pooling) or 2 x 2 windows of 14 pooled columns (4x4/2 pooling)
   const bool seg2 = L.pool_k ? (L.out_side <= 28 && L.in_side <= 64) : L.in_side <= 64;
   const int pool = L.pool_k * 10 + L.pool_s;
+  if (L.split) {  // fp32-class path: L.cin counts the physical (hi + lo) channels
+    if (kind != HalfKind::kF16) return cudaErrorInvalidValue;
+    if (L.amode == 2) return launch_tc_split<1, 16, 31, 1, 2, 16>(L, in, out, N, st);
+    if (cb == 4 && cp == 32 && pool == 41 && !L.join_src) return launch_tc_split<4, 32, 41, 1, 0>(L, in, out, N, st);
+    if (cb == 8 && cp == 32 && pool == 41)
+      return L.join_src ? launch_tc_split<8, 32, 41, 1, 0, 32, true>(L, in, out, N, st)
+                        : launch_tc_split<8, 32, 41, 1, 0>(L, in, out, N, st);
+    if (cb == 8 && cp == 64 && pool == 42 && !L.join_src) return launch_tc_split<8, 64, 42, 1, 0>(L, in, out, N, st);
+    if (cb == 16 && cp == 32 && pool == 42 && L.join_src) return launch_tc_split<16, 32, 42, 1, 0, 32, true>(L, in, out, N, st);
+    if (cb == 16 && cp == 32 && pool == 0 && !L.join_src)
+      return seg2 ? launch_tc_split<16, 32, 0, 2, 0>(L, in, out, N, st) : launch_tc_split<16, 32, 0, 1, 0>(L, in, out, N, st);
+    return cudaErrorInvalidValue;
+  }
   if (L.amode == 2) return launch_tc<1, 16, 31, 1, 2, 8>(L, in, out, N, kind, st);
   if (cb == 1 && cp == 32 && pool == 41) return launch_tc<1, 32, 41, 1, 1>(L, in, out, N, kind, st);
   if (cb == 4 && cp == 32 && pool == 41)
@@ -1278,12 +1422,41 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
   return cudaGetLastError();
 }
 
+// fp32 NHWC [N, S, S, C] * scale -> split chunked tensor with Cpad logical channels (hi planes, then lo planes, fp16)
+__global__ void f32_to_split_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, int S, int C, int Cpad,
+                                    float scale) {
+  const size_t total = static_cast<size_t>(N) * S * S * Cpad;
+  const int CBl = Cpad / 8;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % Cpad);
+    size_t r = i / Cpad;
+    const int x = static_cast<int>(r % S);
+    r /= S;
+    const int y = static_cast<int>(r % S);
+    const int n = static_cast<int>(r / S);
+    const float v = c < C ? in[((static_cast<size_t>(n) * S + y) * S + x) * C + c] * scale : 0.f;
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const size_t at = ((((static_cast<size_t>(n) * S + y) * (2 * CBl) + c / 8) * S) + x) * 8 + (c % 8);
+    out[at] = *reinterpret_cast<const uint16_t*>(&h);
+    out[at + static_cast<size_t>(CBl) * S * 8] = *reinterpret_cast<const uint16_t*>(&l);
+  }
+}
+
+cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, int Cpad, float scale, cudaStream_t st) {
+  size_t total = static_cast<size_t>(N) * S * S * Cpad;
+  int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
+  f32_to_split_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint16_t*>(out), N, S, C, Cpad, scale);
+  return cudaGetLastError();
+}
+
 cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale,
-                         cudaStream_t st) {
+                         cudaStream_t st, bool split) {
   size_t total = static_cast<size_t>(N) * S * S * Ch;
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   chunked_to_f32_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(in), out, N, S, Ch,
-                                                kind == HalfKind::kBF16, scale);
+                                                kind == HalfKind::kBF16, scale, split ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -184,13 +184,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
 // AMODE: 0 = channel-chunk planes (Cin >= 16), 1 = Cin 8: pixel pairs form a K=16 step (LBO = 16 B),
 //        2 = conv0: a 16-byte chunk holds pixels (x, x+1) x (c0,c1,c2,0); chunks x and x+2 (LBO = 32 B) form one
 //            K=16 step that covers all three dx taps; the two k-steps are the hi and lo halves of the weights
-template <int CB, int COUT, int AMODE, bool WINDOWS>
+// SPLIT (AMODE 0 only): the fp32-class path.  Activations are stored as hi + lo 16-bit pairs, planes
+// [hi chunks 0..CB/2-1 | lo chunks 0..CB/2-1] (CB = PHYSICAL planes = 2 x logical chunks), weights as [Wh planes | Wl
+// planes], and one input row takes three products into the same accumulators: xh*Wh, xl*Wh, xh*Wl (xl*Wl is below the
+// fp32 noise floor).  Only the K-step enumeration differs from the plain layer: 4.5 x the logical chunk count steps.
+template <int CB, int COUT, int AMODE, bool WINDOWS, bool SPLIT = false>
 struct TcCfg {
+  static_assert(!SPLIT || (AMODE == 0 && CB % 4 == 0), "split layers: hi and lo halves, each an even number of chunks");
   // windowed tiles are written by one tiled TMA box [CB][4 windows][32 px][8] -> dense 128-pixel planes
   static constexpr int kPlanePxT = WINDOWS ? 128 : kPlanePx;
   static constexpr int kPlaneBytesT = kPlanePxT * 16;
   static constexpr int kPlanes = AMODE == 0 ? 3 * CB : 4;       // weight planes
-  static constexpr int kKSteps = AMODE == 0 ? 3 * (CB / 2) : 2; // MMAs per input row
+  static constexpr int kCBL = SPLIT ? CB / 2 : CB;               // logical channel chunks
+  static constexpr int kKSteps = AMODE == 0 ? (SPLIT ? 9 * (kCBL / 2) : 3 * (CB / 2)) : 2;  // MMAs per input row
   static constexpr int kSlots = (512 / COUT) > 16 ? 16 : (512 / COUT);
   static constexpr int kLogSlots = kSlots == 16 ? 4 : 3;
   static_assert(kSlots == 16 || kSlots == 8, "ring size must be a power of two");
@@ -204,14 +210,21 @@ struct TcCfg {
   static constexpr int kSmemBytes = kFixedBytes + kStages * kStageBytes;
   static_assert(kStages >= 2, "not enough shared memory for a double-buffered input ring");
   // descriptor offsets (in 16-byte units) of k-step ks relative to the stage / weight base
+  // split layers: step ks = product (ks / (3 * kCBL / 2)): 0 = xh*Wh, 1 = xl*Wh, 2 = xh*Wl; inside a product the order is
+  // (dx, chunk pair) as in the plain layer
+  static constexpr int kPairs = kCBL / 2 > 0 ? kCBL / 2 : 1;  // chunk pairs per tap
   __host__ __device__ static constexpr uint32_t a_off16(int ks) {
-    return AMODE == 0 ? static_cast<uint32_t>((2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * kPlanePxT + ks / (CB / 2 > 0 ? CB / 2 : 1))
-           : AMODE == 1 ? static_cast<uint32_t>(2 * ks)
-                        : 0u;
+    if (AMODE == 1) return static_cast<uint32_t>(2 * ks);
+    if (AMODE != 0) return 0u;
+    const int prod = ks / (3 * kPairs), r = ks % (3 * kPairs);
+    const int plane = 2 * (r % kPairs) + ((SPLIT && prod == 1) ? kCBL : 0);
+    return static_cast<uint32_t>(plane * kPlanePxT + r / kPairs);
   }
   __host__ __device__ static constexpr uint32_t b_off16(int ks) {
-    return AMODE == 0 ? static_cast<uint32_t>(((ks / (CB / 2 > 0 ? CB / 2 : 1)) * CB + 2 * (ks % (CB / 2 > 0 ? CB / 2 : 1))) * 3 * COUT)
-                      : static_cast<uint32_t>(2 * ks * 3 * COUT);
+    if (AMODE != 0) return static_cast<uint32_t>(2 * ks * 3 * COUT);
+    const int prod = ks / (3 * kPairs), r = ks % (3 * kPairs);
+    const int plane = (r / kPairs) * kCBL + 2 * (r % kPairs) + ((SPLIT && prod == 2) ? 3 * kCBL : 0);
+    return static_cast<uint32_t>(plane * 3 * COUT);
   }
   static constexpr uint32_t kALbo16 = AMODE == 0 ? kPlanePxT : (AMODE == 1 ? 1 : 2);  // K-direction core-matrix stride / 16
   static constexpr uint32_t kBLbo16 = 3 * COUT;

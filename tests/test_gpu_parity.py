@@ -11,7 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT_DIR = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
-TOL = {"fp32": 1e-3, "fp16": 2e-2}
+TOL = {"fp32": 1e-3, "fp32tc": 1e-3, "fp16": 2e-2}
 
 
 @pytest.fixture(scope="module")
@@ -26,7 +26,7 @@ def _handle(capi, ckpt_prefix, precision, **kw):
     return h
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc", "fp16"])
 def test_suite64_matches_golden(capi, ckpt_prefix, suite64, golden, precision):
     h = _handle(capi, ckpt_prefix, precision)
     top1, probs, logits = h.infer_u8_bgr(suite64, want_logits=True)
@@ -38,7 +38,7 @@ def test_suite64_matches_golden(capi, ckpt_prefix, suite64, golden, precision):
     np.testing.assert_allclose(probs.sum(axis=1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc", "fp16"])
 def test_per_layer_activations(capi, ckpt_prefix, suite64, weights, precision):
     """Every conv block output (pooled, after the residual join) against the folded fp64 oracle."""
     from oracle.fold import fold, folded_forward
@@ -54,7 +54,7 @@ def test_per_layer_activations(capi, ckpt_prefix, suite64, weights, precision):
         scale = np.abs(want).max() + 1e-6
         rel = np.abs(got - want).max() / scale
         print("layer %d %s max rel err %.3e (absmax %.3f)" % (layer, got.shape, rel, scale))
-        assert rel <= (2e-5 if precision == "fp32" else 6e-3), "layer %d" % layer
+        assert rel <= {"fp32": 2e-5, "fp32tc": 1e-4, "fp16": 6e-3}[precision], "layer %d" % layer
 
 
 def test_fused_block2_matches_layerwise_kernels(capi, ckpt_prefix, suite64, weights):
@@ -95,7 +95,7 @@ def test_fused_block2_matches_layerwise_kernels(capi, ckpt_prefix, suite64, weig
         assert np.array_equal(fused[n][1], fused[37][1][:n])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc", "fp16"])
 def test_feed_variants_agree(capi, ckpt_prefix, suite64, oracle32, precision):
     """u8 BGR (RoomNet.infer), u8 RGB (quantised Java path) and float RGB (raw sess.run feed)."""
     h = _handle(capi, ckpt_prefix, precision)
@@ -106,7 +106,7 @@ def test_feed_variants_agree(capi, ckpt_prefix, suite64, oracle32, precision):
     t2, p2, l2 = h.infer_f32_rgb(x, want_logits=True)
     assert np.array_equal(t0, t1) and np.array_equal(t0, t2)
     # same arithmetic with the input-channel axis permuted: only the fp32 summation order differs
-    assert np.abs(l0 - l1).max() <= (1e-4 if precision == "fp32" else 2e-3)
+    assert np.abs(l0 - l1).max() <= {"fp32": 1e-4, "fp32tc": 5e-4, "fp16": 2e-3}[precision]
     assert np.abs(l0 - l2).max() <= TOL[precision]
     ref = oracle32.forward(x)
     assert np.abs(l2 - ref["logits"]).max() <= TOL[precision]
@@ -119,7 +119,7 @@ def test_feed_variants_agree(capi, ckpt_prefix, suite64, oracle32, precision):
     assert np.array_equal(t3, t0) and np.array_equal(l3, l0) and np.array_equal(p3, p0)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp32tc", "fp16"])
 def test_batch_position_independence(capi, ckpt_prefix, suite64, precision):
     """Bit-identical results whatever the batch size / micro-batch split (SURVEY §8e determinism)."""
     h_big = _handle(capi, ckpt_prefix, precision, max_batch=64)
@@ -160,7 +160,7 @@ def test_error_behaviour(capi, ckpt_prefix):
     assert e.value.code == capi.RN_ERR_CUDA
 
 
-@pytest.mark.parametrize("side,precision", [(300, "fp32"), (300, "fp16"), (600, "fp16")])
+@pytest.mark.parametrize("side,precision", [(300, "fp32"), (300, "fp32tc"), (300, "fp16"), (600, "fp16")])
 def test_other_resolutions(capi, ckpt_prefix, weights, precision, side):
     """README's alternate resolutions with a synthesised dense/kernel (BASELINE config 4)."""
     from oracle.roomnet_oracle import RoomNetOracle, synthetic_dense0, synthetic_suite
