@@ -44,8 +44,7 @@ enum rn_precision {
   RN_PREC_FP16 = 1,  /* 16-bit tensor-core path: fp16 operands, fp32 accumulate (tcgen05 kind::f16); budget 2e-2 */
   RN_PREC_BF16 = 2,  /* same kernels with bf16 operands; measured to MISS the 2e-2 budget on flat images */
   RN_PREC_FP32_TC = 3 /* fp32-class path on the tensor cores: activations and weights as hi + lo fp16 pairs, three
-                         products per MAC (xh*wh + xl*wh + xh*wl) into fp32 accumulators, fp32 epilogues; budget 1e-3.
-                         conv2d_7 and the small tail run on the fp32 CUDA-core kernels */
+                         products per MAC (xh*wh + xl*wh + xh*wl) into fp32 accumulators, fp32 epilogues; budget 1e-3 */
 };
 
 enum rn_flags {

@@ -38,11 +38,10 @@ Replica::Replica(int device, const NetShape& shape, int precision, int max_batch
     : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
   layerwise_ = (flags & RN_FLAG_LAYERWISE) != 0;
   half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
-  // RN_PREC_FP32_TC: conv0..conv6 as three-product split-fp16 tensor-core layers (hi + lo activations, [Wh | Wl]
-  // weights, fp32 epilogues); conv7 (K = 1152: both operand halves of a row pair do not fit in shared memory) and the
-  // small tail run on the fp32 CUDA-core kernels
+  // RN_PREC_FP32_TC: conv0..conv7 as three-product split-fp16 tensor-core layers (hi + lo activations, [Wh | Wl]
+  // weights, fp32 epilogues); the small tail (conv8, conv9, dense head) is fp32 as on the 16-bit path
   split_ = precision == RN_PREC_FP32_TC;
-  first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : (split_ ? 7 : 8);
+  first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
 }
 
 Replica::~Replica() {
@@ -229,7 +228,7 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
       L.pool_s = cs.pool_s;
       L.out_side = cs.out_side;
       // split layers keep [Wh | Wl] and hi + lo stages in shared memory: 64-channel inputs leave room for 32 outputs
-      L.cout_parts = split_ ? (cin_l >= 64 ? cs.cout / 32 : 1) : (cs.cout > 64 ? cs.cout / 64 : 1);
+      L.cout_parts = split_ ? (cin_l >= 64 ? std::max(1, cs.cout / 32) : 1) : (cs.cout > 64 ? cs.cout / 64 : 1);
       std::vector<double> b6(f.conv[i].b.size());
       for (size_t k = 0; k < b6.size(); ++k) b6[k] = f.conv[i].b[k] / 6.0;
       RN_CUDA(UploadF32(b6, &tc_bias_[i]));
@@ -419,7 +418,7 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
       shape_.conv[9].pool_k == 4 && shape_.conv[9].pool_s == 2 && shape_.conv[9].join_src == 7) {
     RN_CUDA(TailFused(cur_->act_h[7], n, cl.out_side, static_cast<float>(1.0 / act_scale_[7]), cw_[8], cb_[8], cw_[9], cb_[9],
                       ja_[9], jb_[9], jc_[9], dense_, shape_.flat_len, half_kind_, d_top1, d_probs, d_logits, cur_->pooled[8],
-                      cur_->joined[9], st));
+                      cur_->joined[9], st, split_));
     Mark("tail_fused", st);
     return cudaSuccess;
   }

@@ -107,7 +107,7 @@ bool TailFusedSupported(int s7, int channels);
 cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float* w8, const float* b8, const float* w9,
                       const float* b9, const float* ja, const float* jb, const float* jc, const DenseParams& dp,
                       int flat_len, HalfKind kind, long long* top1, float* probs, float* logits, float* dbg8,
-                      float* dbg9, cudaStream_t st);
+                      float* dbg9, cudaStream_t st, bool split = false);
 // chunked 16-bit -> NHWC fp32
 cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, int Cpad, float scale, cudaStream_t st);
 cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale, cudaStream_t st,

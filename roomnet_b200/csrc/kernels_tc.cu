@@ -437,7 +437,8 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
       uint32_t jdx = 0, jtx2 = 0, jbot[JOIN ? NP : 1];
       int jy_prev = -1;
       uint4 jpl[2], jpr[2];  // kJoinPreload: left/right taps of the lower source row of the next two output rows
-      float jtxf = 0.f;
+      float jtxf = 0.f, jbot_f[(JOIN && SPLIT) ? 8 : 1];  // split joins: fp32 horizontal weight, cached lower source row
+      int jy_split = -2;
       if (JOIN) {
         const float fx = static_cast<float>(col) * p.res_scale;
         const int jx0 = static_cast<int>(fx);
@@ -624,13 +625,14 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
                   float ty = 0.f;
                   const uint8_t* r0 = nullptr;
                   const uint8_t* r1p = nullptr;
+                  int jy0 = -1, jy1 = -1;
                   if constexpr (JOIN) {
                     const float fy = static_cast<float>(it.po0 + row) * p.res_scale;
-                    const int y0 = static_cast<int>(fy);
-                    const int y1 = min(y0 + 1, p.res_side - 1);
-                    ty = fy - static_cast<float>(y0);
-                    r0 = jsrc + static_cast<uint32_t>(y0) * jrow_bytes;
-                    r1p = jsrc + static_cast<uint32_t>(y1) * jrow_bytes;
+                    jy0 = static_cast<int>(fy);
+                    jy1 = min(jy0 + 1, p.res_side - 1);
+                    ty = fy - static_cast<float>(jy0);
+                    r0 = jsrc + static_cast<uint32_t>(jy0) * jrow_bytes;
+                    r1p = jsrc + static_cast<uint32_t>(jy1) * jrow_bytes;
                   }
                   const size_t lo_off = static_cast<size_t>(p.cb_out_total) * out_plane_bytes;  // hi plane -> lo plane
                   const uint32_t jlo_off = static_cast<uint32_t>(p.cb_out_total) * jplane_bytes;
@@ -651,15 +653,41 @@ __global__ void __launch_bounds__(tc_threads(CREAL), 1) conv_tc_kernel(const TcP
                           out8[2 * q + 1] = a.y + b.y;
                         }
                       };
-                      float tl[8], tr[8], bl[8], br[8];
-                      tap(r0, 0, tl);
-                      tap(r0, jdx, tr);
-                      tap(r1p, 0, bl);
-                      tap(r1p, jdx, br);
+                      // horizontal leg per source row; the lower row of this output row is the upper row of the next one
+                      // whenever the source rows advance by one (conv2d_3's 215 -> 205 resize)
+                      auto hrow = [&](const uint8_t* rowp, float* out8) {
+                        float l8[8], r8[8];
+                        tap(rowp, 0, l8);
+                        tap(rowp, jdx, r8);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) out8[e] = l8[e] + (r8[e] - l8[e]) * jtxf;
+                      };
+                      float top[8], bot[8];
+                      if (CG == 8 && jy_split == jy0) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) top[e] = jbot_f[e];
+                      } else {
+                        hrow(r0, top);
+                      }
+                      hrow(r1p, bot);
+                      if (CG == 8) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) jbot_f[e] = bot[e];
+                        jy_split = jy1;
+                      }
+                      {  // the next two output rows read the source rows below: start pulling them towards L1 now
+                        const int step = POOL == 42 ? 2 : 1;
+#pragma unroll
+                        for (int a = 1; a <= 2; ++a) {
+                          const uint8_t* pn = jsrc + static_cast<uint32_t>(min(jy1 + a * step, p.res_side - 1)) * jrow_bytes +
+                                              cb * jplane_bytes;
+                          asm volatile("prefetch.global.L1 [%0];" ::"l"(pn));
+                          asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + jlo_off));
+                        }
+                      }
 #pragma unroll
                       for (int e = 0; e < 8; ++e) {
-                        const float top = tl[e] + (tr[e] - tl[e]) * jtxf, bot = bl[e] + (br[e] - bl[e]) * jtxf;
-                        const float rs = top + (bot - top) * ty;
+                        const float rs = top[e] + (bot[e] - top[e]) * ty;
                         const int ch = grp * CG + 8 * cb + e;
                         v[e] = v[e] + fmaf(s_abc[COUT + ch], rs, s_abc[2 * COUT + ch]);  // A was applied to the window sums
                       }
@@ -837,6 +865,7 @@ struct TailParams {
   int S7;           // side of the input map
   float in_scale;   // stored -> true
   int flat_len;
+  int split;        // the input tensor carries hi + lo planes (RN_PREC_FP32_TC)
 };
 
 constexpr int kTailC = 16;
@@ -949,16 +978,23 @@ __global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __rest
   }
   pdl_wait();  // everything above is constant data; p7 is the previous kernel's output
   // chunked 16-bit [y][cb(2)][x][8] -> channel-major fp32, true scale
-  const uint16_t* src = p7 + static_cast<size_t>(n) * S * S * kTailC;
+  // (fp32-class path: rows of [hi0 | hi1 | lo0 | lo1] planes, the value is hi + lo)
+  const int planes = tp.split ? 4 : 2;
+  const uint16_t* src = p7 + static_cast<size_t>(n) * S * S * 8 * planes;
   for (int i = threadIdx.x; i < S * S * kTailC; i += blockDim.x) {
     const int e = i % 8, x = (i / 8) % S, cb = (i / (8 * S)) % 2, y = i / (16 * S);
-    const uint16_t raw = src[i];
+    const int at = ((y * planes + cb) * S + x) * 8 + e;
+    const uint16_t raw = src[at];
     float f;
     if (bf16) {
       f = __uint_as_float(static_cast<uint32_t>(raw) << 16);
     } else {
       __half h = *reinterpret_cast<const __half*>(&raw);
       f = __half2float(h);
+      if (tp.split) {
+        const uint16_t raw_lo = src[at + 2 * S * 8];
+        f += __half2float(*reinterpret_cast<const __half*>(&raw_lo));
+      }
     }
     s_in[((cb * 8 + e) * S + y) * S + x] = f * tp.in_scale;
   }
@@ -1367,6 +1403,8 @@ cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfK
     if (cb == 16 && cp == 32 && pool == 42 && L.join_src) return launch_tc_split<16, 32, 42, 1, 0, 32, true>(L, in, out, N, st);
     if (cb == 16 && cp == 32 && pool == 0 && !L.join_src)
       return seg2 ? launch_tc_split<16, 32, 0, 2, 0>(L, in, out, N, st) : launch_tc_split<16, 32, 0, 1, 0>(L, in, out, N, st);
+    if (cb == 32 && cp == 16 && pool == 42 && !L.join_src)
+      return seg2 ? launch_tc_split<32, 16, 42, 2, 0>(L, in, out, N, st) : launch_tc_split<32, 16, 42, 1, 0>(L, in, out, N, st);
     return cudaErrorInvalidValue;
   }
   if (L.amode == 2) return launch_tc<1, 16, 31, 1, 2, 8>(L, in, out, N, kind, st);
@@ -1403,8 +1441,8 @@ bool TailFusedSupported(int s7, int channels) { return channels == kTailC && s7 
 cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float* w8, const float* b8, const float* w9,
                       const float* b9, const float* ja, const float* jb, const float* jc, const DenseParams& dp,
                       int flat_len, HalfKind kind, long long* top1, float* probs, float* logits, float* dbg8,
-                      float* dbg9, cudaStream_t st) {
-  TailParams tp{w8, b8, w9, b9, ja, jb, jc, dp, S7, in_scale, flat_len};
+                      float* dbg9, cudaStream_t st, bool split) {
+  TailParams tp{w8, b8, w9, b9, ja, jb, jc, dp, S7, in_scale, flat_len, split ? 1 : 0};
   const int S8 = (S7 - 2 - 4) / 2 + 1, S9 = (S8 - 2 - 4) / 2 + 1;
   size_t floats = 16 * S7 * S7 + 16 * (S7 - 2) * (S7 - 2) + 16 * S8 * S8 + 2 * 16 * S9 * S9 + 2 * 9 * 16 * 16;
   for (int l = 0; l < 4; ++l) floats += static_cast<size_t>(l == 0 ? flat_len : dp.out[l - 1]) * dp.out[l] + dp.out[l];
@@ -1420,6 +1458,44 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
                 static_cast<int>(kind == HalfKind::kBF16), top1, probs, logits, dbg8, dbg9);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
+}
+
+// Vector form of chunked_to_f32_kernel for fp16 tensors: one thread per (image row, chunk, pixel), pixels fastest, so
+// the 16-byte chunk loads of a warp are one contiguous 512-byte run and every store fills whole 32-byte sectors.
+__global__ void chunked_to_f32_vec_kernel(const uint4* __restrict__ in, float4* __restrict__ out, int N, int S, int C,
+                                          float scale, int split) {
+  const int CBl = C / 8, CBn = split ? 2 * CBl : CBl;
+  const size_t total = static_cast<size_t>(N) * S * CBl * S;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % S);
+    size_t r = i / S;
+    const int cb = static_cast<int>(r % CBl);
+    r /= CBl;  // r = n * S + y
+    const size_t at = (r * CBn + cb) * S + x;
+    const uint4 h = in[at];
+    float v[8];
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[q]));
+      v[2 * q] = f.x;
+      v[2 * q + 1] = f.y;
+    }
+    if (split) {
+      const uint4 l = in[at + static_cast<size_t>(CBl) * S];
+      const uint32_t lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&lw[q]));
+        v[2 * q] += f.x;
+        v[2 * q + 1] += f.y;
+      }
+    }
+    float4* o = out + ((r * S + x) * C + cb * 8) / 4;
+    o[0] = make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+    o[1] = make_float4(v[4] * scale, v[5] * scale, v[6] * scale, v[7] * scale);
+  }
 }
 
 // fp32 NHWC [N, S, S, C] * scale -> split chunked tensor with Cpad logical channels (hi planes, then lo planes, fp16)
@@ -1454,6 +1530,12 @@ cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, i
 cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale,
                          cudaStream_t st, bool split) {
   size_t total = static_cast<size_t>(N) * S * S * Ch;
+  if (kind == HalfKind::kF16 && Ch % 8 == 0) {
+    int vblocks = static_cast<int>(std::min<size_t>((total / 8 + 255) / 256, static_cast<size_t>(SmCount()) * 16));
+    chunked_to_f32_vec_kernel<<<vblocks, 256, 0, st>>>(static_cast<const uint4*>(in), reinterpret_cast<float4*>(out), N, S, Ch,
+                                                       scale, split ? 1 : 0);
+    return cudaGetLastError();
+  }
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
   chunked_to_f32_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint16_t*>(in), out, N, S, Ch,
                                                 kind == HalfKind::kBF16, scale, split ? 1 : 0);

@@ -7,8 +7,9 @@ import torch
 from roomnet_b200.workload import default_checkpoint_prefix, synthetic_suite
 from roomnet_b200 import _capi
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+precision = sys.argv[2] if len(sys.argv) > 2 else "fp16"
 steps = 10
-h = _capi.Handle(precision="fp16"); h.load_tf_checkpoint(default_checkpoint_prefix())
+h = _capi.Handle(precision=precision); h.load_tf_checkpoint(default_checkpoint_prefix())
 imgs = synthetic_suite(64)[np.arange(B) % 64]
 d_in = torch.from_numpy(np.ascontiguousarray(imgs)).cuda()
 d_top1 = torch.empty(B, dtype=torch.int64, device="cuda"); d_probs = torch.empty(B, 6, device="cuda")
