@@ -43,8 +43,10 @@ enum rn_precision {
   RN_PREC_FP32 = 0,  /* fp32 FMA on CUDA cores end to end; budget: max|dlogit| <= 1e-3 */
   RN_PREC_FP16 = 1,  /* 16-bit tensor-core path: fp16 operands, fp32 accumulate (tcgen05 kind::f16); budget 2e-2 */
   RN_PREC_BF16 = 2,  /* same kernels with bf16 operands; measured to MISS the 2e-2 budget on flat images */
-  RN_PREC_FP32_TC = 3 /* fp32-class path on the tensor cores: activations and weights as hi + lo fp16 pairs, three
+  RN_PREC_FP32_TC = 3, /* fp32-class path on the tensor cores: activations and weights as hi + lo fp16 pairs, three
                          products per MAC (xh*wh + xl*wh + xh*wl) into fp32 accumulators, fp32 epilogues; budget 1e-3 */
+  RN_PREC_BF16X3 = 4  /* BF16 operands that DO meet the 2e-2 budget: the three-product scheme of RN_PREC_FP32_TC with bf16
+                         halves (hi + lo = 16 mantissa bits per operand), a third of the single-product rate */
 };
 
 enum rn_flags {

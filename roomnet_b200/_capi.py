@@ -18,8 +18,8 @@ RN_FLAG_LAYERWISE = 1
 RN_MAX_DEVICES = 16
 
 RN_OK, RN_ERR_INVALID_ARG, RN_ERR_IO, RN_ERR_FORMAT, RN_ERR_NOT_LOADED, RN_ERR_CUDA, RN_ERR_INTERNAL = range(7)
-RN_PREC_FP32, RN_PREC_FP16, RN_PREC_BF16, RN_PREC_FP32_TC = 0, 1, 2, 3
-PRECISIONS = {"fp32": RN_PREC_FP32, "fp16": RN_PREC_FP16, "bf16": RN_PREC_BF16, "fp32tc": RN_PREC_FP32_TC}
+RN_PREC_FP32, RN_PREC_FP16, RN_PREC_BF16, RN_PREC_FP32_TC, RN_PREC_BF16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"fp32": RN_PREC_FP32, "fp16": RN_PREC_FP16, "bf16": RN_PREC_BF16, "fp32tc": RN_PREC_FP32_TC, "bf16x3": RN_PREC_BF16X3}
 
 
 class RoomNetError(RuntimeError):

@@ -256,7 +256,7 @@ static int CreateImpl(const rn_config* cfg, rn_handle** out) {
     g_create_error = "rn_config.abi_version mismatch";
     return RN_ERR_INVALID_ARG;
   }
-  if (cfg->precision < RN_PREC_FP32 || cfg->precision > RN_PREC_FP32_TC) {
+  if (cfg->precision < RN_PREC_FP32 || cfg->precision > RN_PREC_BF16X3) {
     g_create_error = "unknown precision";
     return RN_ERR_INVALID_ARG;
   }

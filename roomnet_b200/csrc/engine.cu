@@ -37,10 +37,12 @@ size_t InputBytesPerImage(const NetShape& s, InputKind k) {
 Replica::Replica(int device, const NetShape& shape, int precision, int max_batch, int flags)
     : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
   layerwise_ = (flags & RN_FLAG_LAYERWISE) != 0;
-  half_kind_ = precision == RN_PREC_BF16 ? HalfKind::kBF16 : HalfKind::kF16;
+  half_kind_ = (precision == RN_PREC_BF16 || precision == RN_PREC_BF16X3) ? HalfKind::kBF16 : HalfKind::kF16;
   // RN_PREC_FP32_TC: conv0..conv7 as three-product split-fp16 tensor-core layers (hi + lo activations, [Wh | Wl]
   // weights, fp32 epilogues); the small tail (conv8, conv9, dense head) is fp32 as on the 16-bit path
-  split_ = precision == RN_PREC_FP32_TC;
+  // RN_PREC_BF16X3: the same three-product scheme with bf16 halves (16 mantissa bits per operand): the BF16 path that
+  // meets the 2e-2 budget, at a third of the single-product rate
+  split_ = precision == RN_PREC_FP32_TC || precision == RN_PREC_BF16X3;
   first_f32_layer_ = precision == RN_PREC_FP32 ? 0 : 8;
 }
 
@@ -241,9 +243,9 @@ cudaError_t Replica::Upload(const FoldedNet& f) {
           for (int c = 0; c < cs.cin; ++c)
             for (int o = 0; o < cs.cout; ++o)
               wpad[(static_cast<size_t>(t) * cin_l + c) * cs.cout + o] = f.conv[i].w[(static_cast<size_t>(t) * cs.cin + c) * cs.cout + o];
-        part_bytes = PackTcWeightsSplit(nullptr, cin_l, cs.cout, L.cout_parts, 1.0, nullptr);
+        part_bytes = PackTcWeightsSplit(nullptr, cin_l, cs.cout, L.cout_parts, half_kind_, 1.0, nullptr);
         host.resize(part_bytes * L.cout_parts);
-        PackTcWeightsSplit(wpad.data(), cin_l, cs.cout, L.cout_parts, 1.0 / (6.0 * g_in), host.data());
+        PackTcWeightsSplit(wpad.data(), cin_l, cs.cout, L.cout_parts, half_kind_, 1.0 / (6.0 * g_in), host.data());
       } else {
       part_bytes = PackTcWeights(nullptr, cs.cin, cs.cout, L.cout_parts, half_kind_, 1.0, nullptr);
       host.resize(part_bytes * L.cout_parts);
@@ -378,7 +380,7 @@ cudaError_t Replica::ForwardTc(const void* d_in, InputKind kind, int n, long lon
     RN_CUDA(AvgPoolF32(cur_->conv_scratch, cur_->pooled[0], n, c0.conv_side, c0.conv_side, c0.cout, c0.pool_k, c0.pool_s, st));
     Mark("pool0_f32", st);
     RN_CUDA(F32ToSplitChunked(cur_->pooled[0], cur_->act_h[0], n, c0.out_side, c0.cout, 16,
-                              static_cast<float>(act_scale_[0]), st));
+                              static_cast<float>(act_scale_[0]), half_kind_, st));
     Mark("f32_to_split", st);
   } else if (kind == InputKind::kF32Rgb) {
     // raw float feed: operands need more than 11 bits, keep conv0 in fp32 on the CUDA cores

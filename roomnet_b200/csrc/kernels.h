@@ -77,9 +77,10 @@ size_t ChunkedBytes(int n, int side, int channels);
 // `in_scale` (optional, [cin]) multiplies the weights of one input channel on top of that.
 size_t PackTcWeights(const double* w_hwio, int cin, int cout, int cout_parts, HalfKind kind, double scale,
                      void* out_host, const double* in_scale = nullptr);
-// fp32-class path: per part [Wh | Wl] with wh = round16(scale * w), wl = round16(scale * w - wh) (fp16); `cin` = LOGICAL
+// split paths: per part [Wh | Wl] with wh = round16(scale * w), wl = round16(scale * w - wh); `cin` = LOGICAL
 // input channels (a multiple of 16).  Returns the bytes of one part.
-size_t PackTcWeightsSplit(const double* w_hwio, int cin, int cout, int cout_parts, double scale, void* out_host);
+size_t PackTcWeightsSplit(const double* w_hwio, int cin, int cout, int cout_parts, HalfKind kind, double scale,
+                          void* out_host);
 // Round a value to the 16-bit storage type of the tensor-core path and return it as a double.
 double RoundToHalfKind(double v, HalfKind kind);
 
@@ -109,7 +110,8 @@ cudaError_t TailFused(const void* p7, int N, int S7, float in_scale, const float
                       int flat_len, HalfKind kind, long long* top1, float* probs, float* logits, float* dbg8,
                       float* dbg9, cudaStream_t st, bool split = false);
 // chunked 16-bit -> NHWC fp32
-cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, int Cpad, float scale, cudaStream_t st);
+cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, int Cpad, float scale, HalfKind kind,
+                              cudaStream_t st);
 cudaError_t ChunkedToF32(const void* in, float* out, int N, int S, int Ch, HalfKind kind, float scale, cudaStream_t st,
                          bool split = false);
 

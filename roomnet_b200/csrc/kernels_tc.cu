@@ -986,15 +986,11 @@ __global__ void __launch_bounds__(1024) tail_fused_kernel(const uint16_t* __rest
     const int at = ((y * planes + cb) * S + x) * 8 + e;
     const uint16_t raw = src[at];
     float f;
+    const uint16_t raw_lo = tp.split ? src[at + 2 * S * 8] : static_cast<uint16_t>(0);
     if (bf16) {
-      f = __uint_as_float(static_cast<uint32_t>(raw) << 16);
+      f = __uint_as_float(static_cast<uint32_t>(raw) << 16) + __uint_as_float(static_cast<uint32_t>(raw_lo) << 16);
     } else {
-      __half h = *reinterpret_cast<const __half*>(&raw);
-      f = __half2float(h);
-      if (tp.split) {
-        const uint16_t raw_lo = src[at + 2 * S * 8];
-        f += __half2float(*reinterpret_cast<const __half*>(&raw_lo));
-      }
+      f = __half2float(*reinterpret_cast<const __half*>(&raw)) + __half2float(*reinterpret_cast<const __half*>(&raw_lo));
     }
     s_in[((cb * 8 + e) * S + y) * S + x] = f * tp.in_scale;
   }
@@ -1095,7 +1091,7 @@ __global__ void chunked_to_f32_kernel(const uint16_t* __restrict__ in, float* __
     }
     if (split) {
       uint16_t raw_lo = in[at + static_cast<size_t>(CBl) * S * 8];
-      f += __half2float(*reinterpret_cast<__half*>(&raw_lo));
+      f += bf16 ? __uint_as_float(static_cast<uint32_t>(raw_lo) << 16) : __half2float(*reinterpret_cast<__half*>(&raw_lo));
     }
     out[i] = f * scale;
   }
@@ -1249,10 +1245,11 @@ cudaError_t launch_tc(const TcConvLayer& L, const void* in, void* out, int N, Ha
   return kind == HalfKind::kBF16 ? launch_tc_impl<CB, COUT, POOL, SEG, AMODE, true, CREAL, JOIN>(L, in, out, N, st)
                                  : launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL, JOIN>(L, in, out, N, st);
 }
-// split (fp32-class) layers exist with fp16 halves only
+// split layers: fp16 halves (RN_PREC_FP32_TC) or bf16 halves (RN_PREC_BF16X3)
 template <int CB, int COUT, int POOL, int SEG, int AMODE, int CREAL = COUT, bool JOIN = false>
-cudaError_t launch_tc_split(const TcConvLayer& L, const void* in, void* out, int N, cudaStream_t st) {
-  return launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL, JOIN, true>(L, in, out, N, st);
+cudaError_t launch_tc_split(const TcConvLayer& L, const void* in, void* out, int N, HalfKind kind, cudaStream_t st) {
+  return kind == HalfKind::kBF16 ? launch_tc_impl<CB, COUT, POOL, SEG, AMODE, true, CREAL, JOIN, true>(L, in, out, N, st)
+                                 : launch_tc_impl<CB, COUT, POOL, SEG, AMODE, false, CREAL, JOIN, true>(L, in, out, N, st);
 }
 
 uint16_t to_half_bits(double v, HalfKind kind) {
@@ -1317,20 +1314,20 @@ size_t PackTcWeights(const double* w, int cin, int cout, int cout_parts, HalfKin
   return part_bytes;
 }
 
-size_t PackTcWeightsSplit(const double* w, int cin, int cout, int cout_parts, double scale, void* out_host) {
+size_t PackTcWeightsSplit(const double* w, int cin, int cout, int cout_parts, HalfKind kind, double scale, void* out_host) {
   // per part: [Wh image | Wl image], each laid out as PackTcWeights does; wh = round16(scale * w), wl = round16(rest)
-  const size_t pb = PackTcWeights(nullptr, cin, cout, cout_parts, HalfKind::kF16, 1.0, nullptr);
+  const size_t pb = PackTcWeights(nullptr, cin, cout, cout_parts, kind, 1.0, nullptr);
   if (!out_host) return 2 * pb;
   const size_t n = static_cast<size_t>(9) * cin * cout;
   std::vector<double> wh(n), wl(n);
   for (size_t i = 0; i < n; ++i) {
     const double v = scale * w[i];
-    wh[i] = RoundToHalfKind(v, HalfKind::kF16);
-    wl[i] = RoundToHalfKind(v - wh[i], HalfKind::kF16);
+    wh[i] = RoundToHalfKind(v, kind);
+    wl[i] = RoundToHalfKind(v - wh[i], kind);
   }
   std::vector<uint8_t> hi(pb * cout_parts), lo(pb * cout_parts);
-  PackTcWeights(wh.data(), cin, cout, cout_parts, HalfKind::kF16, 1.0, hi.data());
-  PackTcWeights(wl.data(), cin, cout, cout_parts, HalfKind::kF16, 1.0, lo.data());
+  PackTcWeights(wh.data(), cin, cout, cout_parts, kind, 1.0, hi.data());
+  PackTcWeights(wl.data(), cin, cout, cout_parts, kind, 1.0, lo.data());
   uint8_t* o = static_cast<uint8_t*>(out_host);
   for (int part = 0; part < cout_parts; ++part) {
     std::memcpy(o + 2 * pb * part, hi.data() + pb * part, pb);
@@ -1393,18 +1390,17 @@ cudaError_t ConvTc(const TcConvLayer& L, const void* in, void* out, int N, HalfK
   const bool seg2 = L.pool_k ? (L.out_side <= 28 && L.in_side <= 64) : L.in_side <= 64;
   const int pool = L.pool_k * 10 + L.pool_s;
   if (L.split) {  // fp32-class path: L.cin counts the physical (hi + lo) channels
-    if (kind != HalfKind::kF16) return cudaErrorInvalidValue;
-    if (L.amode == 2) return launch_tc_split<1, 16, 31, 1, 2, 16>(L, in, out, N, st);
-    if (cb == 4 && cp == 32 && pool == 41 && !L.join_src) return launch_tc_split<4, 32, 41, 1, 0>(L, in, out, N, st);
+    if (L.amode == 2) return launch_tc_split<1, 16, 31, 1, 2, 16>(L, in, out, N, kind, st);
+    if (cb == 4 && cp == 32 && pool == 41 && !L.join_src) return launch_tc_split<4, 32, 41, 1, 0>(L, in, out, N, kind, st);
     if (cb == 8 && cp == 32 && pool == 41)
-      return L.join_src ? launch_tc_split<8, 32, 41, 1, 0, 32, true>(L, in, out, N, st)
-                        : launch_tc_split<8, 32, 41, 1, 0>(L, in, out, N, st);
-    if (cb == 8 && cp == 64 && pool == 42 && !L.join_src) return launch_tc_split<8, 64, 42, 1, 0>(L, in, out, N, st);
-    if (cb == 16 && cp == 32 && pool == 42 && L.join_src) return launch_tc_split<16, 32, 42, 1, 0, 32, true>(L, in, out, N, st);
+      return L.join_src ? launch_tc_split<8, 32, 41, 1, 0, 32, true>(L, in, out, N, kind, st)
+                        : launch_tc_split<8, 32, 41, 1, 0>(L, in, out, N, kind, st);
+    if (cb == 8 && cp == 64 && pool == 42 && !L.join_src) return launch_tc_split<8, 64, 42, 1, 0>(L, in, out, N, kind, st);
+    if (cb == 16 && cp == 32 && pool == 42 && L.join_src) return launch_tc_split<16, 32, 42, 1, 0, 32, true>(L, in, out, N, kind, st);
     if (cb == 16 && cp == 32 && pool == 0 && !L.join_src)
-      return seg2 ? launch_tc_split<16, 32, 0, 2, 0>(L, in, out, N, st) : launch_tc_split<16, 32, 0, 1, 0>(L, in, out, N, st);
+      return seg2 ? launch_tc_split<16, 32, 0, 2, 0>(L, in, out, N, kind, st) : launch_tc_split<16, 32, 0, 1, 0>(L, in, out, N, kind, st);
     if (cb == 32 && cp == 16 && pool == 42 && !L.join_src)
-      return seg2 ? launch_tc_split<32, 16, 42, 2, 0>(L, in, out, N, st) : launch_tc_split<32, 16, 42, 1, 0>(L, in, out, N, st);
+      return seg2 ? launch_tc_split<32, 16, 42, 2, 0>(L, in, out, N, kind, st) : launch_tc_split<32, 16, 42, 1, 0>(L, in, out, N, kind, st);
     return cudaErrorInvalidValue;
   }
   if (L.amode == 2) return launch_tc<1, 16, 31, 1, 2, 8>(L, in, out, N, kind, st);
@@ -1500,7 +1496,7 @@ __global__ void chunked_to_f32_vec_kernel(const uint4* __restrict__ in, float4* 
 
 // fp32 NHWC [N, S, S, C] * scale -> split chunked tensor with Cpad logical channels (hi planes, then lo planes, fp16)
 __global__ void f32_to_split_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, int N, int S, int C, int Cpad,
-                                    float scale) {
+                                    float scale, int bf16) {
   const size_t total = static_cast<size_t>(N) * S * S * Cpad;
   const int CBl = Cpad / 8;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -1512,18 +1508,27 @@ __global__ void f32_to_split_kernel(const float* __restrict__ in, uint16_t* __re
     const int y = static_cast<int>(r % S);
     const int n = static_cast<int>(r / S);
     const float v = c < C ? in[((static_cast<size_t>(n) * S + y) * S + x) * C + c] * scale : 0.f;
-    const __half h = __float2half_rn(v);
-    const __half l = __float2half_rn(v - __half2float(h));
     const size_t at = ((((static_cast<size_t>(n) * S + y) * (2 * CBl) + c / 8) * S) + x) * 8 + (c % 8);
-    out[at] = *reinterpret_cast<const uint16_t*>(&h);
-    out[at + static_cast<size_t>(CBl) * S * 8] = *reinterpret_cast<const uint16_t*>(&l);
+    if (bf16) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+      out[at] = *reinterpret_cast<const uint16_t*>(&h);
+      out[at + static_cast<size_t>(CBl) * S * 8] = *reinterpret_cast<const uint16_t*>(&l);
+    } else {
+      const __half h = __float2half_rn(v);
+      const __half l = __float2half_rn(v - __half2float(h));
+      out[at] = *reinterpret_cast<const uint16_t*>(&h);
+      out[at + static_cast<size_t>(CBl) * S * 8] = *reinterpret_cast<const uint16_t*>(&l);
+    }
   }
 }
 
-cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, int Cpad, float scale, cudaStream_t st) {
+cudaError_t F32ToSplitChunked(const float* in, void* out, int N, int S, int C, int Cpad, float scale, HalfKind kind,
+                              cudaStream_t st) {
   size_t total = static_cast<size_t>(N) * S * S * Cpad;
   int blocks = static_cast<int>(std::min<size_t>((total + 255) / 256, static_cast<size_t>(SmCount()) * 16));
-  f32_to_split_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint16_t*>(out), N, S, C, Cpad, scale);
+  f32_to_split_kernel<<<blocks, 256, 0, st>>>(in, static_cast<uint16_t*>(out), N, S, C, Cpad, scale,
+                                              kind == HalfKind::kBF16 ? 1 : 0);
   return cudaGetLastError();
 }
 
