@@ -76,6 +76,7 @@ WANT = collections.OrderedDict([
 ])
 CAPTURES = [("full", "16-bit tensor-core path, `tools/profile_once.py --batch 256` (one launch = one half-batch of 128 images)"),
             ("fp32", "fp32 CUDA-core path, `tools/profile_once.py --batch 8 --precision fp32`"),
+            ("fp32tc", "fp32-class tensor-core path (split-fp16 layers), `tools/profile_once.py --batch 256 --precision fp32tc`"),
             ("front", "front-end kernels and the 300 / 600 variants, `tools/profile_front.py`")]
 traffic = {}
 for suffix, what in CAPTURES:
