@@ -224,6 +224,23 @@ def test_replicas_on_two_gpus_are_bit_identical(capi, ckpt_prefix, suite64):
     _, p1, l1 = one.infer_u8_bgr(imgs, want_logits=True)
     _, p2, l2 = two.infer_u8_bgr(imgs, want_logits=True)
     assert np.array_equal(l1, l2) and np.array_equal(p1, p2)
+    # asynchronous calls through the replicas' workers: three calls in flight, then a synchronous one behind them
+    x = torch.from_numpy(np.ascontiguousarray(imgs)).pin_memory()
+    outs = [(torch.empty(len(imgs), dtype=torch.int64).pin_memory(), torch.empty(len(imgs), 6).pin_memory(),
+             torch.empty(len(imgs), 6).pin_memory()) for _ in range(3)]
+    tickets = [two.submit_raw(x.data_ptr(), len(imgs), t.data_ptr(), p.data_ptr(), l.data_ptr()) for t, p, l in outs]
+    _, _, l3 = two.infer_u8_bgr(imgs[:37], want_logits=True)
+    two.wait(tickets[-1])
+    for t, p, l in outs:
+        assert np.array_equal(l.numpy(), l1) and np.array_equal(p.numpy(), p1)
+    assert np.array_equal(l3, l1[:37])
+    # the batched photo front end splits its list over the replicas as well
+    rng = np.random.default_rng(5)
+    photos = [rng.integers(0, 256, (int(rng.integers(100, 400)), int(rng.integers(100, 400)), 3), dtype=np.uint8)
+              for _ in range(21)]
+    a = one.infer_images_u8_bgr(photos, want_logits=True)
+    b = two.infer_images_u8_bgr(photos, want_logits=True)
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0])
 
 
 def test_drop_in_roomnet_class(ckpt_prefix, suite64, golden):
