@@ -104,9 +104,10 @@ int rn_set_dense0(rn_handle* h, const float* kernel /* [flat_len,32] */, int32_t
 int rn_infer_u8_bgr(rn_handle* h, const uint8_t* nhwc, int32_t n, int64_t* top1, float* probs, float* logits);
 
 /* Asynchronous form of rn_infer_u8_bgr for callers that stream batches (classify_im_dir, infer.py:65-100, feeds
- * one image after the other; the batch scheduler here keeps two calls in flight).  rn_submit_u8_bgr enqueues the
- * host->device copies, the kernels and the device->host result copies of one call and returns a ticket; it blocks
- * only while both staging slots of a replica are still busy.  The output buffers (and, when `nhwc` is page-locked
+ * one image after the other; a batch scheduler on this ABI keeps two or three calls in flight).  rn_submit_u8_bgr
+ * enqueues the host->device copies and the kernels of one call (the last kernel stores the results into mapped host
+ * memory) and returns a ticket; it blocks only while all eight staging slots of a replica (one per micro-batch of at
+ * most max_batch images) are still busy.  The output buffers (and, when `nhwc` is page-locked
  * memory, the input) must stay valid until rn_wait(h, ticket) has returned: results are written by a later
  * rn_submit_u8_bgr / rn_wait on the calling thread.  rn_wait(h, 0) waits for everything submitted so far; the
  * synchronous entry points wait for earlier submissions first.  Same arithmetic, same results as rn_infer_u8_bgr. */

@@ -163,7 +163,7 @@ int InferImpl(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* 
 }
 
 // rn_submit_*: the shards of one call are enqueued by the replicas' workers (one replica: by the caller); nothing waits
-// for the GPU here unless a replica's two staging slots are both still in flight.
+// for the GPU here unless every staging slot of a replica (Replica::kSlots micro-batches) is still in flight.
 int SubmitImpl(rn_handle* h, const void* in, InputKind kind, int32_t n, int64_t* top1, float* probs, float* logits,
                uint64_t* ticket) {
   if (!h) return RN_ERR_INVALID_ARG;

@@ -138,10 +138,10 @@ cudaError_t Replica::Init() {
   for (int i = 0; i < 2; ++i) RN_CUDA(cudaMallocHost(&h_in_[i], in_bytes));
   for (int i = 0; i < kSlots; ++i) {
     RN_CUDA(Alloc(&d_in_[i], in_bytes));
-    RN_CUDA(Alloc(reinterpret_cast<void**>(&d_top1_[i]), B * sizeof(long long)));
-    RN_CUDA(Alloc(reinterpret_cast<void**>(&d_probs_[i]), B * C * sizeof(float)));
-    RN_CUDA(Alloc(reinterpret_cast<void**>(&d_logits_[i]), B * C * sizeof(float)));
-    RN_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_out_[i]), B * (sizeof(long long) + 2 * C * sizeof(float))));
+    // results: the tail kernel stores top-1 / probabilities / logits (56 bytes per image) straight into this pinned,
+    // device-mapped host buffer - no device-to-host copy operations on the compute stream
+    RN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_out_[i]), B * (sizeof(long long) + 2 * C * sizeof(float)),
+                          cudaHostAllocMapped | cudaHostAllocPortable));
   }
   return cudaSuccess;
 }
@@ -505,14 +505,23 @@ cudaError_t Replica::DrainSlot(int slot) {
   if (!q.active) return cudaSuccess;
   q.active = false;
   RN_CUDA(cudaEventSynchronize(ev_done_[slot]));
-  const int C = shape_.num_classes;
-  const char* base = h_out_[slot];
-  if (q.top1) std::memcpy(q.top1, base, q.m * sizeof(long long));
-  if (q.probs) std::memcpy(q.probs, base + max_batch_ * sizeof(long long), static_cast<size_t>(q.m) * C * sizeof(float));
-  if (q.logits)
-    std::memcpy(q.logits, base + max_batch_ * (sizeof(long long) + C * sizeof(float)),
-                static_cast<size_t>(q.m) * C * sizeof(float));
+  Deliver(slot, q.m, q.top1, q.probs, q.logits);
   return cudaSuccess;
+}
+
+Replica::HostOut Replica::Out(int slot) const {
+  const int C = shape_.num_classes;
+  char* base = h_out_[slot];
+  return HostOut{reinterpret_cast<long long*>(base), reinterpret_cast<float*>(base + max_batch_ * sizeof(long long)),
+                 reinterpret_cast<float*>(base + max_batch_ * (sizeof(long long) + C * sizeof(float)))};
+}
+
+void Replica::Deliver(int slot, int m, int64_t* top1, float* probs, float* logits) const {
+  const int C = shape_.num_classes;
+  const HostOut ho = Out(slot);
+  if (top1) std::memcpy(top1, ho.top1, m * sizeof(long long));
+  if (probs) std::memcpy(probs, ho.probs, static_cast<size_t>(m) * C * sizeof(float));
+  if (logits) std::memcpy(logits, ho.logits, static_cast<size_t>(m) * C * sizeof(float));
 }
 
 // error path: nothing of this replica may still be running (or be delivered) when the failing call returns
@@ -557,7 +566,7 @@ cudaError_t Replica::SubmitHost(const void* h_in, InputKind kind, int n, int64_t
   cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may set a sticky-less error
   // Micro-batch schedule of one call: the first H2D copy is exposed when nothing is in flight, so the first
   // micro-batch is small; the rest are as large as possible (kernel efficiency) while still alternating between
-  // the two staging slots / activation sets so that copies overlap the previous micro-batch's kernels.
+  // the two activation sets so that copies overlap the previous micro-batches' kernels.
   std::vector<int> sizes;
   bool idle = true;
   for (const auto& q : pend_) idle = idle && !q.active;
@@ -600,20 +609,12 @@ cudaError_t Replica::SubmitHost(const void* h_in, InputKind kind, int n, int64_t
     cur_ = &sets_[profiling_ ? 0 : (slot_seq_ & 1)];
     cudaStream_t cs = profiling_ ? compute_ : cur_->stream;
     if ((e = cudaStreamWaitEvent(cs, ev_h2d_[slot], 0)) != cudaSuccess) return fail(e);
-    e = ForwardDevice(d_in_[slot], kind, m, d_top1_[slot], d_probs_[slot], d_logits_[slot], cs);
+    const HostOut ho = Out(slot);
+    e = ForwardDevice(d_in_[slot], kind, m, ho.top1, ho.probs, ho.logits, cs);
     if (e != cudaSuccess) {
       AbortPending();
       return e;
     }
-    char* base = h_out_[slot];
-    if ((e = cudaMemcpyAsync(base, d_top1_[slot], m * sizeof(long long), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-      return fail(e);
-    if ((e = cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[slot], m * C * sizeof(float),
-                             cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-      return fail(e);
-    if ((e = cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[slot],
-                             m * C * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-      return fail(e);
     if ((e = cudaEventRecord(ev_done_[slot], cs)) != cudaSuccess) return fail(e);
     PendingOut& q = pend_[slot];
     q.m = m;
@@ -749,20 +750,12 @@ cudaError_t Replica::InferImages(const uint8_t* const* imgs, const int* H, const
                               compute_));
     ++last_launches_;
     cur_ = &sets_[0];
-    cudaError_t e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, m, d_top1_[0], d_probs_[0], d_logits_[0], compute_);
+    const HostOut ho = Out(0);
+    cudaError_t e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, m, ho.top1, ho.probs, ho.logits, compute_);
     if (e != cudaSuccess) return e;
-    char* base = h_out_[0];
-    RN_CUDA(cudaMemcpyAsync(base, d_top1_[0], m * sizeof(long long), cudaMemcpyDeviceToHost, compute_));
-    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * sizeof(long long), d_probs_[0], m * C * sizeof(float),
-                            cudaMemcpyDeviceToHost, compute_));
-    RN_CUDA(cudaMemcpyAsync(base + max_batch_ * (sizeof(long long) + C * sizeof(float)), d_logits_[0],
-                            m * C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
     RN_CUDA(cudaStreamSynchronize(compute_));  // `descs` and the caller's images are pageable host memory
-    if (top1) std::memcpy(top1 + off, base, m * sizeof(long long));
-    if (probs) std::memcpy(probs + static_cast<size_t>(off) * C, base + max_batch_ * sizeof(long long), m * C * sizeof(float));
-    if (logits)
-      std::memcpy(logits + static_cast<size_t>(off) * C, base + max_batch_ * (sizeof(long long) + C * sizeof(float)),
-                  m * C * sizeof(float));
+    Deliver(0, m, top1 ? top1 + off : nullptr, probs ? probs + static_cast<size_t>(off) * C : nullptr,
+            logits ? logits + static_cast<size_t>(off) * C : nullptr);
   }
   return cudaSuccess;
 }
@@ -775,7 +768,7 @@ cudaError_t Replica::InferYuv420(const uint8_t* y, const uint8_t* u, const uint8
     if (ew != cudaSuccess) return ew;
   }
   RN_CUDA(cudaSetDevice(device_));
-  const int S = shape_.im_side, C = shape_.num_classes;
+  const int S = shape_.im_side;
   const size_t oy = 0, ou = (y_size + 255) & ~static_cast<size_t>(255), ov = ou + ((u_size + 255) & ~static_cast<size_t>(255));
   const size_t total = ov + v_size;
   if (total > d_raw_cap_) {
@@ -794,17 +787,11 @@ cudaError_t Replica::InferYuv420(const uint8_t* y, const uint8_t* u, const uint8
   last_launches_ = 1;
   if (rgb_out) RN_CUDA(cudaMemcpyAsync(rgb_out, dst, static_cast<size_t>(S) * S * 3, cudaMemcpyDeviceToHost, compute_));
   cur_ = &sets_[0];
-  cudaError_t e = ForwardDevice(dst, InputKind::kU8Rgb, 1, d_top1_[0], d_probs_[0], d_logits_[0], compute_);
+  const HostOut ho = Out(0);
+  cudaError_t e = ForwardDevice(dst, InputKind::kU8Rgb, 1, ho.top1, ho.probs, ho.logits, compute_);
   if (e != cudaSuccess) return e;
-  long long t1 = 0;
-  std::vector<float> buf(2 * C);
-  RN_CUDA(cudaMemcpyAsync(&t1, d_top1_[0], sizeof(long long), cudaMemcpyDeviceToHost, compute_));
-  RN_CUDA(cudaMemcpyAsync(buf.data(), d_probs_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
-  RN_CUDA(cudaMemcpyAsync(buf.data() + C, d_logits_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
   RN_CUDA(cudaStreamSynchronize(compute_));
-  if (top1) *top1 = t1;
-  if (probs) std::memcpy(probs, buf.data(), C * sizeof(float));
-  if (logits) std::memcpy(logits, buf.data() + C, C * sizeof(float));
+  Deliver(0, 1, top1, probs, logits);
   return cudaSuccess;
 }
 
@@ -813,18 +800,11 @@ cudaError_t Replica::InferImage(const uint8_t* h_img, int H, int W, int64_t* top
   if (e != cudaSuccess) return e;
   last_launches_ = 1;
   cur_ = &sets_[0];
-  const int C = shape_.num_classes;
-  e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, 1, d_top1_[0], d_probs_[0], d_logits_[0], compute_);
+  const HostOut ho = Out(0);
+  e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, 1, ho.top1, ho.probs, ho.logits, compute_);
   if (e != cudaSuccess) return e;
-  long long t1 = 0;
-  std::vector<float> buf(2 * C);
-  RN_CUDA(cudaMemcpyAsync(&t1, d_top1_[0], sizeof(long long), cudaMemcpyDeviceToHost, compute_));
-  RN_CUDA(cudaMemcpyAsync(buf.data(), d_probs_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
-  RN_CUDA(cudaMemcpyAsync(buf.data() + C, d_logits_[0], C * sizeof(float), cudaMemcpyDeviceToHost, compute_));
   RN_CUDA(cudaStreamSynchronize(compute_));
-  if (top1) *top1 = t1;
-  if (probs) std::memcpy(probs, buf.data(), C * sizeof(float));
-  if (logits) std::memcpy(logits, buf.data() + C, C * sizeof(float));
+  Deliver(0, 1, top1, probs, logits);
   return cudaSuccess;
 }
 

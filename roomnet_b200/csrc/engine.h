@@ -43,8 +43,8 @@ class Replica {
                           uint8_t* rgb_out);
   cudaError_t InferImages(const uint8_t* const* imgs, const int* H, const int* W, int n, int64_t* top1, float* probs,
                           float* logits);
-  // Asynchronous form: SubmitHost enqueues the copies and kernels of one call and returns (it blocks only when both
-  // staging slots are still in flight); the results are delivered to the caller's buffers by a later SubmitHost that
+  // Asynchronous form: SubmitHost enqueues the copies and kernels of one call and returns (it blocks only when every
+  // staging slot is still in flight); the results are delivered to the caller's buffers by a later SubmitHost that
   // needs the slot, or by WaitHost(ticket), which returns once every call up to `ticket` has been delivered.
   cudaError_t SubmitHost(const void* h_in, InputKind kind, int n, int64_t* top1, float* probs, float* logits,
                          uint64_t ticket);
@@ -163,10 +163,14 @@ class Replica {
   // staging
   void* d_in_[kSlots] = {};
   void* h_in_[2] = {nullptr, nullptr};  // pinned bounce buffers for pageable caller memory (micro-batch j: j & 1)
-  long long* d_top1_[kSlots] = {};
-  float* d_probs_[kSlots] = {};
-  float* d_logits_[kSlots] = {};
-  char* h_out_[kSlots] = {};
+  char* h_out_[kSlots] = {};  // pinned + device-mapped result buffers, written by the tail kernel itself
+  struct HostOut {
+    long long* top1;
+    float* probs;
+    float* logits;
+  };
+  HostOut Out(int slot) const;
+  void Deliver(int slot, int m, int64_t* top1, float* probs, float* logits) const;
 };
 
 }  // namespace rn
