@@ -157,6 +157,33 @@ int rn_infer_image_u8_bgr(rn_handle* h, const uint8_t* img, int32_t H, int32_t W
 int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths,
                            int32_t n, int64_t* top1, float* probs, float* logits);
 
+/* cv2.imread(fpath) + RoomNet.infer_optimized(im)       infer.py:81-82
+ * n files as they sit on disk (files[i] = sizes[i] encoded bytes).  For baseline JPEG files (8-bit, Huffman, grey or
+ * YCbCr with 4:4:4 / 4:2:2 / 4:2:0 sampling, any EXIF orientation) only the entropy decoding runs on the host (on
+ * `threads` threads, 0 = as many as the machine has, at most 16); dequantisation, inverse DCT, chroma upsampling,
+ * colour conversion and EXIF orientation run on the device with the integer arithmetic of the decoder cv2 links
+ * (libjpeg-turbo defaults), so the decoded image - and everything after it - is bit-identical to cv2.imread's, and the
+ * decoded photo never exists in host memory.  status[i] (required) receives RN_JPEG_OK, RN_JPEG_UNSUPPORTED
+ * (progressive, arithmetic, CMYK, 12-bit, other samplings, not a JPEG at all) or RN_JPEG_CORRUPT (damaged or truncated
+ * stream); the outputs of entries that are not RN_JPEG_OK are left untouched - decode those with cv2.imread and pass
+ * them to rn_infer_images_u8_bgr, which is what roomnet_b200.network.RoomNet.infer_files does. */
+enum rn_jpeg_status { RN_JPEG_OK = 0, RN_JPEG_UNSUPPORTED = 1, RN_JPEG_CORRUPT = 2 };
+int rn_infer_jpeg(rn_handle* h, const uint8_t* const* files, const uint64_t* sizes, int32_t n, int32_t threads,
+                  int64_t* top1, float* probs, float* logits, int32_t* status);
+
+/* cv2.imread(fpath) alone                                infer.py:81
+ * Decodes one file on the device and returns the BGR image (height x width x 3, EXIF orientation applied).  With
+ * out == NULL only height / width / status are filled in.  *status as for rn_infer_jpeg. */
+int rn_decode_jpeg_u8_bgr(rn_handle* h, const uint8_t* file, uint64_t size, uint8_t* out, uint64_t out_capacity,
+                          int32_t* height, int32_t* width, int32_t* status);
+
+/* Host-only helpers of the JPEG front end (no device needed).  rn_jpeg_info: info = {status, width, height,
+ * components, luma h sampling, luma v sampling, EXIF orientation, number of int16 coefficients}.
+ * rn_jpeg_coefficients: the entropy-decoded, still quantised DCT coefficients, per component [block rows][block
+ * columns][64] in natural order, components back to back (what the device kernels consume); returns the rn_jpeg_status. */
+int rn_jpeg_info(const uint8_t* file, uint64_t size, int64_t info[8]);
+int rn_jpeg_coefficients(const uint8_t* file, uint64_t size, int16_t* coefs, uint64_t capacity);
+
 /* CameraActivity.onImageAvailable -> ImageUtils.convertYUV420ToARGB8888 -> ClassifierActivity.processImage
  *   mobile/.../env/ImageUtils.java:131-151 (+ YUV2RGB :100-129), getTransformationMatrix :168-225,
  *   ClassifierActivity.java:89-106 (frameToCropTransform, canvas.drawBitmap), Classifier.java:226-243

@@ -64,6 +64,11 @@ def _load():
         "rn_preprocess_u8": ([vp, vp, i32, i32, vp], C.c_int),
         "rn_infer_image_u8_bgr": ([vp, vp, i32, i32, vp, vp, vp], C.c_int),
         "rn_infer_images_u8_bgr": ([vp, C.POINTER(vp), C.POINTER(i32), C.POINTER(i32), i32, vp, vp, vp], C.c_int),
+        "rn_infer_jpeg": ([vp, C.POINTER(vp), C.POINTER(C.c_uint64), i32, i32, vp, vp, vp, vp], C.c_int),
+        "rn_decode_jpeg_u8_bgr": ([vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+                                  C.c_int),
+        "rn_jpeg_info": ([vp, C.c_uint64, i64p], C.c_int),
+        "rn_jpeg_coefficients": ([vp, C.c_uint64, vp, C.c_uint64], C.c_int),
         "rn_infer_yuv420": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
         "rn_flat_len": ([vp], C.c_int),
@@ -85,10 +90,33 @@ def _load():
 
 
 lib = _load()
+JPEG_OK, JPEG_UNSUPPORTED, JPEG_CORRUPT = 0, 1, 2
+
+
+def jpeg_info(data):
+    """Host-only: (status, width, height, components, luma h, luma v, EXIF orientation, coefficient count)."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    info = (C.c_int64 * 8)()
+    rc = lib.rn_jpeg_info(buf.ctypes.data, buf.size, info)
+    if rc != RN_OK:
+        raise RoomNetError(rc, "rn_jpeg_info")
+    return tuple(int(v) for v in info)
+
+
+def jpeg_coefficients(data):
+    """Host-only: (status, int16 coefficients or None) - the entropy-decoded, still quantised DCT coefficients."""
+    info = jpeg_info(data)
+    if info[0] != JPEG_OK:
+        return info[0], None
+    buf = np.frombuffer(data, dtype=np.uint8)
+    coefs = np.empty((info[7],), np.int16)
+    st = lib.rn_jpeg_coefficients(buf.ctypes.data, buf.size, coefs.ctypes.data, coefs.size)
+    return st, (coefs if st == JPEG_OK else None)
 EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors", "rn_set_dense0",
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
             "rn_submit_u8_bgr", "rn_wait",
-            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_infer_jpeg",
+            "rn_decode_jpeg_u8_bgr", "rn_jpeg_info", "rn_jpeg_coefficients", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
 
@@ -220,6 +248,36 @@ class Handle:
         self._check(lib.rn_infer_images_u8_bgr(self._h, ptrs, hs, ws, n, top1.ctypes.data, probs.ctypes.data,
                                                logits.ctypes.data))
         return (top1, probs, logits) if want_logits else (top1, probs)
+
+    def infer_jpeg(self, files, threads=0, want_logits=False):
+        """Encoded files (bytes objects): entropy decoding on host threads, the rest of the decoder + crop + resize +
+        forward pass on the device.  Returns (top1, probs[, logits], status); rows whose status is not JPEG_OK are
+        not filled in (decode those files on the host and use infer_images_u8_bgr)."""
+        n = len(files)
+        bufs = [np.frombuffer(f, dtype=np.uint8) for f in files]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_uint64 * n)(*[b.size for b in bufs])
+        top1 = np.full((n,), -1, np.int64)
+        probs = np.zeros((n, self.num_classes), np.float32)
+        logits = np.zeros((n, self.num_classes), np.float32)
+        status = np.full((n,), JPEG_UNSUPPORTED, np.int32)
+        self._check(lib.rn_infer_jpeg(self._h, ptrs, sizes, n, threads, top1.ctypes.data, probs.ctypes.data,
+                                      logits.ctypes.data, status.ctypes.data))
+        return (top1, probs, logits, status) if want_logits else (top1, probs, status)
+
+    def decode_jpeg(self, data):
+        """cv2.imdecode(data, cv2.IMREAD_COLOR) for a baseline JPEG, second half of the decoder on the device.
+        Returns (image or None, status)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        hh, ww, st = C.c_int32(), C.c_int32(), C.c_int32()
+        self._check(lib.rn_decode_jpeg_u8_bgr(self._h, buf.ctypes.data, buf.size, None, 0, C.byref(hh), C.byref(ww),
+                                              C.byref(st)))
+        if st.value != JPEG_OK:
+            return None, st.value
+        out = np.empty((hh.value, ww.value, 3), np.uint8)
+        self._check(lib.rn_decode_jpeg_u8_bgr(self._h, buf.ctypes.data, buf.size, out.ctypes.data, out.nbytes,
+                                              C.byref(hh), C.byref(ww), C.byref(st)))
+        return (out if st.value == JPEG_OK else None), st.value
 
     def infer_yuv420(self, y, u, v, width, height, y_row_stride, uv_row_stride, uv_pixel_stride, rotation=0):
         """One YUV_420_888 camera frame (planes as uint8 arrays) -> (top1, probs, logits, rgb the network saw)."""

@@ -479,6 +479,105 @@ int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32
   });
 }
 
+int rn_infer_jpeg(rn_handle* h, const uint8_t* const* files, const uint64_t* sizes, int32_t n, int32_t threads,
+                  int64_t* top1, float* probs, float* logits, int32_t* status) {
+  return Guarded(h, [&]() -> int {
+    if (!h) return RN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!files || !sizes || !status || n < 0) return Fail(h, RN_ERR_INVALID_ARG, "null argument or negative count");
+    for (int i = 0; i < n; ++i)
+      if (!files[i]) return Fail(h, RN_ERR_INVALID_ARG, "file " + std::to_string(i) + ": null pointer");
+    if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): there is no CPU inference path");
+    if (!h->loaded) return Fail(h, RN_ERR_NOT_LOADED, "weights have not been loaded (rn_load_tf_checkpoint)");
+    if (n == 0) return RN_OK;
+    auto t0 = std::chrono::steady_clock::now();
+    const int g = static_cast<int>(h->replicas.size());
+    const int C = h->shape.num_classes;
+    int hw = static_cast<int>(std::thread::hardware_concurrency());
+    if (hw < 1) hw = 1;
+    const int nt = std::max(1, (threads > 0 ? threads : std::min(hw, 16)) / g);
+    std::vector<size_t> sz(sizes, sizes + n);
+    std::vector<int> begin(g + 1, 0);
+    for (int r = 0; r < g; ++r) begin[r + 1] = begin[r] + n / g + (r < n % g ? 1 : 0);
+    std::vector<cudaError_t> st(g, cudaSuccess);
+    auto run = [&](int r) {
+      const int b = begin[r], m = begin[r + 1] - begin[r];
+      if (m == 0) return;
+      st[r] = h->replicas[r]->InferJpegs(files + b, sz.data() + b, m, nt, top1 ? top1 + b : nullptr,
+                                         probs ? probs + static_cast<size_t>(b) * C : nullptr,
+                                         logits ? logits + static_cast<size_t>(b) * C : nullptr, status + b);
+    };
+    if (g == 1) {
+      run(0);
+    } else {
+      for (int r = 0; r < g; ++r) {
+        h->workers[r]->Wait();
+        h->workers[r]->Submit([&run, r] { run(r); });
+      }
+      for (int r = 0; r < g; ++r) h->workers[r]->Wait();
+    }
+    h->last_launches = 0;
+    for (int r = 0; r < g; ++r) {
+      if (st[r] != cudaSuccess) return Fail(h, RN_ERR_CUDA, h->replicas[r]->error());
+      h->last_launches += h->replicas[r]->last_launches();
+    }
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (h->lat_ms.size() < (1u << 20)) h->lat_ms.push_back(ms);
+    h->calls += 1;
+    h->images += n;
+    return RN_OK;
+  });
+}
+
+int rn_decode_jpeg_u8_bgr(rn_handle* h, const uint8_t* file, uint64_t size, uint8_t* out, uint64_t out_capacity,
+                          int32_t* height, int32_t* width, int32_t* status) {
+  return Guarded(h, [&]() -> int {
+    if (!h) return RN_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> lock(h->mu);
+    if (!file || !height || !width || !status) return Fail(h, RN_ERR_INVALID_ARG, "null argument");
+    if (h->replicas.empty()) return Fail(h, RN_ERR_CUDA, "host-only handle (n_devices = 0): the decoder's second half runs on the device");
+    int hh = 0, ww = 0;
+    cudaError_t e = h->replicas[0]->DecodeJpeg(file, size, out, out_capacity, &hh, &ww, status);
+    if (e != cudaSuccess) return Fail(h, e == cudaErrorInvalidValue ? RN_ERR_INVALID_ARG : RN_ERR_CUDA, h->replicas[0]->error());
+    *height = hh;
+    *width = ww;
+    return RN_OK;
+  });
+}
+
+int rn_jpeg_info(const uint8_t* file, uint64_t size, int64_t info[8]) {
+  if (!file || !info) return RN_ERR_INVALID_ARG;
+  try {
+    rn::JpegInfo f;
+    const int st = rn::JpegParseHeader(file, size, &f);
+    const bool swap = f.orientation >= 5;
+    info[0] = st;
+    info[1] = swap ? f.height : f.width;
+    info[2] = swap ? f.width : f.height;
+    info[3] = f.ncomp;
+    info[4] = f.hmax;
+    info[5] = f.vmax;
+    info[6] = f.orientation;
+    info[7] = static_cast<int64_t>(f.coef_count);
+    return RN_OK;
+  } catch (...) {
+    return RN_ERR_INTERNAL;
+  }
+}
+
+int rn_jpeg_coefficients(const uint8_t* file, uint64_t size, int16_t* coefs, uint64_t capacity) {
+  if (!file || !coefs) return RN_JPEG_CORRUPT;
+  try {
+    rn::JpegInfo f;
+    const int st = rn::JpegParseHeader(file, size, &f);
+    if (st != rn::kJpegOk) return st;
+    if (capacity < f.coef_count) return RN_JPEG_CORRUPT;
+    return rn::JpegDecodeCoefficients(file, size, f, coefs);
+  } catch (...) {
+    return RN_JPEG_CORRUPT;
+  }
+}
+
 int rn_infer_yuv420(rn_handle* h, const uint8_t* y, const uint8_t* u, const uint8_t* v, int32_t y_size, int32_t u_size,
                     int32_t v_size, int32_t width, int32_t height, int32_t y_row_stride, int32_t uv_row_stride,
                     int32_t uv_pixel_stride, int32_t rotation, int64_t* top1, float* probs, float* logits,

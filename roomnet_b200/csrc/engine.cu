@@ -51,6 +51,10 @@ Replica::~Replica() {
   cudaDeviceSynchronize();
   for (void* p : allocs_) cudaFree(p);
   if (d_raw_) cudaFree(d_raw_);
+  if (d_coef_) cudaFree(d_coef_);
+  if (d_samples_) cudaFree(d_samples_);
+  if (d_jmeta_) cudaFree(d_jmeta_);
+  if (h_coef_) cudaFreeHost(h_coef_);
   for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
     if (h_in_[i]) cudaFreeHost(h_in_[i]);

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "fold.h"
+#include "jpeg_host.h"
 #include "kernels.h"
 
 namespace rn {
@@ -43,6 +44,14 @@ class Replica {
                           uint8_t* rgb_out);
   cudaError_t InferImages(const uint8_t* const* imgs, const int* H, const int* W, int n, int64_t* top1, float* probs,
                           float* logits);
+  // n encoded baseline-JPEG files (cv2.imread + infer_optimized of infer.py:81-82): entropy decoding on `threads` host
+  // threads, everything else on the device.  status[i] = JpegStatus; files that are not kJpegOk leave their outputs
+  // untouched (the caller decodes those on the host).
+  cudaError_t InferJpegs(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1, float* probs,
+                         float* logits, int32_t* status);
+  // Decode only: the BGR image as cv2.imread returns it (EXIF orientation applied); out == nullptr queries the size.
+  cudaError_t DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, size_t capacity, int* height, int* width,
+                         int32_t* status);
   // Asynchronous form: SubmitHost enqueues the copies and kernels of one call and returns (it blocks only when every
   // staging slot is still in flight); the results are delivered to the caller's buffers by a later SubmitHost that
   // needs the slot, or by WaitHost(ticket), which returns once every call up to `ticket` has been delivered.
@@ -155,6 +164,16 @@ class Replica {
   bool layerwise_ = false;   // RN_FLAG_LAYERWISE: no fused residual-block kernel
   bool block2_fused_last_ = false;  // the last forward pass ran residual block 2 as one kernel
 
+  // JPEG front end: pinned coefficient staging, device coefficient / sample-plane arenas, descriptors; grown on demand
+  cudaError_t GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images);
+  cudaError_t JpegToRaw(const uint8_t* const* files, const size_t* sizes, const std::vector<int>& index,
+                        const std::vector<JpegInfo>& info, int threads, std::vector<CropDesc>* crops, std::vector<char>* ok,
+                        int32_t* status);
+  int16_t* h_coef_ = nullptr;
+  int16_t* d_coef_ = nullptr;
+  uint8_t* d_samples_ = nullptr;
+  void* d_jmeta_ = nullptr;
+  size_t h_coef_cap_ = 0, d_coef_cap_ = 0, d_samples_cap_ = 0, d_jmeta_cap_ = 0;
   // preprocessing scratch (raw image + tap tables), grown on demand
   uint8_t* d_raw_ = nullptr;
   size_t d_raw_cap_ = 0;

@@ -1,0 +1,48 @@
+// Host half of the JPEG front end (replaces cv2.imread of the reference's classify_im_dir, infer.py:81, for baseline
+// JPEG files): marker parsing and Huffman (entropy) decoding, which are serial bit-stream work, stay on the CPU; what
+// they produce - quantised DCT coefficients - goes to the device, where dequantisation, the inverse DCT, chroma
+// upsampling and the colour conversion run as CUDA kernels (kernels_jpeg.cu) with the integer arithmetic of
+// libjpeg-turbo's default decoder (JDCT_ISLOW, fancy upsampling), i.e. bit-identical to cv2.imread.
+//
+// Supported: 8-bit baseline / extended-sequential Huffman JPEG (SOF0 / SOF1), grey or YCbCr, luma sampling 1x1, 2x1,
+// 2x2 with 1x1 chroma, any number of scans, restart intervals, EXIF orientation.  Everything else (progressive,
+// arithmetic coding, CMYK, 12-bit, exotic sampling, damaged streams) is reported as kJpegUnsupported so that the caller
+// decodes that file on the host instead.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+namespace rn {
+
+enum JpegStatus : int { kJpegOk = 0, kJpegUnsupported = 1, kJpegCorrupt = 2 };
+
+struct JpegComponent {
+  int id = 0;
+  int h = 1, v = 1;    // sampling factors
+  int tq = 0;          // quantisation table
+  int wblocks = 0;     // ceil(downsampled width / 8): blocks that carry image data
+  int hblocks = 0;
+  int dw = 0, dh = 0;  // downsampled width / height in samples (libjpeg: downsampled_width / _height)
+  size_t coef_offset = 0;  // first coefficient of this component in the image's coefficient array (int16 units)
+};
+
+struct JpegInfo {
+  int width = 0, height = 0;
+  int ncomp = 0;
+  int hmax = 1, vmax = 1;
+  int orientation = 1;  // EXIF tag 0x0112 (1..8), 1 when absent
+  int restart_interval = 0;
+  JpegComponent comp[3];
+  uint16_t quant[4][64];  // natural (row-major) order
+  bool have_quant[4] = {false, false, false, false};
+  size_t coef_count = 0;  // int16 coefficients of the whole image (sum over components of wblocks*hblocks*64)
+  size_t sos_offset = 0;  // internal: where the first scan starts
+};
+
+// Header pass: fills `info` (geometry, tables, orientation); no entropy decoding.
+JpegStatus JpegParseHeader(const uint8_t* data, size_t size, JpegInfo* info);
+// Entropy-decodes every scan into `coefs` (info.coef_count int16 values, zero-initialised by this call): per component
+// a [hblocks][wblocks][64] array in natural order, NOT dequantised.
+JpegStatus JpegDecodeCoefficients(const uint8_t* data, size_t size, const JpegInfo& info, int16_t* coefs);
+
+}  // namespace rn

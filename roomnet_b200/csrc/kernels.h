@@ -45,6 +45,30 @@ cudaError_t Yuv420CropU8(const uint8_t* y, const uint8_t* u, const uint8_t* v, c
                          cudaStream_t st);
 cudaError_t CropResizeBatchU8(const uint8_t* arena, const CropDesc* descs, int n, uint8_t* dst, int S, cudaStream_t st);
 
+// ---- JPEG front end, device half (kernels_jpeg.cu; host half: jpeg_host.h) ----
+// One component of one image: quantised coefficients [hblocks][wblocks][64] (natural order) -> sample plane of
+// wblocks*8 x hblocks*8 bytes.
+struct JpegPlaneDesc {
+  unsigned long long coef_offset;   // first coefficient (int16 units) in the coefficient arena
+  unsigned long long plane_offset;  // first byte of the plane in the sample arena (8-byte aligned)
+  int wblocks, hblocks;
+  int quant_index;  // row of the uint16[64] quantisation-table array
+  int pad;
+};
+// One image: its planes, the chroma geometry, and where the oriented BGR image goes in the raw-image arena.
+struct JpegImageDesc {
+  unsigned long long plane[3];
+  unsigned long long out_offset;
+  int pitch[3];
+  int width, height, ncomp;
+  int hs, vs;    // luma sampling factors (1 or 2); chroma is 1x1
+  int cdw, cdh;  // chroma width / height in samples
+  int orientation, out_w;
+};
+cudaError_t JpegIdct(const int16_t* coefs, const JpegPlaneDesc* planes, int n_planes, const uint16_t* quant,
+                     uint8_t* samples, cudaStream_t st);
+cudaError_t JpegColor(const uint8_t* samples, const JpegImageDesc* images, int n_images, uint8_t* raw, cudaStream_t st);
+
 // ---- 16-bit tensor-core path (kernels_tc.cu) --------------------------------
 // Activation layout between tensor-core layers ("chunked rows"):
 //   T[n][y][cb][x][8]  16-bit elements, cb = channel / 8.  One (n, y, cb) plane row

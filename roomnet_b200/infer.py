@@ -32,6 +32,7 @@ INPUT_IMAGES_DIR = './test_images/set2/images'   # reference infer.py:25
 IMG_SIDE = 224                                   # reference infer.py:26
 BATCH = 256
 BATCH_BYTES = 512 << 20           # decoded pixels per device call (bounds host memory on large photos)
+FILE_BATCH_BYTES = 256 << 20      # encoded bytes per device call on the file path (overlay=False)
 IO_THREADS = min(32, os.cpu_count() or 1)
 DECODE_AHEAD = 2 * IO_THREADS     # files being decoded ahead of the device
 MAX_PENDING_WRITES = 64           # overlay / copy writes in flight
@@ -91,6 +92,11 @@ def _read_image(path):
     return image
 
 
+def _read_bytes(path):
+    with open(path, 'rb') as f:
+        return f.read()
+
+
 def _emit(path, image, target_dir, name, label, confidence, overlay):
     """Output side of one file (reference infer.py:86-95)."""
     if overlay:
@@ -133,6 +139,50 @@ def classify_im_dir(nn, imgs_dir, overlay=True):
                 row += 1
             while len(writes) > MAX_PENDING_WRITES:  # bounded: finished images are released as they are written
                 writes.popleft().result()
+
+        if not overlay and hasattr(nn, 'infer_files'):
+            # plain copies do not need the pixels on the host: hand the encoded files to the library, which decodes
+            # baseline JPEGs on the device (bit-identical to cv2.imread) and falls back to cv2 for the rest
+            reading = deque()
+            nxt = 0
+            group, group_bytes = [], 0
+
+            def flush_files(group):
+                nonlocal row
+                if not group:
+                    return
+                top1, probs = nn.infer_files([blob for _, blob in group])
+                for (path, _), cls, prob in zip(group, top1, probs):
+                    label, confidence = CLASS_LABELS[cls], prob[cls]
+                    name = path.split(os.sep)[-1]
+                    print(path, '--->', label, confidence)
+                    writes.append(pool.submit(_emit, path, None, out_dir + os.sep + label, name, label, confidence,
+                                              False))
+                    sheet.write(row, 0, name)
+                    sheet.write(row, 1, label)
+                    sheet.write(row, 2, str(confidence))
+                    row += 1
+                while len(writes) > MAX_PENDING_WRITES:
+                    writes.popleft().result()
+
+            try:
+                while nxt < len(paths) or reading:
+                    while nxt < len(paths) and len(reading) < DECODE_AHEAD:
+                        reading.append((paths[nxt], pool.submit(_read_bytes, paths[nxt])))
+                        nxt += 1
+                    path, fut = reading.popleft()
+                    blob = fut.result()
+                    group.append((path, blob))
+                    group_bytes += len(blob)
+                    if len(group) >= BATCH or group_bytes >= FILE_BATCH_BYTES:
+                        flush_files(group)
+                        group, group_bytes = [], 0
+                flush_files(group)
+            finally:
+                for w in writes:
+                    w.result()
+                workbook.save(xl_fpath)
+            return xl_fpath
 
         # decode a bounded window ahead of the device; a batch is closed at BATCH images or BATCH_BYTES of pixels,
         # whichever comes first (a directory of multi-megapixel photos must not hold hundreds of them in memory)

@@ -129,6 +129,28 @@ class RoomNet:
         batch = np.stack([self.preprocess(im) for im in ims])
         return self.sess.infer_u8_bgr(batch)
 
+    def infer_files(self, blobs, decode_threads=0):
+        """cv2.imread + infer_optimized of reference infer.py:81-82 for a list of files given as their encoded bytes.
+
+        Baseline JPEG files are decoded on the device (entropy decoding on host threads, inverse DCT / upsampling /
+        colour conversion / EXIF orientation as CUDA kernels, bit-identical to cv2.imread), everything else (PNG,
+        progressive JPEG, ...) through cv2.imdecode on the host and the batched photo call.  An undecodable file
+        raises AttributeError like the reference does when cv2.imread returns None (network.py:138)."""
+        self._require()
+        import cv2
+        top1, probs, status = self.sess.infer_jpeg(blobs, threads=decode_threads)
+        rest = [i for i, st in enumerate(status) if st != 0]
+        if rest:
+            ims = [cv2.imdecode(np.frombuffer(blobs[i], dtype=np.uint8), cv2.IMREAD_COLOR) for i in rest]
+            for i, im in zip(rest, ims):
+                if im is None:
+                    raise AttributeError("'NoneType' object has no attribute 'shape' (file %d of the list is not an "
+                                         "image cv2 can read)" % i)
+            t, p = self.infer_optimized_batch(ims)
+            top1[rest] = t
+            probs[rest] = p
+        return top1, probs
+
     def train_step(self, x_in, y):
         raise NotImplementedError("training is out of scope of the inference hot path (reference network.py:158-170)")
 

@@ -60,6 +60,10 @@ class _StubSession:
         probs[np.arange(len(batch)), idx] = 0.9
         return idx, probs
 
+    def infer_jpeg(self, blobs, threads=0, want_logits=False):
+        n = len(blobs)  # a session without the device decoder: every file goes back to cv2 on the host
+        return np.full(n, -1, np.int64), np.zeros((n, 6), np.float32), np.ones(n, np.int32)
+
 
 def test_classify_im_dir_outputs(tmp_path):
     imgs_dir = tmp_path / "images"

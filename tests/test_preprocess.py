@@ -130,3 +130,13 @@ def test_gpu_classify_im_dir_on_real_files(ckpt_prefix, tmp_path):
             assert over is not None and over.shape == decoded[names.index(n)].shape
         import shutil
         shutil.rmtree(out_dir)
+    # overlay=False: the files go to the library as encoded bytes - the JPEGs are decoded on the device, the PNGs by
+    # cv2 on the host - and are copied verbatim; same labels as above
+    nn = RoomNet(num_classes=6, im_side=224, compute_bn_mean_var=False, optimized_inference=True)
+    nn.load(ckpt_prefix)
+    classify_im_dir(nn, str(imgs_dir), overlay=False)
+    nn.close()
+    placed2 = {f: lab for lab in CLASS_LABELS for f in os.listdir(os.path.join(out_dir, lab))}
+    assert placed2 == placed
+    for n in names:
+        assert open(os.path.join(out_dir, placed2[n], n), "rb").read() == open(imgs_dir / n, "rb").read()
