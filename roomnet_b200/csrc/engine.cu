@@ -54,7 +54,8 @@ Replica::~Replica() {
   if (d_coef_) cudaFree(d_coef_);
   if (d_samples_) cudaFree(d_samples_);
   if (d_jmeta_) cudaFree(d_jmeta_);
-  if (h_coef_) cudaFreeHost(h_coef_);
+  for (int16_t* p : h_coef_)
+    if (p) cudaFreeHost(p);
   for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);
   for (int i = 0; i < 2; ++i)
     if (h_in_[i]) cudaFreeHost(h_in_[i]);

@@ -165,15 +165,17 @@ class Replica {
   bool block2_fused_last_ = false;  // the last forward pass ran residual block 2 as one kernel
 
   // JPEG front end: pinned coefficient staging, device coefficient / sample-plane arenas, descriptors; grown on demand
-  cudaError_t GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images);
-  cudaError_t JpegToRaw(const uint8_t* const* files, const size_t* sizes, const std::vector<int>& index,
-                        const std::vector<JpegInfo>& info, int threads, std::vector<CropDesc>* crops, std::vector<char>* ok,
+  struct JpegBatch;
+  cudaError_t GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images, int n_host);
+  void JpegDecodeHost(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int16_t* h_coef, int threads);
+  cudaError_t JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::vector<CropDesc>* crops, std::vector<char>* ok,
                         int32_t* status);
-  int16_t* h_coef_ = nullptr;
+  static constexpr int kJpegRing = 4;
+  int16_t* h_coef_[kJpegRing] = {};  // pinned ring: host threads fill buffers ahead of the one the device reads
   int16_t* d_coef_ = nullptr;
   uint8_t* d_samples_ = nullptr;
   void* d_jmeta_ = nullptr;
-  size_t h_coef_cap_ = 0, d_coef_cap_ = 0, d_samples_cap_ = 0, d_jmeta_cap_ = 0;
+  size_t h_coef_cap_[kJpegRing] = {}, d_coef_cap_ = 0, d_samples_cap_ = 0, d_jmeta_cap_ = 0;
   // preprocessing scratch (raw image + tap tables), grown on demand
   uint8_t* d_raw_ = nullptr;
   size_t d_raw_cap_ = 0;

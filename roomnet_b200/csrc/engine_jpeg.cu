@@ -4,8 +4,13 @@
 // the whole micro-batch -> forward pass.  The decoded photo never exists in host memory.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <thread>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "engine.h"
 #include "jpeg_host.h"
@@ -22,6 +27,10 @@ namespace rn {
   } while (0)
 
 namespace {
+struct NvtxRangeJpeg {
+  explicit NvtxRangeJpeg(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRangeJpeg() { nvtxRangePop(); }
+};
 inline size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // reference network.py:137-146: offset = abs((w - h) // 2) with Python floor division
@@ -39,7 +48,16 @@ CropDesc CentreCrop(int h, int w, size_t offset) {
 }
 }  // namespace
 
-cudaError_t Replica::GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images) {
+// One micro-batch of files on its way through the decoder.
+struct Replica::JpegBatch {
+  std::vector<int> index;      // positions in the caller's list
+  std::vector<JpegInfo> info;
+  std::vector<size_t> coef_off;  // int16 units into the pinned coefficient buffer
+  size_t coef_total = 0;
+  std::vector<int> st;         // JpegStatus per file after entropy decoding
+};
+
+cudaError_t Replica::GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images, int n_host) {
   auto grow = [&](void** p, size_t* cap, size_t need, bool host) -> cudaError_t {
     if (need <= *cap) return cudaSuccess;
     cudaError_t e = cudaStreamSynchronize(compute_);
@@ -52,7 +70,8 @@ cudaError_t Replica::GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, siz
     if (e == cudaSuccess) *cap = want;
     return e;
   };
-  RN_CUDA(grow(reinterpret_cast<void**>(&h_coef_), &h_coef_cap_, coef_bytes, true));
+  for (int b = 0; b < n_host; ++b)
+    RN_CUDA(grow(reinterpret_cast<void**>(&h_coef_[b]), &h_coef_cap_[b], coef_bytes, true));
   RN_CUDA(grow(reinterpret_cast<void**>(&d_coef_), &d_coef_cap_, coef_bytes, false));
   RN_CUDA(grow(reinterpret_cast<void**>(&d_samples_), &d_samples_cap_, sample_bytes, false));
   RN_CUDA(grow(reinterpret_cast<void**>(&d_raw_), &d_raw_cap_, raw_bytes, false));
@@ -61,19 +80,32 @@ cudaError_t Replica::GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, siz
   return cudaSuccess;
 }
 
-// Decodes the listed files into oriented BGR images in d_raw_ (enqueued on compute_, not synchronised).
-// crops[k] / ok[k] describe list entry k; status (optional) receives the per-file JpegStatus at index[k].
-cudaError_t Replica::JpegToRaw(const uint8_t* const* files, const size_t* sizes, const std::vector<int>& index,
-                               const std::vector<JpegInfo>& info, int threads, std::vector<CropDesc>* crops,
+// Host half of a batch: entropy decoding into a pinned buffer; files are independent, a handful of threads share them.
+void Replica::JpegDecodeHost(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int16_t* h_coef, int threads) {
+  const int m = static_cast<int>(b->index.size());
+  b->st.assign(m, kJpegOk);
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (int k = next.fetch_add(1); k < m; k = next.fetch_add(1))
+      b->st[k] = JpegDecodeCoefficients(files[b->index[k]], sizes[b->index[k]], b->info[k], h_coef + b->coef_off[k]);
+  };
+  const int nt = std::max(1, std::min(threads, m));
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+  work();
+  for (auto& t : pool) t.join();
+}
+
+// Device half: coefficients -> oriented BGR images in d_raw_ (enqueued on compute_, not synchronised).
+// crops[k] / ok[k] describe entry k of the batch; status (optional) receives the per-file JpegStatus.
+cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::vector<CropDesc>* crops,
                                std::vector<char>* ok, int32_t* status) {
-  const int m = static_cast<int>(index.size());
-  std::vector<size_t> coef_off(m), raw_off(m);
+  const int m = static_cast<int>(b.index.size());
+  std::vector<size_t> raw_off(m);
   std::vector<size_t> plane_off(static_cast<size_t>(m) * 3, 0);
-  size_t coef_total = 0, sample_total = 0, raw_total = 0;
+  size_t sample_total = 0, raw_total = 0;
   for (int k = 0; k < m; ++k) {
-    const JpegInfo& f = info[k];
-    coef_off[k] = coef_total;
-    coef_total += Align(f.coef_count, 64);
+    const JpegInfo& f = b.info[k];
     for (int c = 0; c < f.ncomp; ++c) {
       plane_off[3 * k + c] = sample_total;
       sample_total += Align(static_cast<size_t>(f.comp[c].wblocks) * f.comp[c].hblocks * 64, 256);
@@ -81,40 +113,21 @@ cudaError_t Replica::JpegToRaw(const uint8_t* const* files, const size_t* sizes,
     raw_off[k] = raw_total;
     raw_total += Align(static_cast<size_t>(f.width) * f.height * 3, 256);
   }
-  cudaError_t e = GrowJpegBuffers(coef_total * sizeof(int16_t), sample_total, raw_total, m);
+  cudaError_t e = GrowJpegBuffers(b.coef_total * sizeof(int16_t), sample_total, raw_total, m, 0);
   if (e != cudaSuccess) return e;
-  // the pinned coefficient buffer is reused from batch to batch: the previous upload must have left it
-  RN_CUDA(cudaStreamSynchronize(compute_));
-
-  // ---- entropy decoding: files are independent, a handful of host threads share them ----
-  std::vector<int> st(m, kJpegOk);
-  {
-    std::atomic<int> next{0};
-    auto work = [&]() {
-      for (int k = next.fetch_add(1); k < m; k = next.fetch_add(1))
-        st[k] = JpegDecodeCoefficients(files[index[k]], sizes[index[k]], info[k], h_coef_ + coef_off[k]);
-    };
-    const int nt = std::max(1, std::min(threads, m));
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-    work();
-    for (auto& t : pool) t.join();
-  }
-
-  // ---- descriptors of what decoded cleanly ----
   std::vector<JpegPlaneDesc> planes;
   std::vector<JpegImageDesc> images;
   std::vector<uint16_t> quant;
   crops->assign(m, CropDesc{});
   ok->assign(m, 0);
   for (int k = 0; k < m; ++k) {
-    if (status) status[index[k]] = st[k];
-    if (st[k] != kJpegOk) continue;
-    const JpegInfo& f = info[k];
+    if (status) status[b.index[k]] = b.st[k];
+    if (b.st[k] != kJpegOk) continue;
+    const JpegInfo& f = b.info[k];
     JpegImageDesc im{};
     for (int c = 0; c < f.ncomp; ++c) {
       JpegPlaneDesc p{};
-      p.coef_offset = coef_off[k] + f.comp[c].coef_offset;
+      p.coef_offset = b.coef_off[k] + f.comp[c].coef_offset;
       p.plane_offset = plane_off[3 * k + c];
       p.wblocks = f.comp[c].wblocks;
       p.hblocks = f.comp[c].hblocks;
@@ -145,14 +158,14 @@ cudaError_t Replica::JpegToRaw(const uint8_t* const* files, const size_t* sizes,
   JpegPlaneDesc* d_planes = reinterpret_cast<JpegPlaneDesc*>(meta);
   JpegImageDesc* d_images = reinterpret_cast<JpegImageDesc*>(meta + static_cast<size_t>(m) * 3 * sizeof(JpegPlaneDesc));
   uint16_t* d_quant = reinterpret_cast<uint16_t*>(meta + static_cast<size_t>(m) * (3 * sizeof(JpegPlaneDesc) + sizeof(JpegImageDesc)));
-  RN_CUDA(cudaMemcpyAsync(d_coef_, h_coef_, coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemcpyAsync(d_coef_, h_coef, b.coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, compute_));
+  // the descriptor vectors are pageable: the runtime stages such copies before the call returns
   RN_CUDA(cudaMemcpyAsync(d_planes, planes.data(), planes.size() * sizeof(JpegPlaneDesc), cudaMemcpyHostToDevice, compute_));
   RN_CUDA(cudaMemcpyAsync(d_images, images.data(), images.size() * sizeof(JpegImageDesc), cudaMemcpyHostToDevice, compute_));
   RN_CUDA(cudaMemcpyAsync(d_quant, quant.data(), quant.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, compute_));
   RN_CUDA(JpegIdct(d_coef_, d_planes, static_cast<int>(planes.size()), d_quant, d_samples_, compute_));
   RN_CUDA(JpegColor(d_samples_, d_images, static_cast<int>(images.size()), d_raw_, compute_));
   last_launches_ += 2;
-  // planes / images / quant are pageable vectors: their copies were staged by the runtime before the calls returned
   return cudaSuccess;
 }
 
@@ -163,24 +176,33 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
     if (ew != cudaSuccess) return ew;
   }
   RN_CUDA(cudaSetDevice(device_));
-  std::vector<JpegInfo> info(1);
-  const JpegStatus hs = JpegParseHeader(file, size, &info[0]);
+  JpegBatch b;
+  b.info.resize(1);
+  b.index.assign(1, 0);
+  const JpegStatus hs = JpegParseHeader(file, size, &b.info[0]);
   *status = hs;
   if (hs != kJpegOk) return cudaSuccess;
-  const bool swap = info[0].orientation >= 5;
-  *height = swap ? info[0].width : info[0].height;
-  *width = swap ? info[0].height : info[0].width;
-  const size_t bytes = static_cast<size_t>(info[0].width) * info[0].height * 3;
+  const JpegInfo& f = b.info[0];
+  const bool swap = f.orientation >= 5;
+  *height = swap ? f.width : f.height;
+  *width = swap ? f.height : f.width;
+  const size_t bytes = static_cast<size_t>(f.width) * f.height * 3;
   if (!out) return cudaSuccess;
   if (capacity < bytes) {
     err_ = "output buffer smaller than height * width * 3";
     return cudaErrorInvalidValue;
   }
+  b.coef_off.assign(1, 0);
+  b.coef_total = Align(f.coef_count, 64);
+  last_launches_ = 0;
+  cudaError_t e = GrowJpegBuffers(b.coef_total * sizeof(int16_t), 0, 0, 1, 1);
+  if (e != cudaSuccess) return e;
+  RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
+  const size_t sz = size;
+  JpegDecodeHost(&file, &sz, &b, h_coef_[0], 1);
   std::vector<CropDesc> crops;
   std::vector<char> ok;
-  last_launches_ = 0;
-  const size_t sz = size;
-  cudaError_t e = JpegToRaw(&file, &sz, std::vector<int>{0}, info, 1, &crops, &ok, status);
+  e = JpegToRaw(b, h_coef_[0], &crops, &ok, status);
   if (e != cudaSuccess) return e;
   if (!ok[0]) return cudaSuccess;
   RN_CUDA(cudaMemcpyAsync(out, d_raw_ + crops[0].offset, bytes, cudaMemcpyDeviceToHost, compute_));
@@ -190,6 +212,7 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
 
 cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1,
                                 float* probs, float* logits, int32_t* status) {
+  NvtxRangeJpeg nvtx_range("rn::InferJpegs (entropy decode on host threads | IDCT + colour + crop + forward on the device)");
   {
     cudaError_t ew = WaitHost(~0ull);  // uses staging slot 0 and activation set 0 on the replica's own stream
     if (ew != cudaSuccess) return ew;
@@ -198,50 +221,122 @@ cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes
   last_launches_ = 0;
   const int S = shape_.im_side, C = shape_.num_classes;
   if (!d_descs_) RN_CUDA(Alloc(&d_descs_, static_cast<size_t>(max_batch_) * sizeof(CropDesc)));
-  // headers first: geometry decides the micro-batches (at most max_batch files and ~1.5 GB of device staging each)
-  std::vector<JpegInfo> all(n);
-  for (int i = 0; i < n; ++i) status[i] = JpegParseHeader(files[i], sizes[i], &all[i]);
-  constexpr size_t kStagingCap = size_t{3} << 29;
-  int i = 0;
-  std::vector<int> index;
-  std::vector<JpegInfo> info;
+  // headers first: geometry decides the micro-batches (at most max_batch files and ~0.4 GB of device staging each)
+  std::vector<JpegBatch> batches;
+  {
+    constexpr size_t kStagingCap = size_t{3} << 27;  // 384 MB: a handful of photographs, so the pipeline fills quickly
+    JpegInfo f;
+    size_t staged = 0;
+    for (int i = 0; i < n; ++i) {
+      status[i] = JpegParseHeader(files[i], sizes[i], &f);
+      if (status[i] != kJpegOk) continue;
+      const size_t need = f.coef_count * 3 + static_cast<size_t>(f.width) * f.height * 3 + 4096;
+      if (batches.empty() || static_cast<int>(batches.back().index.size()) >= max_batch_ ||
+          staged + need > kStagingCap) {
+        batches.emplace_back();
+        staged = 0;
+      }
+      staged += need;
+      JpegBatch& b = batches.back();
+      b.index.push_back(i);
+      b.info.push_back(f);
+      b.coef_off.push_back(b.coef_total);
+      b.coef_total += Align(f.coef_count, 64);
+    }
+  }
+  if (batches.empty()) return cudaSuccess;
+  size_t max_coef = 0;
+  for (const auto& b : batches) max_coef = std::max(max_coef, b.coef_total);
+  const int nb = static_cast<int>(batches.size());
+  {
+    cudaError_t e = GrowJpegBuffers(max_coef * sizeof(int16_t), 0, 0, 0, std::min(nb, kJpegRing));
+    if (e != cudaSuccess) return e;
+  }
+  RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffers
+
+  // Host threads walk the files of ALL batches in order (so small batches do not idle them) and run up to
+  // kJpegRing - 1 batches ahead of the device: batch b is entropy-decoded into pinned buffer b % kJpegRing, which is
+  // free once the device work of batch b - kJpegRing has completed.
+  std::mutex mu;
+  std::condition_variable cv;
+  int released = 0;  // batches whose pinned buffer may be overwritten
+  bool abort = false;
+  std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[nb]);
+  std::vector<std::pair<int, int>> items;
+  for (int b = 0; b < nb; ++b) {
+    done[b].store(0);
+    batches[b].st.assign(batches[b].index.size(), kJpegOk);
+    for (int k = 0; k < static_cast<int>(batches[b].index.size()); ++k) items.emplace_back(b, k);
+  }
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (int i = next.fetch_add(1); i < static_cast<int>(items.size()); i = next.fetch_add(1)) {
+      const int b = items[i].first, k = items[i].second;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return abort || released >= b - (kJpegRing - 1); });
+        if (abort) return;
+      }
+      JpegBatch& bt = batches[b];
+      bt.st[k] = JpegDecodeCoefficients(files[bt.index[k]], sizes[bt.index[k]], bt.info[k], h_coef_[b % kJpegRing] + bt.coef_off[k]);
+      if (done[b].fetch_add(1) + 1 == static_cast<int>(bt.index.size())) {
+        { std::lock_guard<std::mutex> lk(mu); }
+        cv.notify_all();
+      }
+    }
+  };
+  std::vector<std::thread> pool;
+  const int nt = std::max(1, std::min(threads, static_cast<int>(items.size())));
+  for (int t = 0; t < nt; ++t) pool.emplace_back(work);
+  auto stop = [&](cudaError_t e) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      abort = true;
+    }
+    cv.notify_all();
+    for (auto& t : pool) t.join();
+    return e;
+  };
   std::vector<CropDesc> crops, packed;
   std::vector<char> ok;
   std::vector<int> where;
-  while (i < n) {
-    index.clear();
-    info.clear();
-    size_t staged = 0;
-    for (; i < n && static_cast<int>(index.size()) < max_batch_; ++i) {
-      if (status[i] != kJpegOk) continue;
-      const size_t px = static_cast<size_t>(all[i].width) * all[i].height;
-      const size_t need = all[i].coef_count * 2 + all[i].coef_count + px * 3 + 4096;
-      if (!index.empty() && staged + need > kStagingCap) break;
-      staged += need;
-      index.push_back(i);
-      info.push_back(all[i]);
+  for (int b = 0; b < nb; ++b) {
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return done[b].load() == static_cast<int>(batches[b].index.size()); });
     }
-    if (index.empty()) continue;
-    cudaError_t e = JpegToRaw(files, sizes, index, info, threads, &crops, &ok, status);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = JpegToRaw(batches[b], h_coef_[b % kJpegRing], &crops, &ok, status);
+    if (e != cudaSuccess) return stop(e);
     packed.clear();
     where.clear();
-    for (size_t k = 0; k < index.size(); ++k) {
+    for (size_t k = 0; k < batches[b].index.size(); ++k) {
       if (!ok[k]) continue;
       packed.push_back(crops[k]);
-      where.push_back(index[k]);
+      where.push_back(batches[b].index[k]);
     }
     const int m = static_cast<int>(packed.size());
-    if (m == 0) continue;
-    RN_CUDA(cudaMemcpyAsync(d_descs_, packed.data(), m * sizeof(CropDesc), cudaMemcpyHostToDevice, compute_));
-    RN_CUDA(CropResizeBatchU8(d_raw_, static_cast<const CropDesc*>(d_descs_), m, static_cast<uint8_t*>(d_in_[0]), S,
-                              compute_));
-    ++last_launches_;
-    cur_ = &sets_[0];
     const HostOut ho = Out(0);
-    e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, m, ho.top1, ho.probs, ho.logits, compute_);
-    if (e != cudaSuccess) return e;
-    RN_CUDA(cudaStreamSynchronize(compute_));
+    if (m > 0) {
+      if ((e = cudaMemcpyAsync(d_descs_, packed.data(), m * sizeof(CropDesc), cudaMemcpyHostToDevice, compute_)) != cudaSuccess ||
+          (e = CropResizeBatchU8(d_raw_, static_cast<const CropDesc*>(d_descs_), m, static_cast<uint8_t*>(d_in_[0]), S,
+                                 compute_)) != cudaSuccess) {
+        err_ = std::string("InferJpegs: ") + cudaGetErrorString(e);
+        return stop(e);
+      }
+      ++last_launches_;
+      cur_ = &sets_[0];
+      e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, m, ho.top1, ho.probs, ho.logits, compute_);
+      if (e != cudaSuccess) return stop(e);
+    }
+    if ((e = cudaStreamSynchronize(compute_)) != cudaSuccess) {
+      err_ = std::string("InferJpegs: ") + cudaGetErrorString(e);
+      return stop(e);
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      released = b + 1;
+    }
+    cv.notify_all();
     for (int k = 0; k < m; ++k) {  // scatter: files that fell out keep their slots untouched
       const int dst = where[k];
       if (top1) top1[dst] = ho.top1[k];
@@ -249,6 +344,7 @@ cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes
       if (logits) std::memcpy(logits + static_cast<size_t>(dst) * C, ho.logits + static_cast<size_t>(k) * C, C * sizeof(float));
     }
   }
+  for (auto& t : pool) t.join();
   return cudaSuccess;
 }
 

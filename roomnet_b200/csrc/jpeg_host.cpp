@@ -57,7 +57,12 @@ struct Huff {
   int mincode[17];
   int valptr[17];
   uint8_t vals[256];
+  // AC fast path, indexed by the next kFastBits bits: code and value bits together when both fit.
+  // bits 0-7 = bits consumed (0 = take the slow path), 8-14 = zero run to skip (64 = end of block), 15 = nothing to
+  // store (ZRL), 16-31 = the coefficient value (signed)
+  int32_t fast[1 << 11];
 };
+constexpr int kFastBits = 11;
 
 bool BuildHuff(const uint8_t* counts, const uint8_t* symbols, int nsym, Huff* t) {
   std::memset(t->lookup, 0, sizeof(t->lookup));
@@ -78,6 +83,30 @@ bool BuildHuff(const uint8_t* counts, const uint8_t* symbols, int nsym, Huff* t)
   }
   t->maxcode[17] = 0x7fffffff;
   t->defined = true;
+  // fast table (meaningful for AC tables; harmless for DC ones, which do not use it)
+  std::memset(t->fast, 0, sizeof(t->fast));
+  code = 0;
+  k = 0;
+  for (int len = 1; len <= kFastBits; ++len) {
+    for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+      const int rs = symbols[k], r = rs >> 4, sz = rs & 15;
+      if (len + sz > kFastBits) continue;
+      const int free_bits = kFastBits - len - sz;
+      for (int v = 0; v < (1 << sz); ++v) {
+        int32_t e;
+        if (sz == 0) {
+          e = (r == 15) ? ((16 << 8) | (1 << 15) | len) : (r == 0 ? ((64 << 8) | (1 << 15) | len) : 0);
+          if (e == 0) continue;  // run/size with size 0 other than EOB / ZRL: undefined in baseline, slow path rejects it
+        } else {
+          const int val = v < (1 << (sz - 1)) ? v - (1 << sz) + 1 : v;
+          e = static_cast<int32_t>(static_cast<uint32_t>(val) << 16) | (r << 8) | (len + sz);
+        }
+        const int first = ((code << sz) | v) << free_bits;
+        for (int j = 0; j < (1 << free_bits); ++j) t->fast[first + j] = e;
+      }
+    }
+    code <<= 1;
+  }
   return true;
 }
 
@@ -91,7 +120,25 @@ struct BitReader {
   int pad_bits = 0;   // zero bits appended after the data ran out
   bool at_marker = false;
 
-  void Fill() {
+  // Refill.  Common case: the next eight bytes hold no 0xFF, so they go in with one load; whole bytes are counted,
+  // the bits of the partial byte below them are OR-ed in again (identically) by the next refill.
+  inline void Fill() {
+    if (!at_marker && end - p >= 8) {
+      uint64_t raw;
+      std::memcpy(&raw, p, 8);
+      const uint64_t inv = ~raw;  // a 0xFF byte in raw is a zero byte here
+      if (!((inv - 0x0101010101010101ull) & ~inv & 0x8080808080808080ull)) {
+        buf |= __builtin_bswap64(raw) >> cnt;
+        const int adv = (63 - cnt) >> 3;
+        p += adv;
+        cnt += adv * 8;
+        return;
+      }
+    }
+    FillSlow();
+  }
+  void FillSlow() {
+    buf &= cnt ? ~0ull << (64 - cnt) : 0ull;  // drop the partial-byte bits of a fast refill: bytes are re-read below
     while (cnt <= 56) {
       unsigned b = 0;
       if (!at_marker && p < end) {
@@ -161,6 +208,16 @@ bool DecodeBlock(BitReader& br, const Huff& dc, const Huff& ac, int* pred, int16
   out[0] = static_cast<int16_t>(*pred);
   for (int k = 1; k < 64;) {
     if (br.cnt < 32) br.Fill();
+    const int32_t e = ac.fast[br.Peek(kFastBits)];
+    if (e & 0xff) {
+      br.Skip(e & 0xff);
+      k += (e >> 8) & 0x7f;
+      if (e & (1 << 15)) continue;  // ZRL, or end of block (k is now >= 64)
+      if (k > 63) return false;
+      out[kZigzag[k]] = static_cast<int16_t>(e >> 16);
+      ++k;
+      continue;
+    }
     const int rs = DecodeSymbol(br, ac);
     if (rs < 0) return false;
     const int r = rs >> 4;
@@ -413,8 +470,6 @@ JpegStatus JpegDecodeCoefficients(const uint8_t* data, size_t size, const JpegIn
                 int16_t* out = dummy;
                 if (bx < k.wblocks && by < k.hblocks) {
                   out = base + (static_cast<size_t>(by) * k.wblocks + bx) * 64;
-                } else {
-                  std::memset(dummy, 0, sizeof(dummy));
                 }
                 if (!DecodeBlock(br, dc[td[i]], ac[ta[i]], &pred[i], out)) return kJpegCorrupt;
               }
