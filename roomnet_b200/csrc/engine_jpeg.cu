@@ -111,7 +111,11 @@ cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::v
       sample_total += Align(static_cast<size_t>(f.comp[c].wblocks) * f.comp[c].hblocks * 64, 256);
     }
     raw_off[k] = raw_total;
-    raw_total += Align(static_cast<size_t>(f.width) * f.height * 3, 256);
+    {
+      const bool swap = f.orientation >= 5;
+      const size_t ow = swap ? f.height : f.width, oh = swap ? f.width : f.height;
+      raw_total += Align(Align(ow, 4) * oh * 3, 256);
+    }
   }
   cudaError_t e = GrowJpegBuffers(b.coef_total * sizeof(int16_t), sample_total, raw_total, m, 0);
   if (e != cudaSuccess) return e;
@@ -147,10 +151,11 @@ cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::v
     im.orientation = f.orientation;
     const bool swap = f.orientation >= 5;
     const int ow = swap ? f.height : f.width, oh = swap ? f.width : f.height;
-    im.out_w = ow;
+    im.out_pitch = static_cast<int>(Align(ow, 4));
     im.out_offset = raw_off[k];
     images.push_back(im);
     (*crops)[k] = CentreCrop(oh, ow, raw_off[k]);
+    (*crops)[k].W = im.out_pitch;  // the crop kernel only uses it as the row pitch
     (*ok)[k] = 1;
   }
   if (images.empty()) return cudaSuccess;
@@ -205,7 +210,9 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
   e = JpegToRaw(b, h_coef_[0], &crops, &ok, status);
   if (e != cudaSuccess) return e;
   if (!ok[0]) return cudaSuccess;
-  RN_CUDA(cudaMemcpyAsync(out, d_raw_ + crops[0].offset, bytes, cudaMemcpyDeviceToHost, compute_));
+  RN_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(*width) * 3, d_raw_ + crops[0].offset,
+                            static_cast<size_t>(crops[0].W) * 3, static_cast<size_t>(*width) * 3, *height,
+                            cudaMemcpyDeviceToHost, compute_));
   RN_CUDA(cudaStreamSynchronize(compute_));
   return cudaSuccess;
 }

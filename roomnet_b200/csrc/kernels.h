@@ -55,7 +55,8 @@ struct JpegPlaneDesc {
   int quant_index;  // row of the uint16[64] quantisation-table array
   int pad;
 };
-// One image: its planes, the chroma geometry, and where the oriented BGR image goes in the raw-image arena.
+// One image: its planes, the chroma geometry, and where the oriented BGR image goes in the raw-image arena (rows of
+// out_pitch pixels, the arena offset a multiple of 256 bytes).
 struct JpegImageDesc {
   unsigned long long plane[3];
   unsigned long long out_offset;
@@ -63,7 +64,8 @@ struct JpegImageDesc {
   int width, height, ncomp;
   int hs, vs;    // luma sampling factors (1 or 2); chroma is 1x1
   int cdw, cdh;  // chroma width / height in samples
-  int orientation, out_w;
+  int orientation;
+  int out_pitch;  // row pitch of the oriented image in pixels (a multiple of four)
 };
 cudaError_t JpegIdct(const int16_t* coefs, const JpegPlaneDesc* planes, int n_planes, const uint16_t* quant,
                      uint8_t* samples, cudaStream_t st);

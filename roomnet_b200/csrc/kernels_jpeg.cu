@@ -116,26 +116,29 @@ jpeg_idct_kernel(const int16_t* __restrict__ coefs, const JpegPlaneDesc* __restr
 // ---- chroma upsampling + colour conversion + EXIF orientation -> packed BGR ----
 __device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
 
-// triangle filter along a row: 3/4 nearer + 1/4 further sample, the decoder's rounding (1 for even, 2 for odd outputs)
-__device__ __forceinline__ int up_h2v1(const uint8_t* __restrict__ row, int x, int dw) {
-  const int i = x >> 1;
-  const int v = row[i];
-  if (x & 1) return i == dw - 1 ? v : (3 * v + row[i + 1] + 2) >> 2;
-  return i == 0 ? v : (3 * v + row[i - 1] + 1) >> 2;
+// Four neighbouring chroma samples a b c d (columns i-1 .. i+2; a / d clamped at the plane border) -> the four pixels
+// 2i .. 2i+3.  Triangle filter of the decoder: 3/4 nearer + 1/4 further sample, rounding 1 for even and 2 for odd
+// outputs; the first and last column of the plane pass through unfiltered.
+__device__ __forceinline__ void up_h2v1(int a, int b, int c, int d, int i, int dw, int out[4]) {
+  out[0] = i == 0 ? b : (3 * b + a + 1) >> 2;
+  out[1] = i == dw - 1 ? b : (3 * b + c + 2) >> 2;
+  out[2] = (3 * c + b + 1) >> 2;
+  out[3] = i + 1 == dw - 1 ? c : (3 * c + d + 2) >> 2;
 }
-// both directions: 9/16, 3/16, 3/16, 1/16; r0 = nearer row, r1 = further row (replicated at the image border)
-__device__ __forceinline__ int up_h2v2(const uint8_t* __restrict__ r0, const uint8_t* __restrict__ r1, int x, int dw) {
-  const int i = x >> 1;
-  const int cur = 3 * r0[i] + r1[i];
-  if (x & 1) {
-    if (i == dw - 1) return (cur * 4 + 7) >> 4;
-    return (cur * 3 + 3 * r0[i + 1] + r1[i + 1] + 7) >> 4;
-  }
-  if (i == 0) return (cur * 4 + 8) >> 4;
-  return (cur * 3 + 3 * r0[i - 1] + r1[i - 1] + 8) >> 4;
+// Both directions (9/16, 3/16, 3/16, 1/16): a .. d are the column sums 3 * nearer row + further row, rounding 8 / 7.
+__device__ __forceinline__ void up_h2v2(int a, int b, int c, int d, int i, int dw, int out[4]) {
+  out[0] = i == 0 ? (4 * b + 8) >> 4 : (3 * b + a + 8) >> 4;
+  out[1] = i == dw - 1 ? (4 * b + 7) >> 4 : (3 * b + c + 7) >> 4;
+  out[2] = (3 * c + b + 8) >> 4;
+  out[3] = i + 1 == dw - 1 ? (4 * c + 7) >> 4 : (3 * c + d + 7) >> 4;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int kColorThreads = 256;
+constexpr int kColorTile = kColorThreads * 4;  // pixels of one row handled by a block per iteration
+
+// One thread = four neighbouring pixels of a row: one 32-bit load of luma, four (eight for 4:2:0) byte loads per chroma
+// plane, three 32-bit stores (the oriented image has a row pitch that is a multiple of four pixels).
+__global__ void __launch_bounds__(kColorThreads)
 jpeg_color_kernel(const uint8_t* __restrict__ samples, const JpegImageDesc* __restrict__ images, uint8_t* __restrict__ raw) {
   const JpegImageDesc d = images[blockIdx.y];
   const int W = d.width, H = d.height;
@@ -143,49 +146,82 @@ jpeg_color_kernel(const uint8_t* __restrict__ samples, const JpegImageDesc* __re
   const uint8_t* pcb = samples + d.plane[1];
   const uint8_t* pcr = samples + d.plane[2];
   uint8_t* out = raw + d.out_offset;
-  const long long total = static_cast<long long>(W) * H;
-  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int y = static_cast<int>(idx / W), x = static_cast<int>(idx - static_cast<long long>(y) * W);
-    const int Y = py[static_cast<size_t>(y) * d.pitch[0] + x];
-    int r = Y, g = Y, b = Y;
+  const int tiles_per_row = (W + kColorTile - 1) / kColorTile;
+  const int total = H * tiles_per_row;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int y = tile / tiles_per_row;
+    const int x = (tile - y * tiles_per_row) * kColorTile + threadIdx.x * 4;
+    if (x >= W) continue;
+    const unsigned yw = *reinterpret_cast<const unsigned*>(py + static_cast<size_t>(y) * d.pitch[0] + x);
+    int cb[4] = {128, 128, 128, 128}, cr[4] = {128, 128, 128, 128};
     if (d.ncomp == 3) {
-      int cb, cr;
       if (d.hs == 1) {
-        cb = pcb[static_cast<size_t>(y) * d.pitch[1] + x];
-        cr = pcr[static_cast<size_t>(y) * d.pitch[2] + x];
-      } else if (d.vs == 1) {
-        cb = up_h2v1(pcb + static_cast<size_t>(y) * d.pitch[1], x, d.cdw);
-        cr = up_h2v1(pcr + static_cast<size_t>(y) * d.pitch[2], x, d.cdw);
+        const unsigned bw = *reinterpret_cast<const unsigned*>(pcb + static_cast<size_t>(y) * d.pitch[1] + x);
+        const unsigned rw = *reinterpret_cast<const unsigned*>(pcr + static_cast<size_t>(y) * d.pitch[2] + x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          cb[k] = (bw >> (8 * k)) & 255;
+          cr[k] = (rw >> (8 * k)) & 255;
+        }
       } else {
-        const int r0 = y >> 1;
-        const int r1 = (y & 1) ? min(r0 + 1, d.cdh - 1) : max(r0 - 1, 0);
-        cb = up_h2v2(pcb + static_cast<size_t>(r0) * d.pitch[1], pcb + static_cast<size_t>(r1) * d.pitch[1], x, d.cdw);
-        cr = up_h2v2(pcr + static_cast<size_t>(r0) * d.pitch[2], pcr + static_cast<size_t>(r1) * d.pitch[2], x, d.cdw);
+        const int i = x >> 1, dw = d.cdw;
+        const int ia = max(i - 1, 0), ic = min(i + 1, dw - 1), id = min(i + 2, dw - 1);
+        if (d.vs == 1) {
+          const uint8_t* rb = pcb + static_cast<size_t>(y) * d.pitch[1];
+          const uint8_t* rr = pcr + static_cast<size_t>(y) * d.pitch[2];
+          up_h2v1(rb[ia], rb[i], rb[ic], rb[id], i, dw, cb);
+          up_h2v1(rr[ia], rr[i], rr[ic], rr[id], i, dw, cr);
+        } else {
+          // nearer chroma row y / 2, further row above (even y) or below (odd y), replicated at the border
+          const int r0 = y >> 1;
+          const int r1 = (y & 1) ? min(r0 + 1, d.cdh - 1) : max(r0 - 1, 0);
+          const uint8_t* b0 = pcb + static_cast<size_t>(r0) * d.pitch[1];
+          const uint8_t* b1 = pcb + static_cast<size_t>(r1) * d.pitch[1];
+          const uint8_t* q0 = pcr + static_cast<size_t>(r0) * d.pitch[2];
+          const uint8_t* q1 = pcr + static_cast<size_t>(r1) * d.pitch[2];
+          up_h2v2(3 * b0[ia] + b1[ia], 3 * b0[i] + b1[i], 3 * b0[ic] + b1[ic], 3 * b0[id] + b1[id], i, dw, cb);
+          up_h2v2(3 * q0[ia] + q1[ia], 3 * q0[i] + q1[i], 3 * q0[ic] + q1[ic], 3 * q0[id] + q1[id], i, dw, cr);
+        }
       }
-      cb -= 128;
-      cr -= 128;
+    }
+    unsigned char px[12];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int Y = (yw >> (8 * k)) & 255;
+      const int u = cb[k] - 128, v = cr[k] - 128;
       // FIX(1.40200) = 91881, FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554 at 16 fractional bits
-      r = clamp255(Y + ((91881 * cr + 32768) >> 16));
-      b = clamp255(Y + ((116130 * cb + 32768) >> 16));
-      g = clamp255(Y + ((-22554 * cb + 32768 - 46802 * cr) >> 16));
+      px[3 * k + 0] = static_cast<unsigned char>(clamp255(Y + ((116130 * u + 32768) >> 16)));
+      px[3 * k + 1] = static_cast<unsigned char>(clamp255(Y + ((-22554 * u + 32768 - 46802 * v) >> 16)));
+      px[3 * k + 2] = static_cast<unsigned char>(clamp255(Y + ((91881 * v + 32768) >> 16)));
     }
-    // EXIF orientation as cv2.imread applies it (transpose and/or flips of the decoded image)
-    int ox = x, oy = y;
-    switch (d.orientation) {
-      case 2: ox = W - 1 - x; break;
-      case 3: ox = W - 1 - x; oy = H - 1 - y; break;
-      case 4: oy = H - 1 - y; break;
-      case 5: ox = y; oy = x; break;
-      case 6: ox = H - 1 - y; oy = x; break;
-      case 7: ox = H - 1 - y; oy = W - 1 - x; break;
-      case 8: ox = y; oy = W - 1 - x; break;
-      default: break;
+    if (d.orientation == 1 && x + 4 <= W) {
+      unsigned* o = reinterpret_cast<unsigned*>(out + (static_cast<size_t>(y) * d.out_pitch + x) * 3);
+      o[0] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+      o[1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+      o[2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+      continue;
     }
-    uint8_t* o = out + (static_cast<size_t>(oy) * d.out_w + ox) * 3;
-    o[0] = static_cast<uint8_t>(b);
-    o[1] = static_cast<uint8_t>(g);
-    o[2] = static_cast<uint8_t>(r);
+    // row tail, or an EXIF orientation as cv2.imread applies it (transpose and / or flips of the decoded image)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = x + k;
+      if (xx >= W) break;
+      int ox = xx, oy = y;
+      switch (d.orientation) {
+        case 2: ox = W - 1 - xx; break;
+        case 3: ox = W - 1 - xx; oy = H - 1 - y; break;
+        case 4: oy = H - 1 - y; break;
+        case 5: ox = y; oy = xx; break;
+        case 6: ox = H - 1 - y; oy = xx; break;
+        case 7: ox = H - 1 - y; oy = W - 1 - xx; break;
+        case 8: ox = y; oy = W - 1 - xx; break;
+        default: break;
+      }
+      uint8_t* o = out + (static_cast<size_t>(oy) * d.out_pitch + ox) * 3;
+      o[0] = px[3 * k + 0];
+      o[1] = px[3 * k + 1];
+      o[2] = px[3 * k + 2];
+    }
   }
 }
 
@@ -203,7 +239,7 @@ cudaError_t JpegIdct(const int16_t* coefs, const JpegPlaneDesc* planes, int n_pl
 cudaError_t JpegColor(const uint8_t* samples, const JpegImageDesc* images, int n_images, uint8_t* raw, cudaStream_t st) {
   if (n_images <= 0) return cudaSuccess;
   dim3 grid(148 * 8 / (n_images < 8 ? n_images : 8) + 1, n_images);
-  jpeg_color_kernel<<<grid, 256, 0, st>>>(samples, images, raw);
+  jpeg_color_kernel<<<grid, kColorThreads, 0, st>>>(samples, images, raw);
   return cudaGetLastError();
 }
 

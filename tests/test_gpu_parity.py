@@ -241,6 +241,12 @@ def test_replicas_on_two_gpus_are_bit_identical(capi, ckpt_prefix, suite64):
     a = one.infer_images_u8_bgr(photos, want_logits=True)
     b = two.infer_images_u8_bgr(photos, want_logits=True)
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[0], b[0])
+    # ... and so does the file call (JPEG decode on each replica's device)
+    import cv2
+    files = [cv2.imencode(".jpg", p, [cv2.IMWRITE_JPEG_QUALITY, 85])[1].tobytes() for p in photos]
+    fa = one.infer_jpeg(files, want_logits=True)
+    fb = two.infer_jpeg(files, want_logits=True)
+    assert (fa[3] == 0).all() and (fb[3] == 0).all() and np.array_equal(fa[2], fb[2])
 
 
 def test_drop_in_roomnet_class(ckpt_prefix, suite64, golden):

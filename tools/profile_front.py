@@ -1,4 +1,5 @@
-"""Runs the front-end kernels once each (for ncu): per-image crop+resize, batched crop+resize, YUV camera front end,
+"""Runs the front-end kernels once each (for ncu): per-image crop+resize, batched crop+resize, JPEG decode (inverse DCT,
+upsampling + colour), YUV camera front end,
 ARGB feed, 300x300 and 600x600 forward passes (their tails use the unfused fp32 kernels)."""
 import os
 import sys
@@ -21,6 +22,10 @@ W, H = 640, 480
 y = rng.integers(0, 256, W * H, dtype=np.uint8)
 uv = rng.integers(0, 256, W * (H // 2) + 1, dtype=np.uint8)
 print("yuv", h.infer_yuv420(y, uv[1:], uv[:-1], W, H, W, W, 2, 90)[0].tolist())
+import cv2  # noqa: E402
+jpegs = [cv2.imencode(".jpg", cv2.resize(p, None, fx=3, fy=3, interpolation=cv2.INTER_CUBIC),
+                      [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes() for p in photos[:8]]
+print("jpeg", h.infer_jpeg(jpegs)[0].tolist())
 print("argb", h.infer_argb8888(rng.integers(0, 2 ** 31, (2, 224, 224), dtype=np.int64).astype(np.int32))[0].tolist())
 h.close()
 for side in (300, 600):
