@@ -54,7 +54,8 @@ enum rn_flags {
    * the fused residual-block kernel.  Same arithmetic; exists so that rn_debug_activation can return the
    * intermediate tensors of a fused block (tf.Session.run can fetch any graph node, network.py:131) and for A/B
    * timing.  Not the benchmarked configuration. */
-  RN_FLAG_LAYERWISE = 1
+  RN_FLAG_LAYERWISE = 1,
+  RN_FLAG_JPEG_HOST_HUFFMAN = 2  /* rn_infer_jpeg: Huffman decoding on host threads for every file (default: on the device) */
 };
 
 /* Replaces the constructor arguments of the reference model object:
@@ -159,9 +160,11 @@ int rn_infer_images_u8_bgr(rn_handle* h, const uint8_t* const* imgs, const int32
 
 /* cv2.imread(fpath) + RoomNet.infer_optimized(im)       infer.py:81-82
  * n files as they sit on disk (files[i] = sizes[i] encoded bytes).  For baseline JPEG files (8-bit, Huffman, grey or
- * YCbCr with 4:4:4 / 4:2:2 / 4:2:0 sampling, any EXIF orientation) only the entropy decoding runs on the host (on
- * `threads` threads, 0 = as many as the machine has, at most 16); dequantisation, inverse DCT, chroma upsampling,
- * colour conversion and EXIF orientation run on the device with the integer arithmetic of the decoder cv2 links
+ * YCbCr with 4:4:4 / 4:2:2 / 4:2:0 sampling, any EXIF orientation) the whole decoder runs on the device: the host only
+ * strips the byte stuffing while it gathers the files (on `threads` threads, 0 = as many as the machine has, at most
+ * 16); Huffman decoding (self-synchronising parallel decode; files with several scans fall back to host threads),
+ * dequantisation, inverse DCT, chroma upsampling, colour conversion and EXIF orientation are CUDA kernels with the
+ * integer arithmetic of the decoder cv2 links
  * (libjpeg-turbo defaults), so the decoded image - and everything after it - is bit-identical to cv2.imread's, and the
  * decoded photo never exists in host memory.  status[i] (required) receives RN_JPEG_OK, RN_JPEG_UNSUPPORTED
  * (progressive, arithmetic, CMYK, 12-bit, other samplings, not a JPEG at all) or RN_JPEG_CORRUPT (damaged or truncated
@@ -181,6 +184,9 @@ int rn_decode_jpeg_u8_bgr(rn_handle* h, const uint8_t* file, uint64_t size, uint
  * components, luma h sampling, luma v sampling, EXIF orientation, number of int16 coefficients}.
  * rn_jpeg_coefficients: the entropy-decoded, still quantised DCT coefficients, per component [block rows][block
  * columns][64] in natural order, components back to back (what the device kernels consume); returns the rn_jpeg_status. */
+/* How many files of rn_infer_jpeg / rn_decode_jpeg_u8_bgr had their Huffman decoding done on the device, and how many
+ * on host threads (several scans, damaged streams, RN_FLAG_JPEG_HOST_HUFFMAN), since the handle was created. */
+int rn_get_jpeg_counters(rn_handle* h, int64_t* device_huffman_files, int64_t* host_huffman_files);
 int rn_jpeg_info(const uint8_t* file, uint64_t size, int64_t info[8]);
 int rn_jpeg_coefficients(const uint8_t* file, uint64_t size, int16_t* coefs, uint64_t capacity);
 

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libroomnet.so")
 
 RN_ABI_VERSION = 2
 RN_FLAG_LAYERWISE = 1
+RN_FLAG_JPEG_HOST_HUFFMAN = 2
 RN_MAX_DEVICES = 16
 
 RN_OK, RN_ERR_INVALID_ARG, RN_ERR_IO, RN_ERR_FORMAT, RN_ERR_NOT_LOADED, RN_ERR_CUDA, RN_ERR_INTERNAL = range(7)
@@ -68,6 +69,7 @@ def _load():
         "rn_decode_jpeg_u8_bgr": ([vp, vp, C.c_uint64, vp, C.c_uint64, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
                                   C.c_int),
         "rn_jpeg_info": ([vp, C.c_uint64, i64p], C.c_int),
+        "rn_get_jpeg_counters": ([vp, i64p, i64p], C.c_int),
         "rn_jpeg_coefficients": ([vp, C.c_uint64, vp, C.c_uint64], C.c_int),
         "rn_infer_yuv420": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
@@ -116,7 +118,7 @@ EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
             "rn_submit_u8_bgr", "rn_wait",
             "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_infer_jpeg",
-            "rn_decode_jpeg_u8_bgr", "rn_jpeg_info", "rn_jpeg_coefficients", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_decode_jpeg_u8_bgr", "rn_get_jpeg_counters", "rn_jpeg_info", "rn_jpeg_coefficients", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
 
@@ -124,7 +126,8 @@ EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors
 class Handle:
     """Thin RAII wrapper over rn_handle."""
 
-    def __init__(self, im_side=224, num_classes=6, precision="fp16", devices=(0,), max_batch=0, layerwise=False):
+    def __init__(self, im_side=224, num_classes=6, precision="fp16", devices=(0,), max_batch=0, layerwise=False,
+                 jpeg_host_huffman=False):
         cfg = RnConfig()
         cfg.abi_version = RN_ABI_VERSION
         cfg.im_side = im_side
@@ -135,7 +138,7 @@ class Handle:
         for i, d in enumerate(devices):
             cfg.devices[i] = d
         cfg.max_batch = max_batch
-        cfg.flags = RN_FLAG_LAYERWISE if layerwise else 0
+        cfg.flags = (RN_FLAG_LAYERWISE if layerwise else 0) | (RN_FLAG_JPEG_HOST_HUFFMAN if jpeg_host_huffman else 0)
         self.im_side, self.num_classes = im_side, num_classes
         self._h = C.c_void_p()
         rc = lib.rn_create(C.byref(cfg), C.byref(self._h))
@@ -264,6 +267,12 @@ class Handle:
         self._check(lib.rn_infer_jpeg(self._h, ptrs, sizes, n, threads, top1.ctypes.data, probs.ctypes.data,
                                       logits.ctypes.data, status.ctypes.data))
         return (top1, probs, logits, status) if want_logits else (top1, probs, status)
+
+    def jpeg_counters(self):
+        """(files Huffman-decoded on the device, files Huffman-decoded on host threads) so far."""
+        d, c = C.c_int64(), C.c_int64()
+        self._check(lib.rn_get_jpeg_counters(self._h, C.byref(d), C.byref(c)))
+        return d.value, c.value
 
     def decode_jpeg(self, data):
         """cv2.imdecode(data, cv2.IMREAD_COLOR) for a baseline JPEG, second half of the decoder on the device.

@@ -281,7 +281,7 @@ static int CreateImpl(const rn_config* cfg, rn_handle** out) {
     g_create_error = "max_batch out of range (<= 4096 images resident per replica; larger calls are micro-batched anyway)";
     return RN_ERR_INVALID_ARG;
   }
-  if (cfg->flags & ~RN_FLAG_LAYERWISE) {
+  if (cfg->flags & ~(RN_FLAG_LAYERWISE | RN_FLAG_JPEG_HOST_HUFFMAN)) {
     g_create_error = "unknown bits in rn_config.flags";
     return RN_ERR_INVALID_ARG;
   }
@@ -701,6 +701,21 @@ int rn_get_stats(rn_handle* h, double* p50_ms, double* p99_ms, int64_t* calls, i
   if (p99_ms) *p99_ms = pct(0.99);
   if (calls) *calls = h->calls;
   if (images) *images = h->images;
+  return RN_OK;
+}
+
+int rn_get_jpeg_counters(rn_handle* h, int64_t* device_huffman_files, int64_t* host_huffman_files) {
+  if (!h) return RN_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lock(h->mu);
+  long long d = 0, c = 0;
+  for (auto& r : h->replicas) {
+    long long rd = 0, rc = 0;
+    r->jpeg_counters(&rd, &rc);
+    d += rd;
+    c += rc;
+  }
+  if (device_huffman_files) *device_huffman_files = d;
+  if (host_huffman_files) *host_huffman_files = c;
   return RN_OK;
 }
 

@@ -37,6 +37,7 @@ size_t InputBytesPerImage(const NetShape& s, InputKind k) {
 Replica::Replica(int device, const NetShape& shape, int precision, int max_batch, int flags)
     : device_(device), precision_(precision), max_batch_(max_batch), shape_(shape) {
   layerwise_ = (flags & RN_FLAG_LAYERWISE) != 0;
+  flags_ = flags;
   half_kind_ = (precision == RN_PREC_BF16 || precision == RN_PREC_BF16X3) ? HalfKind::kBF16 : HalfKind::kF16;
   // RN_PREC_FP32_TC: conv0..conv7 as three-product split-fp16 tensor-core layers (hi + lo activations, [Wh | Wl]
   // weights, fp32 epilogues); the small tail (conv8, conv9, dense head) is fp32 as on the 16-bit path
@@ -54,6 +55,8 @@ Replica::~Replica() {
   if (d_coef_) cudaFree(d_coef_);
   if (d_samples_) cudaFree(d_samples_);
   if (d_jmeta_) cudaFree(d_jmeta_);
+  if (d_huff_) cudaFree(d_huff_);
+  if (h_huff_flags_) cudaFreeHost(h_huff_flags_);
   for (int16_t* p : h_coef_)
     if (p) cudaFreeHost(p);
   for (cudaEvent_t e : prof_events_) cudaEventDestroy(e);

@@ -68,6 +68,11 @@ class Replica {
   // infer_optimized for one arbitrary-size BGR image entirely on the device (Preprocess + forward).
   cudaError_t InferImage(const uint8_t* h_img, int H, int W, int64_t* top1, float* probs, float* logits);
   int last_launches() const { return last_launches_; }
+  // files whose Huffman decoding ran on the device / on host threads so far
+  void jpeg_counters(long long* device_files, long long* host_files) const {
+    *device_files = jpeg_device_huffman_files_;
+    *host_files = jpeg_host_huffman_files_;
+  }
   // Per-kernel device timing (CUDA events on the launching stream, recorded between launches).
   void set_profiling(bool on) { profiling_ = on; }
   struct KernelTime {
@@ -166,6 +171,18 @@ class Replica {
 
   // JPEG front end: pinned coefficient staging, device coefficient / sample-plane arenas, descriptors; grown on demand
   struct JpegBatch;
+  cudaError_t InferJpegsHostHuffman(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1,
+                                    float* probs, float* logits, int32_t* status);
+  cudaError_t JpegHuffmanOnDevice(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
+                                  std::vector<int>* err);
+  void JpegHuffmanErrors(std::vector<int>* err) const;
+  uint8_t* d_huff_ = nullptr;  // device arena of the Huffman stage (streams, per-subsequence state, descriptors)
+  size_t d_huff_cap_ = 0;
+  int* h_huff_flags_ = nullptr;  // pinned: [0] convergence flag, [16 ..] per-file error flags
+  std::vector<int> huff_file_of_;
+  int jpeg_huffman_rounds_ = 0;
+  long long jpeg_device_huffman_files_ = 0, jpeg_host_huffman_files_ = 0;
+  int flags_ = 0;
   cudaError_t GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images, int n_host);
   void JpegDecodeHost(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int16_t* h_coef, int threads);
   cudaError_t JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::vector<CropDesc>* crops, std::vector<char>* ok,

@@ -14,6 +14,7 @@
 
 #include "engine.h"
 #include "jpeg_host.h"
+#include "roomnet.h"
 
 namespace rn {
 
@@ -163,7 +164,8 @@ cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::v
   JpegPlaneDesc* d_planes = reinterpret_cast<JpegPlaneDesc*>(meta);
   JpegImageDesc* d_images = reinterpret_cast<JpegImageDesc*>(meta + static_cast<size_t>(m) * 3 * sizeof(JpegPlaneDesc));
   uint16_t* d_quant = reinterpret_cast<uint16_t*>(meta + static_cast<size_t>(m) * (3 * sizeof(JpegPlaneDesc) + sizeof(JpegImageDesc)));
-  RN_CUDA(cudaMemcpyAsync(d_coef_, h_coef, b.coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, compute_));
+  if (h_coef)  // (device Huffman decoding: the coefficients are already in d_coef_)
+    RN_CUDA(cudaMemcpyAsync(d_coef_, h_coef, b.coef_total * sizeof(int16_t), cudaMemcpyHostToDevice, compute_));
   // the descriptor vectors are pageable: the runtime stages such copies before the call returns
   RN_CUDA(cudaMemcpyAsync(d_planes, planes.data(), planes.size() * sizeof(JpegPlaneDesc), cudaMemcpyHostToDevice, compute_));
   RN_CUDA(cudaMemcpyAsync(d_images, images.data(), images.size() * sizeof(JpegImageDesc), cudaMemcpyHostToDevice, compute_));
@@ -172,6 +174,166 @@ cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::v
   RN_CUDA(JpegColor(d_samples_, d_images, static_cast<int>(images.size()), d_raw_, compute_));
   last_launches_ += 2;
   return cudaSuccess;
+}
+
+// Device-Huffman stage of one batch: host threads strip the byte stuffing of each file's scan into a pinned buffer,
+// the device decodes the streams into d_coef_ (enqueued on compute_).  b->st[k] = kJpegOk for the files handed to the
+// device, anything else = leave that file to the host decoder.  (*err)[k] becomes valid after the stream has been
+// synchronised: non-zero = the device found the stream damaged.
+cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
+                                         std::vector<int>* err) {
+  const int m = static_cast<int>(b->index.size());
+  b->st.assign(m, kJpegUnsupported);
+  err->assign(m, 0);
+  // ---- layout of the pinned staging buffer: [streams | sub_seg] ----
+  std::vector<size_t> stream_off(m);
+  size_t stream_total = 0;
+  for (int k = 0; k < m; ++k) {
+    stream_off[k] = stream_total;
+    stream_total += JpegStreamCapacity(b->info[k], sizes[b->index[k]]);
+  }
+  stream_total += kSubseqBytes;  // look-ahead slack behind the last stream
+  const size_t n_sub_total = stream_total / kSubseqBytes;
+  const size_t stage_bytes = stream_total + n_sub_total * sizeof(int32_t);
+  {
+    cudaError_t e = GrowJpegBuffers((stage_bytes + 1) / 2 * 2, 0, 0, 0, 1);  // h_coef_[0] doubles as the staging buffer
+    if (e != cudaSuccess) return e;
+  }
+  RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
+  uint8_t* h_stream = reinterpret_cast<uint8_t*>(h_coef_[0]);
+  int32_t* h_sub_seg = reinterpret_cast<int32_t*>(h_stream + stream_total);
+  std::vector<JpegScanPlan> plans(m);
+  {
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int k = next.fetch_add(1); k < m; k = next.fetch_add(1)) {
+        const size_t cap = (k + 1 < m ? stream_off[k + 1] : stream_total - kSubseqBytes) - stream_off[k];
+        b->st[k] = JpegPrepareScan(files[b->index[k]], sizes[b->index[k]], b->info[k], &plans[k], h_stream + stream_off[k],
+                                   cap, h_sub_seg + stream_off[k] / kSubseqBytes);
+      }
+    };
+    const int nt = std::max(1, std::min(threads, m));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+  }
+  // ---- descriptors ----
+  std::vector<HuffFileDesc> fds;
+  std::vector<HuffBlockDesc> bds;
+  std::vector<DevHuffTable> tabs;
+  std::vector<int> file_of;  // batch entry of each descriptor
+  size_t dc_total = 0;
+  for (int k = 0; k < m; ++k) {
+    if (b->st[k] != kJpegOk) continue;
+    const JpegInfo& f = b->info[k];
+    const JpegScanPlan& p = plans[k];
+    HuffFileDesc d{};
+    d.stream_off = stream_off[k];
+    d.sub_base = static_cast<unsigned>(stream_off[k] / kSubseqBytes);
+    d.n_sub = static_cast<unsigned>(p.stream_bytes / kSubseqBytes);
+    d.total_blocks = p.total_blocks;
+    d.seg_blocks = p.seg_blocks;
+    d.bpm = p.bpm;
+    d.mcus_x = p.mcus_x;
+    d.ncomp = f.ncomp;
+    d.table_index = static_cast<int>(tabs.size());
+    d.dc_off = dc_total;
+    dc_total += Align(p.total_blocks, 64);
+    for (int c = 0; c < f.ncomp; ++c) {
+      d.coef_off[c] = b->coef_off[k] + f.comp[c].coef_offset;
+      d.wblocks[c] = f.comp[c].wblocks;
+      d.hblocks[c] = f.comp[c].hblocks;
+      d.comp_h[c] = f.comp[c].h;
+      d.comp_v[c] = f.comp[c].v;
+    }
+    std::memcpy(d.blk_comp, p.blk_comp, 8);
+    std::memcpy(d.blk_hh, p.blk_hh, 8);
+    std::memcpy(d.blk_vv, p.blk_vv, 8);
+    tabs.insert(tabs.end(), p.tab, p.tab + 6);
+    for (unsigned s0 = 0; s0 < d.n_sub; s0 += 256) bds.push_back(HuffBlockDesc{static_cast<int>(fds.size()), s0});
+    fds.push_back(d);
+    file_of.push_back(k);
+  }
+  if (fds.empty()) return cudaSuccess;
+  const int nf = static_cast<int>(fds.size()), nb = static_cast<int>(bds.size());
+  // ---- device arenas ----
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += Align(bytes, 256);
+    return o;
+  };
+  const size_t o_stream = take(stage_bytes);
+  const size_t o_state = take(n_sub_total * 8), o_used = take(n_sub_total * 8), o_nblk = take(n_sub_total * 4),
+               o_loc = take(n_sub_total * 4);
+  const size_t o_bsum = take(nb * 4), o_bflag = take(nb * 4), o_carry = take(nb * 4), o_bds = take(nb * sizeof(HuffBlockDesc));
+  const size_t o_fds = take(nf * sizeof(HuffFileDesc)), o_tabs = take(tabs.size() * sizeof(DevHuffTable));
+  const size_t o_dc = take(dc_total * 2), o_err = take(nf * 4 + 8);
+  {
+    auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
+      if (need <= *cap) return cudaSuccess;
+      cudaError_t e = cudaStreamSynchronize(compute_);
+      if (e != cudaSuccess) return e;
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+      *cap = 0;
+      e = cudaMalloc(p, need + need / 4);
+      if (e == cudaSuccess) *cap = need + need / 4;
+      return e;
+    };
+    RN_CUDA(grow(reinterpret_cast<void**>(&d_huff_), &d_huff_cap_, off));
+    RN_CUDA(GrowJpegBuffers(b->coef_total * sizeof(int16_t), 0, 0, 0, 0));
+    if (!h_huff_flags_) RN_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_huff_flags_), 64 + max_batch_ * sizeof(int)));
+  }
+  uint8_t* base = d_huff_;
+  RN_CUDA(cudaMemcpyAsync(base + o_stream, h_stream, stage_bytes, cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemcpyAsync(base + o_bds, bds.data(), nb * sizeof(HuffBlockDesc), cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemcpyAsync(base + o_fds, fds.data(), nf * sizeof(HuffFileDesc), cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemcpyAsync(base + o_tabs, tabs.data(), tabs.size() * sizeof(DevHuffTable), cudaMemcpyHostToDevice, compute_));
+  RN_CUDA(cudaMemsetAsync(base + o_err, 0, nf * 4 + 8, compute_));
+  RN_CUDA(cudaMemsetAsync(d_coef_, 0, b->coef_total * sizeof(int16_t), compute_));
+  HuffBatch hb{};
+  hb.files = reinterpret_cast<const HuffFileDesc*>(base + o_fds);
+  hb.blocks = reinterpret_cast<const HuffBlockDesc*>(base + o_bds);
+  hb.tables = reinterpret_cast<const DevHuffTable*>(base + o_tabs);
+  hb.streams = base + o_stream;
+  hb.sub_seg = reinterpret_cast<const int*>(base + o_stream + stream_total);
+  hb.state = reinterpret_cast<unsigned long long*>(base + o_state);
+  hb.start_used = reinterpret_cast<unsigned long long*>(base + o_used);
+  hb.nblk = reinterpret_cast<unsigned*>(base + o_nblk);
+  hb.local_off = reinterpret_cast<unsigned*>(base + o_loc);
+  hb.block_sum = reinterpret_cast<unsigned*>(base + o_bsum);
+  hb.block_has_start = reinterpret_cast<int*>(base + o_bflag);
+  hb.carry = reinterpret_cast<unsigned*>(base + o_carry);
+  hb.coefs = d_coef_;
+  hb.dcdiff = reinterpret_cast<int16_t*>(base + o_dc);
+  hb.file_error = reinterpret_cast<int*>(base + o_err);
+  hb.changed = reinterpret_cast<int*>(base + o_err) + nf;
+  hb.h_changed = h_huff_flags_;
+  hb.n_files = nf;
+  hb.n_blocks = nb;
+  hb.rounds_out = &jpeg_huffman_rounds_;
+  {
+    cudaError_t e = HuffDecode(hb, compute_);
+    if (e != cudaSuccess) {
+      err_ = std::string("device Huffman decode: ") + cudaGetErrorString(e);
+      return e;
+    }
+  }
+  last_launches_ += 4 + jpeg_huffman_rounds_ + 1;
+  // error flags travel back with the rest of the batch (valid after the caller's stream synchronisation)
+  RN_CUDA(cudaMemcpyAsync(h_huff_flags_ + 16, base + o_err, nf * sizeof(int), cudaMemcpyDeviceToHost, compute_));
+  huff_file_of_ = file_of;
+  h_huff_flags_[1] = 0;
+  (void)err;
+  return cudaSuccess;
+}
+
+// after the stream has been synchronised: which batch entries did the device report as damaged
+void Replica::JpegHuffmanErrors(std::vector<int>* err) const {
+  for (size_t j = 0; j < huff_file_of_.size(); ++j)
+    if (h_huff_flags_[16 + j]) (*err)[huff_file_of_[j]] = 1;
 }
 
 cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, size_t capacity, int* height, int* width,
@@ -200,15 +362,33 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
   b.coef_off.assign(1, 0);
   b.coef_total = Align(f.coef_count, 64);
   last_launches_ = 0;
-  cudaError_t e = GrowJpegBuffers(b.coef_total * sizeof(int16_t), 0, 0, 1, 1);
-  if (e != cudaSuccess) return e;
-  RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
-  const size_t sz = size;
-  JpegDecodeHost(&file, &sz, &b, h_coef_[0], 1);
   std::vector<CropDesc> crops;
   std::vector<char> ok;
-  e = JpegToRaw(b, h_coef_[0], &crops, &ok, status);
-  if (e != cudaSuccess) return e;
+  const size_t sz = size;
+  cudaError_t e = cudaSuccess;
+  bool on_device = false;
+  if (!(flags_ & RN_FLAG_JPEG_HOST_HUFFMAN)) {
+    std::vector<int> err;
+    e = JpegHuffmanOnDevice(&file, &sz, &b, 1, &err);
+    if (e != cudaSuccess) return e;
+    if (b.st[0] == kJpegOk) {
+      e = JpegToRaw(b, nullptr, &crops, &ok, status);
+      if (e != cudaSuccess) return e;
+      RN_CUDA(cudaStreamSynchronize(compute_));
+      JpegHuffmanErrors(&err);
+      on_device = err[0] == 0;
+      if (on_device) ++jpeg_device_huffman_files_;
+    }
+  }
+  if (!on_device) {
+    e = GrowJpegBuffers(b.coef_total * sizeof(int16_t), 0, 0, 1, 1);
+    if (e != cudaSuccess) return e;
+    RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
+    JpegDecodeHost(&file, &sz, &b, h_coef_[0], 1);
+    e = JpegToRaw(b, h_coef_[0], &crops, &ok, status);
+    if (e != cudaSuccess) return e;
+    ++jpeg_host_huffman_files_;
+  }
   if (!ok[0]) return cudaSuccess;
   RN_CUDA(cudaMemcpy2DAsync(out, static_cast<size_t>(*width) * 3, d_raw_ + crops[0].offset,
                             static_cast<size_t>(crops[0].W) * 3, static_cast<size_t>(*width) * 3, *height,
@@ -217,15 +397,9 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
   return cudaSuccess;
 }
 
-cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1,
-                                float* probs, float* logits, int32_t* status) {
+cudaError_t Replica::InferJpegsHostHuffman(const uint8_t* const* files, const size_t* sizes, int n, int threads,
+                                           int64_t* top1, float* probs, float* logits, int32_t* status) {
   NvtxRangeJpeg nvtx_range("rn::InferJpegs (entropy decode on host threads | IDCT + colour + crop + forward on the device)");
-  {
-    cudaError_t ew = WaitHost(~0ull);  // uses staging slot 0 and activation set 0 on the replica's own stream
-    if (ew != cudaSuccess) return ew;
-  }
-  RN_CUDA(cudaSetDevice(device_));
-  last_launches_ = 0;
   const int S = shape_.im_side, C = shape_.num_classes;
   if (!d_descs_) RN_CUDA(Alloc(&d_descs_, static_cast<size_t>(max_batch_) * sizeof(CropDesc)));
   // headers first: geometry decides the micro-batches (at most max_batch files and ~0.4 GB of device staging each)
@@ -352,6 +526,117 @@ cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes
     }
   }
   for (auto& t : pool) t.join();
+  return cudaSuccess;
+}
+
+cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1,
+                                float* probs, float* logits, int32_t* status) {
+  {
+    cudaError_t ew = WaitHost(~0ull);  // uses staging slot 0 and activation set 0 on the replica's own stream
+    if (ew != cudaSuccess) return ew;
+  }
+  RN_CUDA(cudaSetDevice(device_));
+  last_launches_ = 0;
+  std::vector<int> todo;  // files for the host Huffman decoder
+  if (flags_ & RN_FLAG_JPEG_HOST_HUFFMAN) {
+    for (int i = 0; i < n; ++i) todo.push_back(i);
+  } else {
+    NvtxRangeJpeg nvtx_range("rn::InferJpegs (Huffman decode + IDCT + colour + crop + forward on the device)");
+    const int S = shape_.im_side, C = shape_.num_classes;
+    if (!d_descs_) RN_CUDA(Alloc(&d_descs_, static_cast<size_t>(max_batch_) * sizeof(CropDesc)));
+    std::vector<JpegBatch> batches;
+    {
+      constexpr size_t kStagingCap = size_t{3} << 29;  // 1.5 GB of device staging per batch
+      JpegInfo f;
+      size_t staged = 0;
+      for (int i = 0; i < n; ++i) {
+        status[i] = JpegParseHeader(files[i], sizes[i], &f);
+        if (status[i] != kJpegOk) continue;
+        const size_t need = f.coef_count * 3 + static_cast<size_t>(f.width) * f.height * 3 + sizes[i] * 2 + 4096;
+        if (batches.empty() || static_cast<int>(batches.back().index.size()) >= max_batch_ || staged + need > kStagingCap) {
+          batches.emplace_back();
+          staged = 0;
+        }
+        staged += need;
+        JpegBatch& b = batches.back();
+        b.index.push_back(i);
+        b.info.push_back(f);
+        b.coef_off.push_back(b.coef_total);
+        b.coef_total += Align(f.coef_count, 64);
+      }
+    }
+    std::vector<CropDesc> crops, packed;
+    std::vector<char> ok;
+    std::vector<int> where, entry, err;
+    for (auto& b : batches) {
+      cudaError_t e = JpegHuffmanOnDevice(files, sizes, &b, threads, &err);
+      if (e != cudaSuccess) return e;
+      const std::vector<int> prepared = b.st;
+      // entries the device did not take: JpegToRaw must skip them, the host path picks them up below
+      e = JpegToRaw(b, nullptr, &crops, &ok, nullptr);
+      if (e != cudaSuccess) return e;
+      packed.clear();
+      where.clear();
+      entry.clear();
+      for (size_t k = 0; k < b.index.size(); ++k) {
+        if (!ok[k]) {
+          todo.push_back(b.index[k]);
+          continue;
+        }
+        packed.push_back(crops[k]);
+        where.push_back(b.index[k]);
+        entry.push_back(static_cast<int>(k));
+      }
+      const int m = static_cast<int>(packed.size());
+      if (m == 0) continue;
+      const HostOut ho = Out(0);
+      RN_CUDA(cudaMemcpyAsync(d_descs_, packed.data(), m * sizeof(CropDesc), cudaMemcpyHostToDevice, compute_));
+      RN_CUDA(CropResizeBatchU8(d_raw_, static_cast<const CropDesc*>(d_descs_), m, static_cast<uint8_t*>(d_in_[0]), S, compute_));
+      ++last_launches_;
+      cur_ = &sets_[0];
+      e = ForwardDevice(d_in_[0], InputKind::kU8Bgr, m, ho.top1, ho.probs, ho.logits, compute_);
+      if (e != cudaSuccess) return e;
+      RN_CUDA(cudaStreamSynchronize(compute_));
+      JpegHuffmanErrors(&err);
+      for (int k = 0; k < m; ++k) {
+        const int dst = where[k];
+        if (err[entry[k]]) {  // the device found the stream damaged: the host decoder has the last word on this file
+          todo.push_back(dst);
+          continue;
+        }
+        ++jpeg_device_huffman_files_;
+        status[dst] = kJpegOk;
+        if (top1) top1[dst] = ho.top1[k];
+        if (probs) std::memcpy(probs + static_cast<size_t>(dst) * C, ho.probs + static_cast<size_t>(k) * C, C * sizeof(float));
+        if (logits) std::memcpy(logits + static_cast<size_t>(dst) * C, ho.logits + static_cast<size_t>(k) * C, C * sizeof(float));
+      }
+    }
+  }
+  if (todo.empty()) return cudaSuccess;
+  // ---- the rest: Huffman decoding on host threads ----
+  std::sort(todo.begin(), todo.end());
+  const int C = shape_.num_classes;
+  const int r = static_cast<int>(todo.size());
+  std::vector<const uint8_t*> f2(r);
+  std::vector<size_t> s2(r);
+  std::vector<int64_t> t2(r, -1);
+  std::vector<float> p2(static_cast<size_t>(r) * C), l2(static_cast<size_t>(r) * C);
+  std::vector<int32_t> st2(r, kJpegUnsupported);
+  for (int j = 0; j < r; ++j) {
+    f2[j] = files[todo[j]];
+    s2[j] = sizes[todo[j]];
+  }
+  cudaError_t e = InferJpegsHostHuffman(f2.data(), s2.data(), r, threads, t2.data(), p2.data(), l2.data(), st2.data());
+  if (e != cudaSuccess) return e;
+  for (int j = 0; j < r; ++j) {
+    const int dst = todo[j];
+    status[dst] = st2[j];
+    if (st2[j] != kJpegOk) continue;
+    ++jpeg_host_huffman_files_;
+    if (top1) top1[dst] = t2[j];
+    if (probs) std::memcpy(probs + static_cast<size_t>(dst) * C, p2.data() + static_cast<size_t>(j) * C, C * sizeof(float));
+    if (logits) std::memcpy(logits + static_cast<size_t>(dst) * C, l2.data() + static_cast<size_t>(j) * C, C * sizeof(float));
+  }
   return cudaSuccess;
 }
 

@@ -495,4 +495,166 @@ JpegStatus JpegDecodeCoefficients(const uint8_t* data, size_t size, const JpegIn
   return kJpegOk;
 }
 
+namespace {
+bool BuildDevHuff(const uint8_t* counts, const uint8_t* symbols, int nsym, DevHuffTable* t) {
+  std::memset(t, 0, sizeof(*t));
+  std::memcpy(t->vals, symbols, nsym);
+  int code = 0, k = 0;
+  for (int len = 1; len <= 16; ++len) {
+    t->valoff[len] = k - code;
+    for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
+      if (code >= (1 << len)) return false;
+      if (len <= 10) {
+        const int first = code << (10 - len);
+        for (int j = 0; j < (1 << (10 - len)); ++j) t->fast[first + j] = static_cast<uint16_t>((len << 8) | symbols[k]);
+      }
+    }
+    t->maxcode[len] = counts[len - 1] ? code - 1 : -1;
+    code <<= 1;
+  }
+  t->maxcode[17] = 0x7fffffff;
+  return true;
+}
+}  // namespace
+
+size_t JpegStreamCapacity(const JpegInfo& info, size_t size) {
+  const size_t mcus = static_cast<size_t>(CeilDiv(info.width, 8 * info.hmax)) * CeilDiv(info.height, 8 * info.vmax);
+  const size_t segs = info.restart_interval ? (mcus + info.restart_interval - 1) / info.restart_interval : 1;
+  return (size / kSubseqBytes + segs + 2) * kSubseqBytes;
+}
+
+JpegStatus JpegPrepareScan(const uint8_t* data, size_t size, const JpegInfo& info, JpegScanPlan* plan, uint8_t* stream,
+                           size_t stream_capacity, int32_t* sub_seg) {
+  // ---- tables and the scan header ----
+  struct RawHuff {
+    bool defined = false;
+    uint8_t counts[16];
+    uint8_t symbols[256];
+    int nsym = 0;
+  } dc[4], ac[4];
+  size_t pos = 2;
+  int restart_interval = 0;
+  const uint8_t* ecs = nullptr;
+  int td[3] = {0, 0, 0}, ta[3] = {0, 0, 0};
+  for (;;) {
+    const int m = NextMarker(data, size, &pos);
+    if (m == 0 || m == 0xD9) return kJpegCorrupt;
+    if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+    Segment s;
+    if (!ReadSegment(data, size, &pos, &s)) return kJpegCorrupt;
+    if (m == 0xC4) {
+      const uint8_t* p = s.payload;
+      size_t n = s.len;
+      while (n > 0) {
+        if (n < 17) return kJpegCorrupt;
+        const int tc = p[0] >> 4, th = p[0] & 15;
+        if (tc > 1 || th > 3) return kJpegCorrupt;
+        int nsym = 0;
+        for (int i = 0; i < 16; ++i) nsym += p[1 + i];
+        if (nsym > 256 || n < static_cast<size_t>(17 + nsym)) return kJpegCorrupt;
+        RawHuff& r = tc ? ac[th] : dc[th];
+        r.defined = true;
+        std::memcpy(r.counts, p + 1, 16);
+        std::memcpy(r.symbols, p + 17, nsym);
+        r.nsym = nsym;
+        p += 17 + nsym;
+        n -= 17 + nsym;
+      }
+    } else if (m == 0xDD) {
+      if (s.len < 2) return kJpegCorrupt;
+      restart_interval = static_cast<int>(Be16(s.payload));
+    } else if (m == 0xDA) {
+      const int ns = s.len >= 1 ? s.payload[0] : 0;
+      if (ns != info.ncomp || s.len < static_cast<size_t>(4 + 2 * ns)) return kJpegUnsupported;  // several scans
+      for (int i = 0; i < ns; ++i) {
+        if (s.payload[1 + 2 * i] != info.comp[i].id) return kJpegUnsupported;  // components out of frame order
+        td[i] = s.payload[2 + 2 * i] >> 4;
+        ta[i] = s.payload[2 + 2 * i] & 15;
+        if (td[i] > 3 || ta[i] > 3 || !dc[td[i]].defined || !ac[ta[i]].defined) return kJpegUnsupported;
+      }
+      const uint8_t* q = s.payload + 1 + 2 * ns;
+      if (q[0] != 0 || q[1] != 63 || q[2] != 0) return kJpegUnsupported;
+      ecs = data + pos;
+      break;
+    }
+  }
+  for (int c = 0; c < info.ncomp; ++c) {
+    if (!BuildDevHuff(dc[td[c]].counts, dc[td[c]].symbols, dc[td[c]].nsym, &plan->tab[2 * c]) ||
+        !BuildDevHuff(ac[ta[c]].counts, ac[ta[c]].symbols, ac[ta[c]].nsym, &plan->tab[2 * c + 1]))
+      return kJpegCorrupt;
+  }
+  // ---- MCU structure ----
+  plan->bpm = 0;
+  for (int c = 0; c < info.ncomp; ++c)
+    for (int vv = 0; vv < info.comp[c].v; ++vv)
+      for (int hh = 0; hh < info.comp[c].h; ++hh) {
+        plan->blk_comp[plan->bpm] = static_cast<uint8_t>(c);
+        plan->blk_hh[plan->bpm] = static_cast<uint8_t>(hh);
+        plan->blk_vv[plan->bpm] = static_cast<uint8_t>(vv);
+        ++plan->bpm;
+      }
+  if (info.ncomp == 1) {  // a single-component scan is not interleaved: one block per MCU, no dummy blocks
+    plan->mcus_x = info.comp[0].wblocks;
+    plan->mcus_y = info.comp[0].hblocks;
+  } else {
+    plan->mcus_x = CeilDiv(info.width, 8 * info.hmax);
+    plan->mcus_y = CeilDiv(info.height, 8 * info.vmax);
+  }
+  const size_t mcus = static_cast<size_t>(plan->mcus_x) * plan->mcus_y;
+  if (mcus * plan->bpm >= (size_t{1} << 31)) return kJpegUnsupported;
+  plan->total_blocks = static_cast<uint32_t>(mcus * plan->bpm);
+  plan->seg_blocks = restart_interval ? static_cast<uint32_t>(restart_interval) * plan->bpm : plan->total_blocks;
+  plan->n_seg = restart_interval ? static_cast<int>((mcus + restart_interval - 1) / restart_interval) : 1;
+  // ---- unstuff; restart segments start on subsequence boundaries ----
+  const uint8_t* p = ecs;
+  const uint8_t* end = data + size;
+  size_t o = 0;
+  int seg = 0;
+  size_t seg_start = 0;
+  bool eoi = false;
+  while (p < end) {
+    const uint8_t* ff = static_cast<const uint8_t*>(std::memchr(p, 0xFF, static_cast<size_t>(end - p)));
+    const size_t run = static_cast<size_t>((ff ? ff : end) - p);
+    if (o + run + 2 * kSubseqBytes > stream_capacity) return kJpegCorrupt;
+    std::memcpy(stream + o, p, run);
+    o += run;
+    if (!ff) {
+      p = end;
+      break;
+    }
+    p = ff + 1;
+    if (p >= end) break;
+    const int m = *p;
+    if (m == 0x00) {
+      stream[o++] = 0xFF;
+      ++p;
+    } else if (m == 0xFF) {
+      // fill byte: the next 0xFF decides
+    } else if (m >= 0xD0 && m <= 0xD7) {
+      if (!restart_interval || m != 0xD0 + (seg & 7) || seg + 1 >= plan->n_seg) return kJpegCorrupt;
+      ++p;
+      const size_t padded = (o + kSubseqBytes - 1) / kSubseqBytes * kSubseqBytes;
+      std::memset(stream + o, 0, padded - o);
+      o = padded;
+      for (size_t i = seg_start / kSubseqBytes; i < o / kSubseqBytes; ++i) sub_seg[i] = seg;
+      if (o == seg_start) return kJpegCorrupt;  // an empty restart segment
+      seg_start = o;
+      ++seg;
+    } else {
+      eoi = (m == 0xD9);
+      break;  // a marker other than RSTn ends the scan
+    }
+  }
+  if (!eoi) return kJpegUnsupported;  // truncated, or more segments follow (another scan): the host decoder decides
+  if (seg + 1 != plan->n_seg) return kJpegCorrupt;
+  const size_t padded = (o + kSubseqBytes - 1) / kSubseqBytes * kSubseqBytes;
+  if (padded + kSubseqBytes > stream_capacity) return kJpegCorrupt;
+  std::memset(stream + o, 0, padded - o);
+  o = padded;
+  if (o == seg_start) return kJpegCorrupt;
+  for (size_t i = seg_start / kSubseqBytes; i < o / kSubseqBytes; ++i) sub_seg[i] = seg;
+  plan->stream_bytes = o;
+  return kJpegOk;
+}
+
 }  // namespace rn

@@ -45,4 +45,35 @@ JpegStatus JpegParseHeader(const uint8_t* data, size_t size, JpegInfo* info);
 // a [hblocks][wblocks][64] array in natural order, NOT dequantised.
 JpegStatus JpegDecodeCoefficients(const uint8_t* data, size_t size, const JpegInfo& info, int16_t* coefs);
 
+// ---- device Huffman decoding (kernels_jpeg_huff.cu): what the host prepares per file ----
+// A Huffman table in the form the device decoder reads: 10-bit direct lookup, canonical-code search for longer codes.
+struct DevHuffTable {
+  uint16_t fast[1024];  // (length << 8) | symbol for codes of <= 10 bits, 0 = longer (or invalid) code
+  int32_t maxcode[18];  // largest code of each length, -1 = none
+  int32_t valoff[17];   // index of the first symbol of each length minus its first code
+  uint8_t vals[256];
+};
+constexpr int kSubseqBytes = 128;  // the device decodes the stream in subsequences of 1024 bits, one thread each
+
+// One file whose entropy-coded data is a single scan over all components (what encoders of photographs write).
+struct JpegScanPlan {
+  int bpm = 0;                 // blocks per MCU
+  uint8_t blk_comp[8] = {};    // block j of an MCU: component, column and row inside the MCU
+  uint8_t blk_hh[8] = {};
+  uint8_t blk_vv[8] = {};
+  int mcus_x = 0, mcus_y = 0;
+  uint32_t total_blocks = 0;   // bpm * mcus_x * mcus_y, dummy edge blocks included
+  uint32_t seg_blocks = 0;     // blocks per restart segment (= total_blocks when the file has no restart markers)
+  int n_seg = 1;
+  DevHuffTable tab[6];         // [2 * component] = DC table, [2 * component + 1] = AC table
+  size_t stream_bytes = 0;     // unstuffed stream written by JpegPrepareScan: a multiple of kSubseqBytes
+};
+// Upper bound of JpegScanPlan::stream_bytes for a file of `size` bytes (known from the header alone).
+size_t JpegStreamCapacity(const JpegInfo& info, size_t size);
+// Removes the byte stuffing and the restart markers of the scan: every restart segment starts on a subsequence
+// boundary of `stream` (padded with zero bytes), sub_seg[i] = restart segment of subsequence i.  kJpegOk = the device
+// can decode this file; anything else = use JpegDecodeCoefficients (several scans, tables redefined, damaged stream ...).
+JpegStatus JpegPrepareScan(const uint8_t* data, size_t size, const JpegInfo& info, JpegScanPlan* plan, uint8_t* stream,
+                           size_t stream_capacity, int32_t* sub_seg);
+
 }  // namespace rn

@@ -7,6 +7,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "jpeg_host.h"
+
 namespace rn {
 
 struct DenseParams {
@@ -70,6 +72,46 @@ struct JpegImageDesc {
 cudaError_t JpegIdct(const int16_t* coefs, const JpegPlaneDesc* planes, int n_planes, const uint16_t* quant,
                      uint8_t* samples, cudaStream_t st);
 cudaError_t JpegColor(const uint8_t* samples, const JpegImageDesc* images, int n_images, uint8_t* raw, cudaStream_t st);
+
+// ---- JPEG front end: Huffman decoding on the device (kernels_jpeg_huff.cu) ----
+// One file = one interleaved scan.  Offsets are into the batch's arenas.
+struct HuffFileDesc {
+  unsigned long long stream_off;   // bytes into the stream arena (a multiple of kSubseqBytes)
+  unsigned long long coef_off[3];  // int16 units into the coefficient arena, per component
+  unsigned long long dc_off;       // int16 units into the DC-difference arena (one per block, scan order)
+  unsigned sub_base, n_sub;        // this file's subsequences in the per-subsequence arrays
+  unsigned total_blocks, seg_blocks;
+  int bpm, mcus_x, ncomp, table_index;  // table_index: first of the file's six DevHuffTable
+  int wblocks[3], hblocks[3], comp_h[3], comp_v[3];
+  unsigned char blk_comp[8], blk_hh[8], blk_vv[8];
+};
+struct HuffBlockDesc {  // one CUDA block = 256 consecutive subsequences of one file
+  int file;
+  unsigned first_sub;
+};
+struct HuffBatch {
+  const HuffFileDesc* files;
+  const HuffBlockDesc* blocks;
+  const DevHuffTable* tables;
+  const unsigned char* streams;
+  const int* sub_seg;
+  unsigned long long* state;
+  unsigned long long* start_used;
+  unsigned* nblk;
+  unsigned* local_off;
+  unsigned* block_sum;
+  int* block_has_start;
+  unsigned* carry;
+  int16_t* coefs;    // zero-initialised by the caller
+  int16_t* dcdiff;
+  int* file_error;   // zero-initialised by the caller; non-zero = damaged stream, decode that file on the host
+  int* changed;      // device scratch
+  int* h_changed;    // pinned host scratch
+  int n_files, n_blocks;
+  int* rounds_out;   // optional: re-synchronisation launches it took
+};
+// Enqueues the whole decode on `st` (synchronises the stream between re-synchronisation rounds).
+cudaError_t HuffDecode(const HuffBatch& b, cudaStream_t st);
 
 // ---- 16-bit tensor-core path (kernels_tc.cu) --------------------------------
 // Activation layout between tensor-core layers ("chunked rows"):

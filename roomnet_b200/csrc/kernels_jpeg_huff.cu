@@ -1,0 +1,439 @@
+// Huffman (entropy) decoding of baseline JPEG scans on the device - the serial half of cv2.imread (infer.py:81).
+//
+// A Huffman stream has no random access, but a decoder started at an arbitrary bit re-synchronises with the true
+// symbol boundaries after a few symbols.  The stream (byte stuffing removed by the host while it gathers the files) is
+// cut into subsequences of 1024 bits, one thread each:
+//   1. every thread decodes its subsequence from a guessed state and remembers the state it ends in
+//      (bit position, block of the MCU, zigzag index);
+//   2. every thread whose predecessor ended in a state other than the one it started from decodes again from there -
+//      repeated (inside a CUDA block through shared memory, between blocks by relaunching) until nothing changes.  The
+//      first subsequence of a restart segment starts from a known state, so the fixed point is the sequential decode;
+//   3. a segmented prefix sum over the blocks completed per subsequence gives every thread its absolute block number;
+//   4. a last pass decodes once more and writes the coefficients where the inverse-DCT kernel expects them; the DC
+//      differences go to a scan-order array and are summed per component (predictor reset at restart markers) by a
+//      segmented scan.
+// Integer / bit work throughout; results are bit-identical to the host decoder (jpeg_host.cpp) by construction and the
+// tests compare the decoded image with cv2's.
+#include "kernels.h"
+
+namespace rn {
+namespace {
+
+constexpr int kSubBits = kSubseqBytes * 8;
+constexpr int kHuffThreads = 256;  // subsequences per CUDA block
+constexpr int kMaxInner = 64;      // re-synchronisation sweeps inside a block per launch
+
+__device__ __constant__ unsigned char kZigzagDev[80] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
+    6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,
+    39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+struct SmemHuff {
+  DevHuffTable tab[6];
+  unsigned words[kHuffThreads * kSubseqBytes / 4 + 4];  // the block's part of the stream (+ 16 bytes of look-ahead)
+};
+
+// decoder state between two symbols
+__device__ __forceinline__ unsigned long long pack_state(unsigned bit, unsigned blk, unsigned k) {
+  return static_cast<unsigned long long>(bit) | (static_cast<unsigned long long>(blk) << 32) |
+         (static_cast<unsigned long long>(k) << 40);
+}
+
+// 32 bits of the stream starting at bit `bit` (relative to the block's window in shared memory)
+__device__ __forceinline__ unsigned peek32(const unsigned* words, unsigned bit) {
+  const unsigned w = bit >> 5;
+  const unsigned a = __byte_perm(words[w], 0, 0x0123), b = __byte_perm(words[w + 1], 0, 0x0123);
+  return __funnelshift_l(b, a, bit & 31);
+}
+
+struct WriteCtx {
+  const HuffFileDesc* f;
+  int16_t* coefs;
+  int16_t* dcdiff;
+  unsigned block;      // absolute block number (scan order) of the block being decoded
+  unsigned seg_end;    // first block of the next restart segment
+  int16_t* dst;        // coefficient block being written (nullptr = dummy edge block)
+  int* error;
+};
+
+__device__ __forceinline__ int16_t* block_dst(const HuffFileDesc& f, int16_t* coefs, unsigned block) {
+  const unsigned mcu = block / f.bpm, j = block - mcu * f.bpm;
+  const int c = f.blk_comp[j];
+  const unsigned my = mcu / f.mcus_x, mx = mcu - my * f.mcus_x;
+  const unsigned bx = mx * f.comp_h[c] + f.blk_hh[j], by = my * f.comp_v[c] + f.blk_vv[j];
+  if (f.ncomp == 1) return coefs + f.coef_off[0] + static_cast<size_t>(block) * 64;
+  if (bx >= static_cast<unsigned>(f.wblocks[c]) || by >= static_cast<unsigned>(f.hblocks[c])) return nullptr;
+  return coefs + f.coef_off[c] + (static_cast<size_t>(by) * f.wblocks[c] + bx) * 64;
+}
+
+// Decodes from (bit, blk, k) until the bit position reaches end_bit (or, when writing, the restart segment is complete).
+// Returns the end state; *nblk = blocks completed on the way.
+template <bool WRITE>
+__device__ __forceinline__ unsigned long long decode_span(const SmemHuff& sm, unsigned win_bit0, unsigned bit, unsigned blk,
+                                                          unsigned k, unsigned end_bit, int bpm,
+                                                          const unsigned char* blk_comp, unsigned* nblk, WriteCtx* wc) {
+  unsigned done = 0;
+  while (bit < end_bit) {
+    const int c = blk_comp[blk];
+    const DevHuffTable& t = sm.tab[2 * c + (k ? 1 : 0)];
+    const unsigned bits = peek32(sm.words, bit - win_bit0);
+    unsigned e = t.fast[bits >> 22];
+    unsigned len, sym;
+    if (e) {
+      len = e >> 8;
+      sym = e & 255;
+    } else {
+      len = 0;
+      sym = 0;
+#pragma unroll 1
+      for (int l = 11; l <= 16; ++l) {
+        const int code = static_cast<int>(bits >> (32 - l));
+        if (code <= t.maxcode[l]) {
+          len = l;
+          sym = t.vals[code + t.valoff[l]];
+          break;
+        }
+      }
+      if (len == 0) {  // not a code: a decoder that is not synchronised yet moves on, the final pass reports damage
+        if (WRITE) *wc->error = 1;
+        len = 1;
+      }
+    }
+    if (k == 0) {
+      const unsigned s = sym & 15;
+      if (WRITE) {
+        int v = 0;
+        if (s) {
+          const unsigned raw = (bits << len) >> (32 - s);
+          v = raw < (1u << (s - 1)) ? static_cast<int>(raw) - (1 << s) + 1 : static_cast<int>(raw);
+        }
+        if (sym > 15) *wc->error = 1;
+        wc->dcdiff[wc->block] = static_cast<int16_t>(v);
+      }
+      bit += len + s;
+      k = 1;
+    } else {
+      const unsigned r = sym >> 4, s = sym & 15;
+      bit += len + s;
+      if (s == 0) {
+        k = (r == 15) ? k + 16 : 64;
+      } else {
+        k += r;
+        if (WRITE) {
+          if (k > 63) {
+            *wc->error = 1;
+          } else if (wc->dst) {
+            const unsigned raw = (bits << len) >> (32 - s);
+            const int v = raw < (1u << (s - 1)) ? static_cast<int>(raw) - (1 << s) + 1 : static_cast<int>(raw);
+            wc->dst[kZigzagDev[k]] = static_cast<int16_t>(v);
+          }
+        }
+        ++k;
+      }
+    }
+    if (k >= 64) {
+      k = 0;
+      blk = blk + 1 == static_cast<unsigned>(bpm) ? 0 : blk + 1;
+      ++done;
+      if (WRITE) {
+        ++wc->block;
+        if (wc->block >= wc->seg_end) break;
+        wc->dst = block_dst(*wc->f, wc->coefs, wc->block);
+      }
+    }
+  }
+  *nblk = done;
+  return pack_state(bit, blk, k);
+}
+
+__device__ __forceinline__ void load_block(SmemHuff& sm, const HuffFileDesc& f, const DevHuffTable* tables,
+                                           const unsigned char* streams, unsigned first_sub) {
+  const unsigned* src_t = reinterpret_cast<const unsigned*>(tables + f.table_index);
+  unsigned* dst_t = reinterpret_cast<unsigned*>(sm.tab);
+  for (int i = threadIdx.x; i < static_cast<int>(6 * sizeof(DevHuffTable) / 4); i += blockDim.x) dst_t[i] = src_t[i];
+  // the arena carries slack behind the last stream, so the look-ahead words never leave it
+  const unsigned* src = reinterpret_cast<const unsigned*>(streams + f.stream_off) + static_cast<size_t>(first_sub) * (kSubseqBytes / 4);
+  const unsigned avail = (f.n_sub - first_sub) * (kSubseqBytes / 4) + 4;
+  const unsigned n = min(static_cast<unsigned>(kHuffThreads * kSubseqBytes / 4 + 4), avail);
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) sm.words[i] = src[i];
+  __syncthreads();
+}
+
+// Passes 1 and 2.  state[] = end state of every subsequence, start_used[] = the state its last decode started from.
+__global__ void __launch_bounds__(kHuffThreads)
+huff_sync_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __restrict__ blocks,
+                 const DevHuffTable* __restrict__ tables, const unsigned char* __restrict__ streams,
+                 const int* __restrict__ sub_seg, unsigned long long* state, unsigned long long* start_used,
+                 unsigned* nblk, int first_round, int* changed) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemHuff& sm = *reinterpret_cast<SmemHuff*>(smem_raw);
+  __shared__ unsigned long long s_state[kHuffThreads];
+  const HuffBlockDesc bd = blocks[blockIdx.x];
+  const HuffFileDesc& f = files[bd.file];
+  load_block(sm, f, tables, streams, bd.first_sub);
+  const unsigned i = bd.first_sub + threadIdx.x;
+  const bool active = i < f.n_sub;
+  const unsigned gi = f.sub_base + i;
+  const unsigned win_bit0 = bd.first_sub * kSubBits;
+  const bool first = active && (i == 0 || sub_seg[gi] != sub_seg[gi - 1]);
+  const unsigned long long fixed = pack_state(i * kSubBits, 0, 0);  // what a restart segment starts with
+  unsigned long long used = 0, mine = 0;
+  unsigned cnt = 0;
+  bool any = false;
+  if (active) {
+    if (first_round) {
+      used = fixed;
+      mine = decode_span<false>(sm, win_bit0, i * kSubBits, 0, 0, (i + 1) * kSubBits, f.bpm, f.blk_comp, &cnt, nullptr);
+      any = true;
+    } else {
+      used = start_used[gi];
+      mine = state[gi];
+      cnt = nblk[gi];
+    }
+  }
+  s_state[threadIdx.x] = mine;
+  __syncthreads();
+  for (int it = 0; it < kMaxInner; ++it) {
+    unsigned long long prev = fixed;
+    if (active && !first) {
+      // across CUDA blocks the predecessor's state comes from the previous launch (none yet in the first round)
+      if (threadIdx.x) prev = s_state[threadIdx.x - 1];
+      else prev = first_round ? used : __ldcg(&state[gi - 1]);
+      const unsigned pbit = static_cast<unsigned>(prev);
+      if (pbit < i * kSubBits || pbit >= i * kSubBits + 32) prev = used;  // (cannot happen; keeps reads inside the window)
+    }
+    __syncthreads();
+    bool ch = false;
+    if (active && !first && prev != used) {
+      used = prev;
+      mine = decode_span<false>(sm, win_bit0, static_cast<unsigned>(prev), static_cast<unsigned>(prev >> 32) & 255,
+                                static_cast<unsigned>(prev >> 40) & 255, (i + 1) * kSubBits, f.bpm, f.blk_comp, &cnt, nullptr);
+      s_state[threadIdx.x] = mine;
+      ch = true;
+      any = true;
+    }
+    if (!__syncthreads_or(ch)) break;
+  }
+  if (active && any) {
+    state[gi] = mine;
+    start_used[gi] = used;
+    nblk[gi] = cnt;
+    if (!first_round) *changed = 1;
+  }
+}
+
+// Pass 3a: per CUDA block, segmented exclusive scan of nblk (restart segments reset the count); block totals out.
+__global__ void __launch_bounds__(kHuffThreads)
+huff_scan_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __restrict__ blocks,
+                 const int* __restrict__ sub_seg, const unsigned* __restrict__ nblk, unsigned* local_off,
+                 unsigned* block_sum, int* block_has_start) {
+  __shared__ unsigned s_val[kHuffThreads];
+  __shared__ int s_flag[kHuffThreads];
+  const HuffBlockDesc bd = blocks[blockIdx.x];
+  const HuffFileDesc& f = files[bd.file];
+  const unsigned i = bd.first_sub + threadIdx.x;
+  const bool active = i < f.n_sub;
+  const unsigned gi = f.sub_base + i;
+  const int first = active && (i == 0 || sub_seg[gi] != sub_seg[gi - 1]);
+  unsigned v = active ? nblk[gi] : 0;
+  int fl = first;
+  s_val[threadIdx.x] = v;
+  s_flag[threadIdx.x] = fl;
+  __syncthreads();
+  // inclusive segmented scan (Hillis-Steele): (v, f) o (v', f') = (f' ? v' : v + v', f | f')
+  for (int d = 1; d < kHuffThreads; d <<= 1) {
+    unsigned pv = 0;
+    int pf = 0;
+    if (threadIdx.x >= static_cast<unsigned>(d)) {
+      pv = s_val[threadIdx.x - d];
+      pf = s_flag[threadIdx.x - d];
+    }
+    __syncthreads();
+    if (threadIdx.x >= static_cast<unsigned>(d)) {
+      if (!fl) v += pv;
+      fl |= pf;
+      s_val[threadIdx.x] = v;
+      s_flag[threadIdx.x] = fl;
+    }
+    __syncthreads();
+  }
+  // exclusive value = blocks completed since the last segment start before this subsequence (inside this CUDA block)
+  if (active) {
+    const unsigned incl_prev = threadIdx.x ? s_val[threadIdx.x - 1] : 0;
+    local_off[gi] = first ? 0 : incl_prev;
+  }
+  if (threadIdx.x == kHuffThreads - 1) {
+    block_sum[blockIdx.x] = v;       // blocks since the last segment start inside this CUDA block (or since its beginning)
+    block_has_start[blockIdx.x] = fl;
+  }
+}
+
+// Pass 3b: carries between CUDA blocks (one thread block; a batch has a few thousand CUDA blocks at most).
+__global__ void huff_carry_kernel(const HuffBlockDesc* __restrict__ blocks, int n_blocks, const unsigned* __restrict__ block_sum,
+                                  const int* __restrict__ block_has_start, unsigned* carry) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned run = 0;
+  int file = -1;
+  for (int b = 0; b < n_blocks; ++b) {
+    if (blocks[b].file != file) {
+      file = blocks[b].file;
+      run = 0;
+    }
+    carry[b] = run;  // valid for the subsequences of block b that precede its first segment start
+    run = block_has_start[b] ? block_sum[b] : run + block_sum[b];
+  }
+}
+
+// Pass 4: decode from the synchronised states and write.
+__global__ void __launch_bounds__(kHuffThreads)
+huff_write_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __restrict__ blocks,
+                  const DevHuffTable* __restrict__ tables, const unsigned char* __restrict__ streams,
+                  const int* __restrict__ sub_seg, const unsigned long long* __restrict__ start_used,
+                  const unsigned* __restrict__ local_off, const unsigned* __restrict__ carry, int16_t* coefs,
+                  int16_t* dcdiff, int* file_error) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SmemHuff& sm = *reinterpret_cast<SmemHuff*>(smem_raw);
+  __shared__ int s_seen_start;
+  const HuffBlockDesc bd = blocks[blockIdx.x];
+  const HuffFileDesc& f = files[bd.file];
+  if (threadIdx.x == 0) s_seen_start = kHuffThreads;
+  load_block(sm, f, tables, streams, bd.first_sub);
+  const unsigned i = bd.first_sub + threadIdx.x;
+  const bool active = i < f.n_sub;
+  const unsigned gi = f.sub_base + i;
+  const bool first = active && (i == 0 || sub_seg[gi] != sub_seg[gi - 1]);
+  if (first) atomicMin(&s_seen_start, static_cast<int>(threadIdx.x));
+  __syncthreads();
+  if (!active) return;
+  const unsigned seg = static_cast<unsigned>(sub_seg[gi]);
+  const unsigned seg_first_block = seg * f.seg_blocks;
+  const unsigned seg_end = min(seg_first_block + f.seg_blocks, f.total_blocks);
+  // blocks completed in this restart segment before this subsequence
+  unsigned before = local_off[gi];
+  if (static_cast<int>(threadIdx.x) < s_seen_start) before += carry[blockIdx.x];
+  const unsigned long long st = start_used[gi];
+  WriteCtx wc;
+  wc.f = &f;
+  wc.coefs = coefs;
+  wc.dcdiff = dcdiff + f.dc_off;
+  wc.block = seg_first_block + before;
+  wc.seg_end = seg_end;
+  wc.error = file_error + bd.file;
+  const bool last_of_seg = i + 1 == f.n_sub || sub_seg[gi + 1] != sub_seg[gi];
+  if (wc.block >= seg_end) {
+    // nothing left for this subsequence (padding behind the last block of the segment) - unless blocks were lost
+    return;
+  }
+  wc.dst = block_dst(f, coefs, wc.block);
+  unsigned cnt = 0;
+  decode_span<true>(sm, bd.first_sub * kSubBits, static_cast<unsigned>(st), static_cast<unsigned>(st >> 32) & 255,
+                    static_cast<unsigned>(st >> 40) & 255, (i + 1) * kSubBits, f.bpm, f.blk_comp, &cnt, &wc);
+  if (last_of_seg && wc.block < seg_end) *wc.error = 1;  // the data ended before the segment's last block
+}
+
+// DC prediction: per (file, component) an inclusive sum of the differences in scan order, reset at restart segments.
+// One CUDA block per (file, component); thread chunks + a segmented scan over the chunk sums.
+__global__ void __launch_bounds__(1024)
+huff_dc_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict__ dcdiff, int16_t* coefs) {
+  __shared__ int s_sum[1024];
+  __shared__ int s_flag[1024];
+  const HuffFileDesc& f = files[blockIdx.x / 3];
+  const int c = blockIdx.x % 3;
+  if (c >= f.ncomp) return;
+  // blocks of component c inside an MCU are consecutive: [j0, j0 + per)
+  int j0 = 0;
+  for (int cc = 0; cc < c; ++cc) j0 += f.comp_h[cc] * f.comp_v[cc];
+  const int per = f.ncomp == 1 ? 1 : f.comp_h[c] * f.comp_v[c];
+  const unsigned mcus = f.total_blocks / f.bpm;
+  const unsigned n = mcus * per;                       // blocks of this component in scan order
+  const unsigned seg_len = (f.seg_blocks / f.bpm) * per;  // ... per restart segment
+  const int16_t* dd = dcdiff + f.dc_off;
+  const unsigned chunk = (n + blockDim.x - 1) / blockDim.x;
+  const unsigned lo = min(threadIdx.x * chunk, n), hi = min(lo + chunk, n);
+  auto scan_index = [&](unsigned t) { return (t / per) * f.bpm + j0 + t % per; };
+  int sum = 0, flag = 0;
+  for (unsigned t = lo; t < hi; ++t) {
+    if (t % seg_len == 0) {
+      sum = 0;
+      flag = 1;
+    }
+    sum += dd[scan_index(t)];
+  }
+  s_sum[threadIdx.x] = sum;
+  s_flag[threadIdx.x] = flag;
+  __syncthreads();
+  int v = sum, fl = flag;
+  for (int d = 1; d < 1024; d <<= 1) {
+    int pv = 0, pf = 0;
+    if (threadIdx.x >= static_cast<unsigned>(d)) {
+      pv = s_sum[threadIdx.x - d];
+      pf = s_flag[threadIdx.x - d];
+    }
+    __syncthreads();
+    if (threadIdx.x >= static_cast<unsigned>(d)) {
+      if (!fl) v += pv;
+      fl |= pf;
+      s_sum[threadIdx.x] = v;
+      s_flag[threadIdx.x] = fl;
+    }
+    __syncthreads();
+  }
+  int pred = threadIdx.x ? s_sum[threadIdx.x - 1] : 0;  // predictor entering this thread's chunk
+  for (unsigned t = lo; t < hi; ++t) {
+    if (t % seg_len == 0) pred = 0;
+    const unsigned b = scan_index(t);
+    pred += dd[b];
+    int16_t* dst = block_dst(f, coefs, b);
+    if (dst) dst[0] = static_cast<int16_t>(pred);
+  }
+}
+
+}  // namespace
+
+cudaError_t HuffDecode(const HuffBatch& b, cudaStream_t st) {
+  if (b.n_blocks <= 0) return cudaSuccess;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !attr_set[dev]) {
+    cudaFuncSetAttribute(huff_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmemHuff)));
+    cudaFuncSetAttribute(huff_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SmemHuff)));
+    attr_set[dev] = true;
+  }
+  const size_t smem = sizeof(SmemHuff);
+  huff_sync_kernel<<<b.n_blocks, kHuffThreads, smem, st>>>(b.files, b.blocks, b.tables, b.streams, b.sub_seg, b.state,
+                                                          b.start_used, b.nblk, 1, b.changed);
+  // re-synchronisation rounds: three launches in a row, then one at a time until a launch changed nothing
+  int rounds = 0;
+  for (;;) {
+    const int burst = rounds == 0 ? 3 : 1;
+    cudaError_t e = cudaMemsetAsync(b.changed, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    for (int r = 0; r < burst; ++r) {
+      if (r == burst - 1 && burst > 1) {
+        e = cudaMemsetAsync(b.changed, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+      }
+      huff_sync_kernel<<<b.n_blocks, kHuffThreads, smem, st>>>(b.files, b.blocks, b.tables, b.streams, b.sub_seg,
+                                                              b.state, b.start_used, b.nblk, 0, b.changed);
+    }
+    rounds += burst;
+    e = cudaMemcpyAsync(b.h_changed, b.changed, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return e;
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return e;
+    if (*b.h_changed == 0) break;
+    if (rounds > b.n_blocks + 4) return cudaErrorUnknown;  // cannot happen: one CUDA block settles per launch at worst
+  }
+  huff_scan_kernel<<<b.n_blocks, kHuffThreads, 0, st>>>(b.files, b.blocks, b.sub_seg, b.nblk, b.local_off, b.block_sum,
+                                                        b.block_has_start);
+  huff_carry_kernel<<<1, 32, 0, st>>>(b.blocks, b.n_blocks, b.block_sum, b.block_has_start, b.carry);
+  huff_write_kernel<<<b.n_blocks, kHuffThreads, smem, st>>>(b.files, b.blocks, b.tables, b.streams, b.sub_seg,
+                                                           b.start_used, b.local_off, b.carry, b.coefs, b.dcdiff,
+                                                           b.file_error);
+  huff_dc_kernel<<<b.n_files * 3, 1024, 0, st>>>(b.files, b.dcdiff, b.coefs);
+  if (b.rounds_out) *b.rounds_out = rounds;
+  return cudaGetLastError();
+}
+
+}  // namespace rn

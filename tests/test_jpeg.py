@@ -141,11 +141,13 @@ def test_files_the_device_path_does_not_take_are_reported_not_mangled():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.fixture(scope="module")
-def handle():
+@pytest.fixture(scope="module", params=["device_huffman", "host_huffman"])
+def handle(request):
+    """Both halves of the decoder on the device (default), or Huffman decoding on host threads."""
     from roomnet_b200.workload import default_checkpoint_prefix
-    h = _capi.Handle(precision="fp16", max_batch=64)
+    h = _capi.Handle(precision="fp16", max_batch=64, jpeg_host_huffman=request.param == "host_huffman")
     h.load_tf_checkpoint(default_checkpoint_prefix())
+    h.huffman_on_device = request.param == "device_huffman"
     yield h
     h.close()
 
@@ -159,11 +161,15 @@ def test_device_decode_is_bit_identical_to_cv2(handle):
     files.append(with_16bit_quant_tables(encode(photo(72, 90), "420", 60)))
     base = encode(photo(170, 250), "420", 85)
     files += [with_exif_orientation(base, o) for o in range(1, 9)]
+    before = handle.jpeg_counters()
     for k, data in enumerate(files):
         ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
         got, st = handle.decode_jpeg(data)
         assert st == _capi.JPEG_OK, k
         assert got.shape == ref.shape and np.array_equal(got, ref), k
+    dev, host = (a - b for a, b in zip(handle.jpeg_counters(), before))
+    # every one of these files is a single interleaved scan: the Huffman decoder that ran is the one asked for
+    assert (dev, host) == ((len(files), 0) if handle.huffman_on_device else (0, len(files)))
 
 
 @pytest.mark.gpu
@@ -186,8 +192,11 @@ def test_file_call_equals_decoded_image_call_and_reports_the_rest(handle):
         kinds.append(kind)
     files.append(files[0][:len(files[0]) // 2])  # truncated
     kinds.append(6)
+    before = handle.jpeg_counters()
     top1, probs, logits, status = handle.infer_jpeg(files, want_logits=True)
     ok = [i for i, k in enumerate(kinds) if k < 4]
+    dev, host = (a - b for a, b in zip(handle.jpeg_counters(), before))
+    assert (dev, host) == ((len(ok), 0) if handle.huffman_on_device else (0, len(ok)))
     assert all(status[i] == _capi.JPEG_OK for i in ok)
     assert all(status[i] == _capi.JPEG_UNSUPPORTED for i, k in enumerate(kinds) if k == 5)
     assert all(status[i] != _capi.JPEG_OK for i, k in enumerate(kinds) if k in (4, 6))

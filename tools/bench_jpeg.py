@@ -35,6 +35,8 @@ def main():
     mbytes = sum(len(f) for f in files) / 1e6
     h = _capi.Handle(precision="fp16", max_batch=64)
     h.load_tf_checkpoint(default_checkpoint_prefix())
+    hh = _capi.Handle(precision="fp16", max_batch=64, jpeg_host_huffman=True)
+    hh.load_tf_checkpoint(default_checkpoint_prefix())
     threads = min(16, os.cpu_count() or 1)
     cv2.setNumThreads(1)
 
@@ -49,11 +51,17 @@ def main():
     def device_path():
         return h.infer_jpeg(files, threads=threads, want_logits=True)
 
+    def host_huffman_path():
+        return hh.infer_jpeg(files, threads=threads, want_logits=True)
+
     ref = host_path()
     t1, p1, l1, st = device_path()
     assert (st == 0).all() and np.array_equal(l1, ref), "device decode must be bit-identical to cv2's"
+    assert h.jpeg_counters() == (n, 0), "every file of this set is a single scan: Huffman decoding on the device"
+    assert np.array_equal(host_huffman_path()[2], ref) and hh.jpeg_counters() == (0, n)
     res = {}
-    for name, fn in (("cv2_host_decode", host_path), ("device_decode", device_path)):
+    for name, fn in (("cv2_host_decode", host_path), ("device_decode", device_path),
+                     ("device_decode_host_huffman", host_huffman_path)):
         ts = []
         for _ in range(3):
             t0 = time.perf_counter()
