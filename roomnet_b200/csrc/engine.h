@@ -174,7 +174,7 @@ class Replica {
   cudaError_t InferJpegsHostHuffman(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1,
                                     float* probs, float* logits, int32_t* status);
   cudaError_t JpegHuffmanOnDevice(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
-                                  std::vector<int>* err);
+                                  std::vector<int>* err, const uint8_t* h_prepared);
   void JpegHuffmanErrors(std::vector<int>* err) const;
   uint8_t* d_huff_ = nullptr;  // device arena of the Huffman stage (streams, per-subsequence state, descriptors)
   size_t d_huff_cap_ = 0;

@@ -56,6 +56,30 @@ struct Replica::JpegBatch {
   std::vector<size_t> coef_off;  // int16 units into the pinned coefficient buffer
   size_t coef_total = 0;
   std::vector<int> st;         // JpegStatus per file after entropy decoding
+  // device Huffman stage: layout of the pinned staging buffer [streams | sub_seg] and the per-file scan plans
+  std::vector<size_t> stream_off;
+  size_t stream_total = 0, stage_bytes = 0;
+  std::vector<JpegScanPlan> plans;
+  void LayOutStreams(const size_t* sizes) {
+    const size_t m = index.size();
+    stream_off.resize(m);
+    stream_total = 0;
+    for (size_t k = 0; k < m; ++k) {
+      stream_off[k] = stream_total;
+      stream_total += JpegStreamCapacity(info[k], sizes[index[k]]);
+    }
+    stream_total += kSubseqBytes;  // look-ahead slack behind the last stream
+    stage_bytes = stream_total + stream_total / kSubseqBytes * sizeof(int32_t);
+    plans.resize(m);
+    st.assign(m, kJpegUnsupported);
+  }
+  // host half for entry k: strip the byte stuffing into the staging buffer
+  void PrepareStream(const uint8_t* const* files, const size_t* sizes, size_t k, uint8_t* h_stage) {
+    const size_t cap = (k + 1 < index.size() ? stream_off[k + 1] : stream_total - kSubseqBytes) - stream_off[k];
+    int32_t* h_sub_seg = reinterpret_cast<int32_t*>(h_stage + stream_total);
+    st[k] = JpegPrepareScan(files[index[k]], sizes[index[k]], info[k], &plans[k], h_stage + stream_off[k], cap,
+                            h_sub_seg + stream_off[k] / kSubseqBytes);
+  }
 };
 
 cudaError_t Replica::GrowJpegBuffers(size_t coef_bytes, size_t sample_bytes, size_t raw_bytes, int n_images, int n_host) {
@@ -176,48 +200,37 @@ cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::v
   return cudaSuccess;
 }
 
-// Device-Huffman stage of one batch: host threads strip the byte stuffing of each file's scan into a pinned buffer,
-// the device decodes the streams into d_coef_ (enqueued on compute_).  b->st[k] = kJpegOk for the files handed to the
+// Device-Huffman stage of one batch: host threads strip the byte stuffing of each file's scan into a pinned buffer
+// (here, or ahead of time by the caller's pipeline: h_prepared), the device decodes the streams into d_coef_
+// (enqueued on compute_).  b->st[k] = kJpegOk for the files handed to the
 // device, anything else = leave that file to the host decoder.  (*err)[k] becomes valid after the stream has been
 // synchronised: non-zero = the device found the stream damaged.
 cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
-                                         std::vector<int>* err) {
+                                         std::vector<int>* err, const uint8_t* h_prepared) {
   const int m = static_cast<int>(b->index.size());
-  b->st.assign(m, kJpegUnsupported);
   err->assign(m, 0);
-  // ---- layout of the pinned staging buffer: [streams | sub_seg] ----
-  std::vector<size_t> stream_off(m);
-  size_t stream_total = 0;
-  for (int k = 0; k < m; ++k) {
-    stream_off[k] = stream_total;
-    stream_total += JpegStreamCapacity(b->info[k], sizes[b->index[k]]);
-  }
-  stream_total += kSubseqBytes;  // look-ahead slack behind the last stream
-  const size_t n_sub_total = stream_total / kSubseqBytes;
-  const size_t stage_bytes = stream_total + n_sub_total * sizeof(int32_t);
-  {
-    cudaError_t e = GrowJpegBuffers((stage_bytes + 1) / 2 * 2, 0, 0, 0, 1);  // h_coef_[0] doubles as the staging buffer
+  const uint8_t* h_stream = h_prepared;
+  if (!h_prepared) {  // not staged by the caller's pipeline: do the host half here
+    b->LayOutStreams(sizes);
+    cudaError_t e = GrowJpegBuffers((b->stage_bytes + 1) / 2 * 2, 0, 0, 0, 1);  // h_coef_[0] doubles as the staging buffer
     if (e != cudaSuccess) return e;
-  }
-  RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
-  uint8_t* h_stream = reinterpret_cast<uint8_t*>(h_coef_[0]);
-  int32_t* h_sub_seg = reinterpret_cast<int32_t*>(h_stream + stream_total);
-  std::vector<JpegScanPlan> plans(m);
-  {
+    RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
+    uint8_t* stage = reinterpret_cast<uint8_t*>(h_coef_[0]);
     std::atomic<int> next{0};
     auto work = [&]() {
-      for (int k = next.fetch_add(1); k < m; k = next.fetch_add(1)) {
-        const size_t cap = (k + 1 < m ? stream_off[k + 1] : stream_total - kSubseqBytes) - stream_off[k];
-        b->st[k] = JpegPrepareScan(files[b->index[k]], sizes[b->index[k]], b->info[k], &plans[k], h_stream + stream_off[k],
-                                   cap, h_sub_seg + stream_off[k] / kSubseqBytes);
-      }
+      for (int k = next.fetch_add(1); k < m; k = next.fetch_add(1)) b->PrepareStream(files, sizes, k, stage);
     };
     const int nt = std::max(1, std::min(threads, m));
     std::vector<std::thread> pool;
     for (int t = 1; t < nt; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
+    h_stream = stage;
   }
+  const std::vector<size_t>& stream_off = b->stream_off;
+  const std::vector<JpegScanPlan>& plans = b->plans;
+  const size_t stream_total = b->stream_total, stage_bytes = b->stage_bytes;
+  const size_t n_sub_total = stream_total / kSubseqBytes;
   // ---- descriptors ----
   std::vector<HuffFileDesc> fds;
   std::vector<HuffBlockDesc> bds;
@@ -369,7 +382,7 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
   bool on_device = false;
   if (!(flags_ & RN_FLAG_JPEG_HOST_HUFFMAN)) {
     std::vector<int> err;
-    e = JpegHuffmanOnDevice(&file, &sz, &b, 1, &err);
+    e = JpegHuffmanOnDevice(&file, &sz, &b, 1, &err, nullptr);
     if (e != cudaSuccess) return e;
     if (b.st[0] == kJpegOk) {
       e = JpegToRaw(b, nullptr, &crops, &ok, status);
@@ -565,13 +578,87 @@ cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes
         b.coef_total += Align(f.coef_count, 64);
       }
     }
+    // Host threads strip the byte stuffing of the files of ALL batches in order, into a ring of pinned staging buffers,
+    // up to kJpegRing - 1 batches ahead of the device.
+    const int nbat = static_cast<int>(batches.size());
+    size_t max_stage = 0;
+    for (auto& b : batches) {
+      b.LayOutStreams(sizes);
+      max_stage = std::max(max_stage, b.stage_bytes);
+    }
+    if (nbat > 0) {
+      cudaError_t e = GrowJpegBuffers((max_stage + 1) / 2 * 2, 0, 0, 0, std::min(nbat, kJpegRing));
+      if (e != cudaSuccess) return e;
+      RN_CUDA(cudaStreamSynchronize(compute_));
+    }
+    std::mutex mu;
+    std::condition_variable cv;
+    int released = 0;
+    bool abort = false;
+    std::unique_ptr<std::atomic<int>[]> done(new std::atomic<int>[std::max(nbat, 1)]);
+    std::vector<std::pair<int, int>> items;
+    for (int bi = 0; bi < nbat; ++bi) {
+      done[bi].store(0);
+      for (int k = 0; k < static_cast<int>(batches[bi].index.size()); ++k) items.emplace_back(bi, k);
+    }
+    std::atomic<int> next{0};
+    auto work = [&]() {
+      for (int i = next.fetch_add(1); i < static_cast<int>(items.size()); i = next.fetch_add(1)) {
+        const int bi = items[i].first, k = items[i].second;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return abort || released >= bi - (kJpegRing - 1); });
+          if (abort) return;
+        }
+        batches[bi].PrepareStream(files, sizes, k, reinterpret_cast<uint8_t*>(h_coef_[bi % kJpegRing]));
+        if (done[bi].fetch_add(1) + 1 == static_cast<int>(batches[bi].index.size())) {
+          { std::lock_guard<std::mutex> lk(mu); }
+          cv.notify_all();
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < std::max(1, std::min(threads, static_cast<int>(items.size()))) && !items.empty(); ++t)
+      pool.emplace_back(work);
+    struct Joiner {  // every exit path stops and joins the pool
+      std::mutex& mu;
+      std::condition_variable& cv;
+      bool& abort;
+      std::vector<std::thread>& pool;
+      ~Joiner() {
+        {
+          std::lock_guard<std::mutex> lk(mu);
+          abort = true;
+        }
+        cv.notify_all();
+        for (auto& t : pool) t.join();
+      }
+    } joiner{mu, cv, abort, pool};
     std::vector<CropDesc> crops, packed;
     std::vector<char> ok;
     std::vector<int> where, entry, err;
-    for (auto& b : batches) {
-      cudaError_t e = JpegHuffmanOnDevice(files, sizes, &b, threads, &err);
+    for (int bi = 0; bi < nbat; ++bi) {
+      JpegBatch& b = batches[bi];
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return done[bi].load() == static_cast<int>(b.index.size()); });
+      }
+      struct Release {  // hand the staging buffer back when this batch is done, whatever happens
+        std::mutex& mu;
+        std::condition_variable& cv;
+        int& released;
+        int value;
+        ~Release() {
+          {
+            std::lock_guard<std::mutex> lk(mu);
+            released = value;
+          }
+          cv.notify_all();
+        }
+      } release{mu, cv, released, bi + 1};
+      cudaError_t e = JpegHuffmanOnDevice(files, sizes, &b, threads, &err,
+                                          reinterpret_cast<const uint8_t*>(h_coef_[bi % kJpegRing]));
       if (e != cudaSuccess) return e;
-      const std::vector<int> prepared = b.st;
       // entries the device did not take: JpegToRaw must skip them, the host path picks them up below
       e = JpegToRaw(b, nullptr, &crops, &ok, nullptr);
       if (e != cudaSuccess) return e;
