@@ -188,6 +188,12 @@ int rn_decode_jpeg_u8_bgr(rn_handle* h, const uint8_t* file, uint64_t size, uint
  * on host threads (several scans, damaged streams, RN_FLAG_JPEG_HOST_HUFFMAN), since the handle was created. */
 int rn_get_jpeg_counters(rn_handle* h, int64_t* device_huffman_files, int64_t* host_huffman_files);
 int rn_jpeg_info(const uint8_t* file, uint64_t size, int64_t info[8]);
+/* Host-only: what the host hands to the device Huffman decoder for this file - the scan with the byte stuffing and the
+ * restart markers removed, every restart segment padded to a multiple of 128 bytes (stream), and the restart segment of
+ * every 128-byte subsequence (sub_seg, capacity / 128 entries).  info = {stream bytes, restart segments, blocks per MCU,
+ * total blocks}.  Returns the rn_jpeg_status (RN_JPEG_UNSUPPORTED = this file takes the host Huffman decoder). */
+int rn_jpeg_prepare_scan(const uint8_t* file, uint64_t size, uint8_t* stream, uint64_t capacity, int32_t* sub_seg,
+                         int64_t info[4]);
 int rn_jpeg_coefficients(const uint8_t* file, uint64_t size, int16_t* coefs, uint64_t capacity);
 
 /* CameraActivity.onImageAvailable -> ImageUtils.convertYUV420ToARGB8888 -> ClassifierActivity.processImage

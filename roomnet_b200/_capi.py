@@ -70,6 +70,7 @@ def _load():
                                   C.c_int),
         "rn_jpeg_info": ([vp, C.c_uint64, i64p], C.c_int),
         "rn_get_jpeg_counters": ([vp, i64p, i64p], C.c_int),
+        "rn_jpeg_prepare_scan": ([vp, C.c_uint64, vp, C.c_uint64, vp, i64p], C.c_int),
         "rn_jpeg_coefficients": ([vp, C.c_uint64, vp, C.c_uint64], C.c_int),
         "rn_infer_yuv420": ([vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], C.c_int),
         "rn_center_crop_rect": ([i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], C.c_int),
@@ -105,6 +106,21 @@ def jpeg_info(data):
     return tuple(int(v) for v in info)
 
 
+def jpeg_prepare_scan(data):
+    """Host-only: (status, unstuffed stream bytes, restart segment of every 128-byte subsequence, (segments, blocks per
+    MCU, total blocks)) - what the device Huffman decoder is given for this file."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    cap = (buf.size // 128 + 70000) * 128
+    stream = np.zeros(cap, np.uint8)
+    sub_seg = np.full(cap // 128, -1, np.int32)
+    info = (C.c_int64 * 4)()
+    st = lib.rn_jpeg_prepare_scan(buf.ctypes.data, buf.size, stream.ctypes.data, cap, sub_seg.ctypes.data, info)
+    if st != JPEG_OK:
+        return st, None, None, None
+    n = int(info[0])
+    return st, stream[:n], sub_seg[:n // 128], (int(info[1]), int(info[2]), int(info[3]))
+
+
 def jpeg_coefficients(data):
     """Host-only: (status, int16 coefficients or None) - the entropy-decoded, still quantised DCT coefficients."""
     info = jpeg_info(data)
@@ -118,7 +134,7 @@ EXPORTED = ["rn_create", "rn_destroy", "rn_load_tf_checkpoint", "rn_load_tensors
             "rn_infer_u8_bgr", "rn_infer_u8_rgb", "rn_infer_f32_rgb", "rn_infer_argb8888", "rn_infer_u8_bgr_device",
             "rn_submit_u8_bgr", "rn_wait",
             "rn_preprocess_u8", "rn_infer_image_u8_bgr", "rn_infer_images_u8_bgr", "rn_infer_jpeg",
-            "rn_decode_jpeg_u8_bgr", "rn_get_jpeg_counters", "rn_jpeg_info", "rn_jpeg_coefficients", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
+            "rn_decode_jpeg_u8_bgr", "rn_get_jpeg_counters", "rn_jpeg_info", "rn_jpeg_prepare_scan", "rn_jpeg_coefficients", "rn_infer_yuv420", "rn_center_crop_rect", "rn_flat_len", "rn_num_kernel_launches", "rn_get_folded",
             "rn_debug_activation", "rn_get_stats", "rn_reset_stats", "rn_set_profiling", "rn_get_profile",
             "rn_last_error", "rn_version"]
 

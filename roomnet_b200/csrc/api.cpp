@@ -565,6 +565,27 @@ int rn_jpeg_info(const uint8_t* file, uint64_t size, int64_t info[8]) {
   }
 }
 
+int rn_jpeg_prepare_scan(const uint8_t* file, uint64_t size, uint8_t* stream, uint64_t capacity, int32_t* sub_seg,
+                         int64_t info[4]) {
+  if (!file || !stream || !sub_seg || !info) return RN_JPEG_CORRUPT;
+  try {
+    rn::JpegInfo f;
+    int st = rn::JpegParseHeader(file, size, &f);
+    if (st != rn::kJpegOk) return st;
+    if (capacity < rn::JpegStreamCapacity(f, size)) return RN_JPEG_CORRUPT;
+    auto plan = std::make_unique<rn::JpegScanPlan>();
+    st = rn::JpegPrepareScan(file, size, f, plan.get(), stream, capacity, sub_seg);
+    if (st != rn::kJpegOk) return st;
+    info[0] = static_cast<int64_t>(plan->stream_bytes);
+    info[1] = plan->n_seg;
+    info[2] = plan->bpm;
+    info[3] = plan->total_blocks;
+    return RN_JPEG_OK;
+  } catch (...) {
+    return RN_JPEG_CORRUPT;
+  }
+}
+
 int rn_jpeg_coefficients(const uint8_t* file, uint64_t size, int16_t* coefs, uint64_t capacity) {
   if (!file || !coefs) return RN_JPEG_CORRUPT;
   try {

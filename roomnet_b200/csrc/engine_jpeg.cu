@@ -1,7 +1,9 @@
 // Replica entry points of the JPEG front end: cv2.imread + infer_optimized of the reference's directory loop
-// (infer.py:79-82) for files that are baseline JPEGs.  Entropy decoding on a few host threads (jpeg_host.cpp), then on
-// the device: inverse DCT -> upsampling + colour conversion (kernels_jpeg.cu) -> centre crop + cv2-identical resize of
-// the whole micro-batch -> forward pass.  The decoded photo never exists in host memory.
+// (infer.py:79-82) for files that are baseline JPEGs.  Host threads strip the byte stuffing of the files into a ring of
+// pinned buffers (jpeg_host.cpp); on the device: Huffman decoding (kernels_jpeg_huff.cu) -> inverse DCT -> upsampling +
+// colour conversion (kernels_jpeg.cu) -> centre crop + cv2-identical resize of the whole micro-batch -> forward pass.
+// The decoded photo never exists in host memory.  Files the device Huffman stage does not take (several scans, damaged
+// streams) go through the host Huffman decoder and the same device kernels.
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>

@@ -1,8 +1,10 @@
 // Host half of the JPEG front end (replaces cv2.imread of the reference's classify_im_dir, infer.py:81, for baseline
-// JPEG files): marker parsing and Huffman (entropy) decoding, which are serial bit-stream work, stay on the CPU; what
-// they produce - quantised DCT coefficients - goes to the device, where dequantisation, the inverse DCT, chroma
-// upsampling and the colour conversion run as CUDA kernels (kernels_jpeg.cu) with the integer arithmetic of
-// libjpeg-turbo's default decoder (JDCT_ISLOW, fancy upsampling), i.e. bit-identical to cv2.imread.
+// JPEG files).  Default: the host parses the markers, puts the Huffman tables into device form and strips the byte
+// stuffing of the scan (JpegPrepareScan); Huffman decoding (kernels_jpeg_huff.cu), dequantisation, inverse DCT, chroma
+// upsampling and colour conversion (kernels_jpeg.cu) are CUDA kernels with the integer arithmetic of libjpeg-turbo's
+// default decoder (JDCT_ISLOW, fancy upsampling), i.e. bit-identical to cv2.imread.  Fallback (files with several
+// scans, RN_FLAG_JPEG_HOST_HUFFMAN) and test oracle: a complete table-driven Huffman decoder on the host
+// (JpegDecodeCoefficients), whose quantised coefficients go to the same device kernels.
 //
 // Supported: 8-bit baseline / extended-sequential Huffman JPEG (SOF0 / SOF1), grey or YCbCr, luma sampling 1x1, 2x1,
 // 2x2 with 1x1 chroma, any number of scans, restart intervals, EXIF orientation.  Everything else (progressive,

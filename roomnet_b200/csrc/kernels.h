@@ -83,7 +83,8 @@ struct HuffFileDesc {
   unsigned total_blocks, seg_blocks;
   int bpm, mcus_x, ncomp, table_index;  // table_index: first of the file's six DevHuffTable
   int wblocks[3], hblocks[3], comp_h[3], comp_v[3];
-  unsigned char blk_comp[8], blk_hh[8], blk_vv[8];
+  alignas(8) unsigned char blk_comp[8];
+  unsigned char blk_hh[8], blk_vv[8];
 };
 struct HuffBlockDesc {  // one CUDA block = 256 consecutive subsequences of one file
   int file;

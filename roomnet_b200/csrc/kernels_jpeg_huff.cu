@@ -71,10 +71,10 @@ __device__ __forceinline__ int16_t* block_dst(const HuffFileDesc& f, int16_t* co
 template <bool WRITE>
 __device__ __forceinline__ unsigned long long decode_span(const SmemHuff& sm, unsigned win_bit0, unsigned bit, unsigned blk,
                                                           unsigned k, unsigned end_bit, int bpm,
-                                                          const unsigned char* blk_comp, unsigned* nblk, WriteCtx* wc) {
+                                                          unsigned long long blk_comp, unsigned* nblk, WriteCtx* wc) {
   unsigned done = 0;
   while (bit < end_bit) {
-    const int c = blk_comp[blk];
+    const int c = static_cast<int>(blk_comp >> (8 * blk)) & 3;
     const DevHuffTable& t = sm.tab[2 * c + (k ? 1 : 0)];
     const unsigned bits = peek32(sm.words, bit - win_bit0);
     unsigned e = t.fast[bits >> 22];
@@ -171,6 +171,7 @@ huff_sync_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __
   const HuffBlockDesc bd = blocks[blockIdx.x];
   const HuffFileDesc& f = files[bd.file];
   load_block(sm, f, tables, streams, bd.first_sub);
+  const unsigned long long comp_of = *reinterpret_cast<const unsigned long long*>(f.blk_comp);  // component of block j
   const unsigned i = bd.first_sub + threadIdx.x;
   const bool active = i < f.n_sub;
   const unsigned gi = f.sub_base + i;
@@ -183,7 +184,7 @@ huff_sync_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __
   if (active) {
     if (first_round) {
       used = fixed;
-      mine = decode_span<false>(sm, win_bit0, i * kSubBits, 0, 0, (i + 1) * kSubBits, f.bpm, f.blk_comp, &cnt, nullptr);
+      mine = decode_span<false>(sm, win_bit0, i * kSubBits, 0, 0, (i + 1) * kSubBits, f.bpm, comp_of, &cnt, nullptr);
       any = true;
     } else {
       used = start_used[gi];
@@ -207,7 +208,7 @@ huff_sync_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __
     if (active && !first && prev != used) {
       used = prev;
       mine = decode_span<false>(sm, win_bit0, static_cast<unsigned>(prev), static_cast<unsigned>(prev >> 32) & 255,
-                                static_cast<unsigned>(prev >> 40) & 255, (i + 1) * kSubBits, f.bpm, f.blk_comp, &cnt, nullptr);
+                                static_cast<unsigned>(prev >> 40) & 255, (i + 1) * kSubBits, f.bpm, comp_of, &cnt, nullptr);
       s_state[threadIdx.x] = mine;
       ch = true;
       any = true;
@@ -268,19 +269,53 @@ huff_scan_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __
   }
 }
 
-// Pass 3b: carries between CUDA blocks (one thread block; a batch has a few thousand CUDA blocks at most).
-__global__ void huff_carry_kernel(const HuffBlockDesc* __restrict__ blocks, int n_blocks, const unsigned* __restrict__ block_sum,
-                                  const int* __restrict__ block_has_start, unsigned* carry) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Pass 3b: carries between CUDA blocks: carry[b] = blocks completed since the last restart-segment start before CUDA
+// block b (0 at the first block of a file).  One thread block, chunked segmented scan.
+__global__ void __launch_bounds__(1024)
+huff_carry_kernel(const HuffBlockDesc* __restrict__ blocks, int n_blocks, const unsigned* __restrict__ block_sum,
+                  const int* __restrict__ block_has_start, unsigned* carry) {
+  __shared__ unsigned s_val[1024];
+  __shared__ int s_flag[1024];
+  const int chunk = (n_blocks + 1023) / 1024;
+  const int lo = min(static_cast<int>(threadIdx.x) * chunk, n_blocks), hi = min(lo + chunk, n_blocks);
+  // a CUDA block restarts the count when it holds a segment start or is the first of its file
+  auto restarts = [&](int b) { return block_has_start[b] || b == 0 || blocks[b].file != blocks[b - 1].file; };
   unsigned run = 0;
-  int file = -1;
-  for (int b = 0; b < n_blocks; ++b) {
-    if (blocks[b].file != file) {
-      file = blocks[b].file;
+  int flag = 0;
+  for (int b = lo; b < hi; ++b) {
+    if (restarts(b)) {
       run = 0;
+      flag = 1;
     }
-    carry[b] = run;  // valid for the subsequences of block b that precede its first segment start
-    run = block_has_start[b] ? block_sum[b] : run + block_sum[b];
+    run += block_sum[b];
+  }
+  s_val[threadIdx.x] = run;
+  s_flag[threadIdx.x] = flag;
+  __syncthreads();
+  unsigned v = run;
+  int fl = flag;
+  for (int d = 1; d < 1024; d <<= 1) {
+    unsigned pv = 0;
+    int pf = 0;
+    if (threadIdx.x >= static_cast<unsigned>(d)) {
+      pv = s_val[threadIdx.x - d];
+      pf = s_flag[threadIdx.x - d];
+    }
+    __syncthreads();
+    if (threadIdx.x >= static_cast<unsigned>(d)) {
+      if (!fl) v += pv;
+      fl |= pf;
+      s_val[threadIdx.x] = v;
+      s_flag[threadIdx.x] = fl;
+    }
+    __syncthreads();
+  }
+  run = threadIdx.x ? s_val[threadIdx.x - 1] : 0;  // count entering this thread's chunk
+  for (int b = lo; b < hi; ++b) {
+    const bool new_file = b == 0 || blocks[b].file != blocks[b - 1].file;
+    if (new_file) run = 0;
+    carry[b] = run;  // for the subsequences of block b that precede its first segment start
+    run = (block_has_start[b] ? 0 : run) + block_sum[b];
   }
 }
 
@@ -298,6 +333,7 @@ huff_write_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* _
   const HuffFileDesc& f = files[bd.file];
   if (threadIdx.x == 0) s_seen_start = kHuffThreads;
   load_block(sm, f, tables, streams, bd.first_sub);
+  const unsigned long long comp_of = *reinterpret_cast<const unsigned long long*>(f.blk_comp);
   const unsigned i = bd.first_sub + threadIdx.x;
   const bool active = i < f.n_sub;
   const unsigned gi = f.sub_base + i;
@@ -327,7 +363,7 @@ huff_write_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* _
   wc.dst = block_dst(f, coefs, wc.block);
   unsigned cnt = 0;
   decode_span<true>(sm, bd.first_sub * kSubBits, static_cast<unsigned>(st), static_cast<unsigned>(st >> 32) & 255,
-                    static_cast<unsigned>(st >> 40) & 255, (i + 1) * kSubBits, f.bpm, f.blk_comp, &cnt, &wc);
+                    static_cast<unsigned>(st >> 40) & 255, (i + 1) * kSubBits, f.bpm, comp_of, &cnt, &wc);
   if (last_of_seg && wc.block < seg_end) *wc.error = 1;  // the data ended before the segment's last block
 }
 
@@ -427,7 +463,7 @@ cudaError_t HuffDecode(const HuffBatch& b, cudaStream_t st) {
   }
   huff_scan_kernel<<<b.n_blocks, kHuffThreads, 0, st>>>(b.files, b.blocks, b.sub_seg, b.nblk, b.local_off, b.block_sum,
                                                         b.block_has_start);
-  huff_carry_kernel<<<1, 32, 0, st>>>(b.blocks, b.n_blocks, b.block_sum, b.block_has_start, b.carry);
+  huff_carry_kernel<<<1, 1024, 0, st>>>(b.blocks, b.n_blocks, b.block_sum, b.block_has_start, b.carry);
   huff_write_kernel<<<b.n_blocks, kHuffThreads, smem, st>>>(b.files, b.blocks, b.tables, b.streams, b.sub_seg,
                                                            b.start_used, b.local_off, b.carry, b.coefs, b.dcdiff,
                                                            b.file_error);

@@ -117,6 +117,41 @@ def test_grey_and_16bit_tables_and_all_orientations():
         assert np.array_equal(cpu_decode(data), ref), o
 
 
+def test_scan_preparation_for_the_device_huffman_decoder():
+    """The host's share of the device Huffman path: byte stuffing and restart markers removed, restart segments on
+    128-byte subsequence boundaries - against a numpy restatement of the same rules (T.81 B.1.1.5, F.1.2.3)."""
+    for h, w, sf, q, extra in CASES[::2] + [(300, 400, "420", 97, (cv2.IMWRITE_JPEG_RST_INTERVAL, 1))]:
+        data = encode(photo(h, w, seed=h * w), sf, q, extra)
+        st, stream, sub_seg, (n_seg, bpm, total_blocks) = _capi.jpeg_prepare_scan(data)
+        assert st == _capi.JPEG_OK
+        a = np.frombuffer(data, np.uint8)
+        sos = data.index(b"\xff\xda")
+        start = sos + 2 + int.from_bytes(data[sos + 2:sos + 4], "big")
+        scan = a[start:len(a) - 2]  # up to EOI
+        ff = np.flatnonzero(scan[:-1] == 0xFF)
+        nxt = scan[ff + 1]
+        rst = ff[(nxt >= 0xD0) & (nxt <= 0xD7)]
+        keep = np.ones(scan.size, bool)
+        keep[ff[nxt == 0] + 1] = False  # the stuffed zero after a data 0xFF
+        keep[rst] = False
+        keep[rst + 1] = False
+        bounds = [0, *rst.tolist(), scan.size]
+        want, seg_ids = [], []
+        for s_i in range(len(bounds) - 1):
+            part = scan[bounds[s_i]:bounds[s_i + 1]][keep[bounds[s_i]:bounds[s_i + 1]]]
+            pad = (-part.size) % 128
+            want.append(np.concatenate([part, np.zeros(pad, np.uint8)]))
+            seg_ids += [s_i] * ((part.size + pad) // 128)
+        want = np.concatenate(want)
+        assert n_seg == len(bounds) - 1
+        assert stream.size == want.size and np.array_equal(stream, want), (h, w, sf, q)
+        assert np.array_equal(sub_seg, np.array(seg_ids, np.int32))
+        hs, vs = {"444": (1, 1), "422": (2, 1), "420": (2, 2)}[sf]
+        assert bpm == hs * vs + 2 and total_blocks == bpm * (-(-w // (8 * hs))) * (-(-h // (8 * vs)))
+    # a truncated file is left to the host decoder
+    assert _capi.jpeg_prepare_scan(data[:len(data) // 2])[0] != _capi.JPEG_OK
+
+
 def test_files_the_device_path_does_not_take_are_reported_not_mangled():
     img = photo(64, 64)
     ok, prog = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])

@@ -18,7 +18,7 @@ $NCU --set full --import-source on -c 30 -o $O/${TAG}_fp32 -f \
 $NCU --set full --import-source on -s 20 -c 10 -o $O/${TAG}_fp32tc -f \
     python tools/profile_once.py --batch 256 --iters 2 --precision fp32tc > $O/${TAG}_fp32tc.log 2>&1
 # 4. front-end kernels, 300 / 600 variants
-$NCU --set full --import-source on -k regex:"crop_resize|yuv420|jpeg_|prep_u8|chunked_to_f32|avgpool|join_kernel|dense_tail|conv3x3" -c 44 \
+$NCU --set full --import-source on -k regex:"crop_resize|yuv420|jpeg_|huff_|prep_u8|chunked_to_f32|avgpool|join_kernel|dense_tail|conv3x3" -c 56 \
     -o $O/${TAG}_front -f python tools/profile_front.py > $O/${TAG}_front.log 2>&1
 tail -n 2 $O/${TAG}_full.log $O/${TAG}_fp32.log $O/${TAG}_front.log
 # gpurun brings back at most 64 MiB: keep the raw metric pages as CSV (what tools/summarize_profiles.py reads) and, of the
