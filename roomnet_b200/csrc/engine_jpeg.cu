@@ -336,6 +336,12 @@ cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size
       return e;
     }
   }
+  if (jpeg_huffman_rounds_ < 0) {  // no fixed point within the launch budget: every file of the batch goes to the host path
+    for (int k = 0; k < m; ++k)
+      if (b->st[k] == kJpegOk) b->st[k] = kJpegUnsupported;
+    huff_file_of_.clear();
+    return cudaSuccess;
+  }
   last_launches_ += 4 + jpeg_huffman_rounds_ + 1;
   // error flags travel back with the rest of the batch (valid after the caller's stream synchronisation)
   RN_CUDA(cudaMemcpyAsync(h_huff_flags_ + 16, base + o_err, nf * sizeof(int), cudaMemcpyDeviceToHost, compute_));

@@ -22,6 +22,7 @@ namespace {
 constexpr int kSubBits = kSubseqBytes * 8;
 constexpr int kHuffThreads = 256;  // subsequences per CUDA block
 constexpr int kMaxInner = 64;      // re-synchronisation sweeps inside a block per launch
+constexpr int kMaxRounds = 16;     // launches before the batch is handed to the host decoder
 
 __device__ __constant__ unsigned char kZigzagDev[80] = {
     0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
@@ -30,20 +31,13 @@ __device__ __constant__ unsigned char kZigzagDev[80] = {
 
 struct SmemHuff {
   DevHuffTable tab[6];
-  unsigned words[kHuffThreads * kSubseqBytes / 4 + 4];  // the block's part of the stream (+ 16 bytes of look-ahead)
+  unsigned words[kHuffThreads * kSubseqBytes / 4 + 8];  // the block's part of the stream (+ 32 bytes of look-ahead)
 };
 
 // decoder state between two symbols
 __device__ __forceinline__ unsigned long long pack_state(unsigned bit, unsigned blk, unsigned k) {
   return static_cast<unsigned long long>(bit) | (static_cast<unsigned long long>(blk) << 32) |
          (static_cast<unsigned long long>(k) << 40);
-}
-
-// 32 bits of the stream starting at bit `bit` (relative to the block's window in shared memory)
-__device__ __forceinline__ unsigned peek32(const unsigned* words, unsigned bit) {
-  const unsigned w = bit >> 5;
-  const unsigned a = __byte_perm(words[w], 0, 0x0123), b = __byte_perm(words[w + 1], 0, 0x0123);
-  return __funnelshift_l(b, a, bit & 31);
 }
 
 struct WriteCtx {
@@ -73,10 +67,22 @@ __device__ __forceinline__ unsigned long long decode_span(const SmemHuff& sm, un
                                                           unsigned k, unsigned end_bit, int bpm,
                                                           unsigned long long blk_comp, unsigned* nblk, WriteCtx* wc) {
   unsigned done = 0;
+  // 64-bit window on the stream: the next symbol's bits are its top 32; refilled one word at a time
+  unsigned w = (bit - win_bit0) >> 5;
+  const unsigned skew = (bit - win_bit0) & 31;
+  unsigned long long buf = ((static_cast<unsigned long long>(__byte_perm(sm.words[w], 0, 0x0123)) << 32) |
+                            __byte_perm(sm.words[w + 1], 0, 0x0123))
+                           << skew;
+  int avail = 64 - static_cast<int>(skew);
+  w += 2;
   while (bit < end_bit) {
     const int c = static_cast<int>(blk_comp >> (8 * blk)) & 3;
     const DevHuffTable& t = sm.tab[2 * c + (k ? 1 : 0)];
-    const unsigned bits = peek32(sm.words, bit - win_bit0);
+    if (avail < 32) {
+      buf |= static_cast<unsigned long long>(__byte_perm(sm.words[w++], 0, 0x0123)) << (32 - avail);
+      avail += 32;
+    }
+    const unsigned bits = static_cast<unsigned>(buf >> 32);
     unsigned e = t.fast[bits >> 22];
     unsigned len, sym;
     if (e) {
@@ -111,10 +117,14 @@ __device__ __forceinline__ unsigned long long decode_span(const SmemHuff& sm, un
         wc->dcdiff[wc->block] = static_cast<int16_t>(v);
       }
       bit += len + s;
+      buf <<= len + s;
+      avail -= static_cast<int>(len + s);
       k = 1;
     } else {
       const unsigned r = sym >> 4, s = sym & 15;
       bit += len + s;
+      buf <<= len + s;
+      avail -= static_cast<int>(len + s);
       if (s == 0) {
         k = (r == 15) ? k + 16 : 64;
       } else {
@@ -153,8 +163,8 @@ __device__ __forceinline__ void load_block(SmemHuff& sm, const HuffFileDesc& f, 
   for (int i = threadIdx.x; i < static_cast<int>(6 * sizeof(DevHuffTable) / 4); i += blockDim.x) dst_t[i] = src_t[i];
   // the arena carries slack behind the last stream, so the look-ahead words never leave it
   const unsigned* src = reinterpret_cast<const unsigned*>(streams + f.stream_off) + static_cast<size_t>(first_sub) * (kSubseqBytes / 4);
-  const unsigned avail = (f.n_sub - first_sub) * (kSubseqBytes / 4) + 4;
-  const unsigned n = min(static_cast<unsigned>(kHuffThreads * kSubseqBytes / 4 + 4), avail);
+  const unsigned avail = (f.n_sub - first_sub) * (kSubseqBytes / 4) + 8;
+  const unsigned n = min(static_cast<unsigned>(kHuffThreads * kSubseqBytes / 4 + 8), avail);
   for (unsigned i = threadIdx.x; i < n; i += blockDim.x) sm.words[i] = src[i];
   __syncthreads();
 }
@@ -459,7 +469,12 @@ cudaError_t HuffDecode(const HuffBatch& b, cudaStream_t st) {
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return e;
     if (*b.h_changed == 0) break;
-    if (rounds > b.n_blocks + 4) return cudaErrorUnknown;  // cannot happen: one CUDA block settles per launch at worst
+    if (rounds >= kMaxRounds) {
+      // a stream whose decoders do not re-synchronise (one CUDA block settles per launch at worst): not worth chasing
+      // on the device - the caller decodes this batch's files with the sequential host decoder
+      if (b.rounds_out) *b.rounds_out = -1;
+      return cudaSuccess;
+    }
   }
   huff_scan_kernel<<<b.n_blocks, kHuffThreads, 0, st>>>(b.files, b.blocks, b.sub_seg, b.nblk, b.local_off, b.block_sum,
                                                         b.block_has_start);
