@@ -30,6 +30,7 @@ __device__ __constant__ unsigned char kZigzagDev[80] = {
     39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
 
 struct SmemHuff {
+  unsigned char zigzag[80];  // (constant memory serialises lanes that index it differently; shared memory does not)
   DevHuffTable tab[6];
   unsigned words[kHuffThreads * kSubseqBytes / 4 + 8];  // the block's part of the stream (+ 32 bytes of look-ahead)
 };
@@ -105,51 +106,37 @@ __device__ __forceinline__ unsigned long long decode_span(const SmemHuff& sm, un
         len = 1;
       }
     }
-    if (k == 0) {
-      const unsigned s = sym & 15;
-      if (WRITE) {
-        int v = 0;
-        if (s) {
-          const unsigned raw = (bits << len) >> (32 - s);
-          v = raw < (1u << (s - 1)) ? static_cast<int>(raw) - (1 << s) + 1 : static_cast<int>(raw);
-        }
+    // One symbol, written with selects rather than branches so that the lanes of a warp stay together whatever kind of
+    // symbol each of them is on: a DC symbol is an AC symbol with run 0 stored at position 0.
+    const bool is_dc = k == 0;
+    const unsigned r = is_dc ? 0u : sym >> 4, sz = sym & 15;
+    const unsigned n = len + sz;
+    const bool ends = !is_dc && sz == 0;  // end of block (run 0) or sixteen zeros (run 15)
+    const unsigned kpos = k + r;          // where this coefficient goes
+    if (WRITE) {
+      const unsigned raw = static_cast<unsigned>((static_cast<unsigned long long>(bits << len) << sz) >> 32);
+      const unsigned half = (1u << sz) >> 1;
+      const int v = raw < half ? static_cast<int>(raw) - static_cast<int>(1u << sz) + 1 : static_cast<int>(raw);
+      if (is_dc) {
         if (sym > 15) *wc->error = 1;
         wc->dcdiff[wc->block] = static_cast<int16_t>(v);
-      }
-      bit += len + s;
-      buf <<= len + s;
-      avail -= static_cast<int>(len + s);
-      k = 1;
-    } else {
-      const unsigned r = sym >> 4, s = sym & 15;
-      bit += len + s;
-      buf <<= len + s;
-      avail -= static_cast<int>(len + s);
-      if (s == 0) {
-        k = (r == 15) ? k + 16 : 64;
-      } else {
-        k += r;
-        if (WRITE) {
-          if (k > 63) {
-            *wc->error = 1;
-          } else if (wc->dst) {
-            const unsigned raw = (bits << len) >> (32 - s);
-            const int v = raw < (1u << (s - 1)) ? static_cast<int>(raw) - (1 << s) + 1 : static_cast<int>(raw);
-            wc->dst[kZigzagDev[k]] = static_cast<int16_t>(v);
-          }
-        }
-        ++k;
+      } else if (!ends) {
+        if (kpos > 63) *wc->error = 1;
+        else if (wc->dst) wc->dst[sm.zigzag[kpos]] = static_cast<int16_t>(v);
       }
     }
-    if (k >= 64) {
-      k = 0;
-      blk = blk + 1 == static_cast<unsigned>(bpm) ? 0 : blk + 1;
-      ++done;
-      if (WRITE) {
-        ++wc->block;
-        if (wc->block >= wc->seg_end) break;
-        wc->dst = block_dst(*wc->f, wc->coefs, wc->block);
-      }
+    k = ends ? (r == 15 ? k + 16 : 64u) : kpos + 1;
+    bit += n;
+    buf <<= n;
+    avail -= static_cast<int>(n);
+    const bool fin = k >= 64;
+    k = fin ? 0u : k;
+    blk = fin ? (blk + 1 == static_cast<unsigned>(bpm) ? 0u : blk + 1) : blk;
+    done += fin ? 1u : 0u;
+    if (WRITE && fin) {
+      ++wc->block;
+      if (wc->block >= wc->seg_end) break;
+      wc->dst = block_dst(*wc->f, wc->coefs, wc->block);
     }
   }
   *nblk = done;
@@ -161,6 +148,7 @@ __device__ __forceinline__ void load_block(SmemHuff& sm, const HuffFileDesc& f, 
   const unsigned* src_t = reinterpret_cast<const unsigned*>(tables + f.table_index);
   unsigned* dst_t = reinterpret_cast<unsigned*>(sm.tab);
   for (int i = threadIdx.x; i < static_cast<int>(6 * sizeof(DevHuffTable) / 4); i += blockDim.x) dst_t[i] = src_t[i];
+  if (threadIdx.x < 80) sm.zigzag[threadIdx.x] = kZigzagDev[threadIdx.x];
   // the arena carries slack behind the last stream, so the look-ahead words never leave it
   const unsigned* src = reinterpret_cast<const unsigned*>(streams + f.stream_off) + static_cast<size_t>(first_sub) * (kSubseqBytes / 4);
   const unsigned avail = (f.n_sub - first_sub) * (kSubseqBytes / 4) + 8;
