@@ -245,6 +245,48 @@ def test_file_call_equals_decoded_image_call_and_reports_the_rest(handle):
 
 
 @pytest.mark.gpu
+def test_damaged_streams_never_break_the_device_decoder():
+    """Bytes flipped inside the entropy-coded data (headers intact): the device Huffman decoder must survive whatever
+    the stream then says - a status per file, no CUDA error - and where both decoders accept a file they agree."""
+    from roomnet_b200.workload import default_checkpoint_prefix
+    rng = np.random.default_rng(21)
+    good = [encode(photo(160 + 8 * k, 240 - 8 * k, seed=k), ("444", "422", "420")[k % 3], 80,
+                   (cv2.IMWRITE_JPEG_RST_INTERVAL, 5) if k % 4 == 0 else ()) for k in range(12)]
+    files = []
+    for k in range(60):
+        d = bytearray(good[k % len(good)])
+        start = d.index(b"\xff\xda") + 14
+        for _ in range(int(rng.integers(1, 5))):
+            mode = int(rng.integers(0, 3))
+            pos = int(rng.integers(start, len(d) - 2))
+            if mode == 0:
+                d[pos] = int(rng.integers(0, 256))
+            elif mode == 1:
+                del d[pos:pos + int(rng.integers(1, 40))]
+            else:
+                d[pos:pos] = bytes(rng.integers(0, 256, int(rng.integers(1, 20)), dtype=np.uint8))
+        files.append(bytes(d))
+    files += good  # undamaged files in the same call still come out right
+    outs = {}
+    for mode in ("device", "host"):
+        h = _capi.Handle(precision="fp16", max_batch=32, jpeg_host_huffman=mode == "host")
+        h.load_tf_checkpoint(default_checkpoint_prefix())
+        outs[mode] = h.infer_jpeg(files, want_logits=True)
+        again = h.infer_jpeg(good, want_logits=True)  # and the handle is still healthy afterwards
+        assert (again[3] == 0).all()
+        outs[mode + "_good"] = again
+        h.close()
+    sd, sh = outs["device"][3], outs["host"][3]
+    assert set(sd.tolist()) <= {0, 1, 2} and set(sh.tolist()) <= {0, 1, 2}
+    assert (sd[-len(good):] == 0).all() and (sh[-len(good):] == 0).all()
+    both = (sd == 0) & (sh == 0)
+    assert both.sum() >= len(good)
+    assert np.array_equal(outs["device"][2][both], outs["host"][2][both])
+    assert np.array_equal(outs["device_good"][2], outs["host_good"][2])
+    assert np.array_equal(outs["device"][2][-len(good):], outs["device_good"][2])
+
+
+@pytest.mark.gpu
 def test_infer_files_falls_back_to_cv2_for_what_the_device_does_not_decode():
     from roomnet_b200.network import RoomNet
     from roomnet_b200.workload import default_checkpoint_prefix

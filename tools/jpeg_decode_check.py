@@ -1,5 +1,7 @@
+"""Decodes 31 JPEG files of every supported kind on the device (Huffman stage included) and compares each with
+cv2.imdecode; the workload of the compute-sanitizer runs on the JPEG kernels (profiles/r02_sanitizer.md)."""
 import sys, numpy as np, cv2
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import os; ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 from roomnet_b200 import _capi
 from test_jpeg import photo, encode, CASES, with_exif_orientation, with_16bit_quant_tables
 h=_capi.Handle(precision="fp16", max_batch=8)
