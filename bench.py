@@ -259,6 +259,55 @@ def latency_leg(calls=1000):
             "launch": "programmatic dependent launch (PDL) chain, one call = 9 kernels"}
 
 
+def jpeg_leg(_capi, np, n=64):
+    """SURVEY 8f n1 on the record: n synthetic photographs as JPEG bytes -> labels through rn_infer_jpeg (the whole JPEG
+    decoder on the device) against cv2.imdecode on host threads + the batched photo call; logits must be identical."""
+    try:
+        import cv2
+    except ImportError:
+        return {"unavailable": "cv2 not importable"}
+    from concurrent.futures import ThreadPoolExecutor
+    from roomnet_b200.workload import default_checkpoint_prefix
+    rng = np.random.default_rng(7)
+    sizes = [(3000, 4000), (2448, 3264), (1080, 1920), (1536, 2048)]
+    files, mpix = [], 0.0
+    for i in range(n):
+        hh, ww = sizes[i % 4]
+        small = rng.integers(0, 256, (hh // 16 + 2, ww // 16 + 2, 3), dtype=np.uint8)
+        img = cv2.resize(small, (ww, hh), interpolation=cv2.INTER_CUBIC).astype(np.int16)
+        img += rng.integers(-10, 11, img.shape, dtype=np.int16)
+        files.append(cv2.imencode(".jpg", np.clip(img, 0, 255).astype(np.uint8), [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes())
+        mpix += hh * ww / 1e6
+    threads = min(16, os.cpu_count() or 1)
+    cv2.setNumThreads(1)
+    h = _capi.Handle(precision="fp16", max_batch=64)
+    h.load_tf_checkpoint(default_checkpoint_prefix())
+
+    def host_decode():
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            ims = list(pool.map(lambda f: cv2.imdecode(np.frombuffer(f, np.uint8), cv2.IMREAD_COLOR), files))
+        return h.infer_images_u8_bgr(ims, want_logits=True)[2]
+
+    ref = host_decode()
+    out = h.infer_jpeg(files, threads=threads, want_logits=True)
+    if not ((out[3] == 0).all() and np.array_equal(out[2], ref)):
+        raise SystemExit("bench: rn_infer_jpeg differs from cv2.imdecode + rn_infer_images_u8_bgr")
+    t = {}
+    for name, fn in (("cv2_host_decode", host_decode), ("device_decode", lambda: h.infer_jpeg(files, threads=threads))):
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        t[name] = best
+    dev_files, host_files = h.jpeg_counters()
+    h.close()
+    return {"files": n, "megapixels": round(mpix, 1), "encoded_MB": round(sum(map(len, files)) / 1e6, 1),
+            "host_threads": threads, "files_per_s": n / t["device_decode"], "gpixel_per_s": mpix / 1e3 / t["device_decode"],
+            "cv2_on_host_threads_files_per_s": n / t["cv2_host_decode"], "logits_bit_identical_to_cv2_path": True,
+            "huffman_decoded_on_device": dev_files > 0 and host_files == 0, "api": "rn_infer_jpeg"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -269,7 +318,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--max-batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra-legs", action="store_true", help="skip the config-3 (one handle, all GPUs) and batch-1 latency legs")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the config-3 (one handle, all GPUs), batch-1 latency, sustained and JPEG front-end legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -430,10 +479,11 @@ def main():
                      "clocks": sus_sampler.stop()}
 
     # ---- BASELINE configs[2] and configs[4] on the record (rank 0; the other ranks idle at the barrier) ----
-    config3 = latency_b1 = None
+    config3 = latency_b1 = jpeg_front = None
     if rank == 0 and not args.no_extra_legs:
         config3 = config3_leg(_capi, np, torch, max(world, args.gpus if world == 1 else world), args.precision, suite)
         latency_b1 = latency_leg()
+        jpeg_front = jpeg_leg(_capi, np)
     host_barrier()
 
     if rank == 0:
@@ -465,6 +515,7 @@ def main():
             "cpu_baseline": cpu,
             "config3": config3,
             "latency_b1": latency_b1,
+            "jpeg_front": jpeg_front,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
