@@ -49,7 +49,18 @@ struct WriteCtx {
   unsigned seg_end;    // first block of the next restart segment
   int16_t* dst;        // coefficient block being written (nullptr = dummy edge block)
   int* error;
+  unsigned mx, my;     // MCU column / row of `block` (kept in step with it: no divisions per block)
 };
+
+// destination of block j of MCU (mx, my)
+__device__ __forceinline__ int16_t* mcu_block_dst(const HuffFileDesc& f, int16_t* coefs, unsigned mx, unsigned my, unsigned j,
+                                                  unsigned block) {
+  if (f.ncomp == 1) return coefs + f.coef_off[0] + static_cast<size_t>(block) * 64;
+  const int c = f.blk_comp[j];
+  const unsigned bx = mx * f.comp_h[c] + f.blk_hh[j], by = my * f.comp_v[c] + f.blk_vv[j];
+  if (bx >= static_cast<unsigned>(f.wblocks[c]) || by >= static_cast<unsigned>(f.hblocks[c])) return nullptr;
+  return coefs + f.coef_off[c] + (static_cast<size_t>(by) * f.wblocks[c] + bx) * 64;
+}
 
 __device__ __forceinline__ int16_t* block_dst(const HuffFileDesc& f, int16_t* coefs, unsigned block) {
   const unsigned mcu = block / f.bpm, j = block - mcu * f.bpm;
@@ -136,7 +147,13 @@ __device__ __forceinline__ unsigned long long decode_span(const SmemHuff& sm, un
     if (WRITE && fin) {
       ++wc->block;
       if (wc->block >= wc->seg_end) break;
-      wc->dst = block_dst(*wc->f, wc->coefs, wc->block);
+      if (blk == 0) {  // next MCU
+        if (++wc->mx == static_cast<unsigned>(wc->f->mcus_x)) {
+          wc->mx = 0;
+          ++wc->my;
+        }
+      }
+      wc->dst = mcu_block_dst(*wc->f, wc->coefs, wc->mx, wc->my, blk, wc->block);
     }
   }
   *nblk = done;
@@ -358,6 +375,11 @@ huff_write_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* _
     // nothing left for this subsequence (padding behind the last block of the segment) - unless blocks were lost
     return;
   }
+  {
+    const unsigned mcu = wc.block / f.bpm;
+    wc.my = mcu / f.mcus_x;
+    wc.mx = mcu - wc.my * f.mcus_x;
+  }
   wc.dst = block_dst(f, coefs, wc.block);
   unsigned cnt = 0;
   decode_span<true>(sm, bd.first_sub * kSubBits, static_cast<unsigned>(st), static_cast<unsigned>(st >> 32) & 255,
@@ -384,14 +406,24 @@ huff_dc_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict
   const int16_t* dd = dcdiff + f.dc_off;
   const unsigned chunk = (n + blockDim.x - 1) / blockDim.x;
   const unsigned lo = min(threadIdx.x * chunk, n), hi = min(lo + chunk, n);
-  auto scan_index = [&](unsigned t) { return (t / per) * f.bpm + j0 + t % per; };
+  // element t of the component = block (t / per) * bpm + j0 + t % per of the scan; walked with counters
+  unsigned mcu0 = lo / per, q0 = lo - mcu0 * per, left0 = seg_len - lo % seg_len;  // left0: elements until the next reset
   int sum = 0, flag = 0;
-  for (unsigned t = lo; t < hi; ++t) {
-    if (t % seg_len == 0) {
-      sum = 0;
-      flag = 1;
+  {
+    unsigned mcu = mcu0, q = q0, left = left0 == seg_len ? 0 : left0;
+    for (unsigned t = lo; t < hi; ++t) {
+      if (left == 0) {
+        sum = 0;
+        flag = 1;
+        left = seg_len;
+      }
+      --left;
+      sum += dd[mcu * f.bpm + j0 + q];
+      if (++q == static_cast<unsigned>(per)) {
+        q = 0;
+        ++mcu;
+      }
     }
-    sum += dd[scan_index(t)];
   }
   s_sum[threadIdx.x] = sum;
   s_flag[threadIdx.x] = flag;
@@ -413,12 +445,26 @@ huff_dc_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict
     __syncthreads();
   }
   int pred = threadIdx.x ? s_sum[threadIdx.x - 1] : 0;  // predictor entering this thread's chunk
+  unsigned mcu = mcu0, q = q0, left = left0 == seg_len ? 0 : left0;
+  unsigned my = mcu / f.mcus_x, mx = mcu - my * f.mcus_x;
   for (unsigned t = lo; t < hi; ++t) {
-    if (t % seg_len == 0) pred = 0;
-    const unsigned b = scan_index(t);
+    if (left == 0) {
+      pred = 0;
+      left = seg_len;
+    }
+    --left;
+    const unsigned b = mcu * f.bpm + j0 + q;
     pred += dd[b];
-    int16_t* dst = block_dst(f, coefs, b);
+    int16_t* dst = mcu_block_dst(f, coefs, mx, my, j0 + q, b);
     if (dst) dst[0] = static_cast<int16_t>(pred);
+    if (++q == static_cast<unsigned>(per)) {
+      q = 0;
+      ++mcu;
+      if (++mx == static_cast<unsigned>(f.mcus_x)) {
+        mx = 0;
+        ++my;
+      }
+    }
   }
 }
 
