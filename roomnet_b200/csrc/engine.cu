@@ -55,7 +55,10 @@ Replica::~Replica() {
   if (d_coef_) cudaFree(d_coef_);
   if (d_samples_) cudaFree(d_samples_);
   if (d_jmeta_) cudaFree(d_jmeta_);
-  if (d_huff_) cudaFree(d_huff_);
+  for (uint8_t* p : d_huff_)
+    if (p) cudaFree(p);
+  for (cudaEvent_t ev : ev_huff_up_)
+    if (ev) cudaEventDestroy(ev);
   if (h_huff_flags_) cudaFreeHost(h_huff_flags_);
   for (int16_t* p : h_coef_)
     if (p) cudaFreeHost(p);

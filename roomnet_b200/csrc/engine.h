@@ -173,11 +173,20 @@ class Replica {
   struct JpegBatch;
   cudaError_t InferJpegsHostHuffman(const uint8_t* const* files, const size_t* sizes, int n, int threads, int64_t* top1,
                                     float* probs, float* logits, int32_t* status);
-  cudaError_t JpegHuffmanOnDevice(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
-                                  std::vector<int>* err, const uint8_t* h_prepared);
+  cudaError_t JpegHuffUpload(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
+                             const uint8_t* h_prepared, int slot);
+  cudaError_t JpegHuffRun(JpegBatch* b, int slot, std::vector<int>* err);
+  struct HuffStage {  // a batch between its upload (copy stream) and its kernels (compute stream)
+    HuffBatch hb{};
+    std::vector<int> file_of;
+    size_t o_err = 0, coef_bytes = 0;
+    int nf = 0;
+    bool any = false;
+  } huff_stage_[2];
+  cudaEvent_t ev_huff_up_[2] = {nullptr, nullptr};
   void JpegHuffmanErrors(std::vector<int>* err) const;
-  uint8_t* d_huff_ = nullptr;  // device arena of the Huffman stage (streams, per-subsequence state, descriptors)
-  size_t d_huff_cap_ = 0;
+  uint8_t* d_huff_[2] = {nullptr, nullptr};  // device arenas of the Huffman stage (streams, per-subsequence state,
+  size_t d_huff_cap_[2] = {0, 0};             // descriptors): one is uploaded to while the kernels read the other
   int* h_huff_flags_ = nullptr;  // pinned: [0] convergence flag, [16 ..] per-file error flags
   std::vector<int> huff_file_of_;
   int jpeg_huffman_rounds_ = 0;

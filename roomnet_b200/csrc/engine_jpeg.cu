@@ -207,16 +207,19 @@ cudaError_t Replica::JpegToRaw(const JpegBatch& b, const int16_t* h_coef, std::v
 // (enqueued on compute_).  b->st[k] = kJpegOk for the files handed to the
 // device, anything else = leave that file to the host decoder.  (*err)[k] becomes valid after the stream has been
 // synchronised: non-zero = the device found the stream damaged.
-cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
-                                         std::vector<int>* err, const uint8_t* h_prepared) {
+cudaError_t Replica::JpegHuffUpload(const uint8_t* const* files, const size_t* sizes, JpegBatch* b, int threads,
+                                    const uint8_t* h_prepared, int slot) {
   const int m = static_cast<int>(b->index.size());
-  err->assign(m, 0);
+  HuffStage& stg = huff_stage_[slot];
+  stg.any = false;
+  stg.file_of.clear();
   const uint8_t* h_stream = h_prepared;
   if (!h_prepared) {  // not staged by the caller's pipeline: do the host half here
     b->LayOutStreams(sizes);
     cudaError_t e = GrowJpegBuffers((b->stage_bytes + 1) / 2 * 2, 0, 0, 0, 1);  // h_coef_[0] doubles as the staging buffer
     if (e != cudaSuccess) return e;
     RN_CUDA(cudaStreamSynchronize(compute_));  // an earlier upload may still be reading the pinned buffer
+    RN_CUDA(cudaStreamSynchronize(copy_));
     uint8_t* stage = reinterpret_cast<uint8_t*>(h_coef_[0]);
     std::atomic<int> next{0};
     auto work = [&]() {
@@ -272,6 +275,10 @@ cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size
   }
   if (fds.empty()) return cudaSuccess;
   const int nf = static_cast<int>(fds.size()), nb = static_cast<int>(bds.size());
+  stg.any = true;
+  stg.nf = nf;
+  stg.file_of = file_of;
+  stg.coef_bytes = b->coef_total * sizeof(int16_t);
   // ---- device arenas ----
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -297,18 +304,26 @@ cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size
       if (e == cudaSuccess) *cap = need + need / 4;
       return e;
     };
-    RN_CUDA(grow(reinterpret_cast<void**>(&d_huff_), &d_huff_cap_, off));
+    // (the compute stream is idle whenever an upload is enqueued: the previous batch has been synchronised and this
+    // batch's kernels come later, so growing an arena here never pulls memory from under a running kernel)
+    RN_CUDA(grow(reinterpret_cast<void**>(&d_huff_[slot]), &d_huff_cap_[slot], off));
     RN_CUDA(GrowJpegBuffers(b->coef_total * sizeof(int16_t), 0, 0, 0, 0));
     if (!h_huff_flags_) RN_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h_huff_flags_), 64 + max_batch_ * sizeof(int)));
+    for (auto& ev : ev_huff_up_)
+      if (!ev) RN_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
-  uint8_t* base = d_huff_;
-  RN_CUDA(cudaMemcpyAsync(base + o_stream, h_stream, stage_bytes, cudaMemcpyHostToDevice, compute_));
-  RN_CUDA(cudaMemcpyAsync(base + o_bds, bds.data(), nb * sizeof(HuffBlockDesc), cudaMemcpyHostToDevice, compute_));
-  RN_CUDA(cudaMemcpyAsync(base + o_fds, fds.data(), nf * sizeof(HuffFileDesc), cudaMemcpyHostToDevice, compute_));
-  RN_CUDA(cudaMemcpyAsync(base + o_tabs, tabs.data(), tabs.size() * sizeof(DevHuffTable), cudaMemcpyHostToDevice, compute_));
-  RN_CUDA(cudaMemsetAsync(base + o_err, 0, nf * 4 + 8, compute_));
-  RN_CUDA(cudaMemsetAsync(d_coef_, 0, b->coef_total * sizeof(int16_t), compute_));
-  HuffBatch hb{};
+  // The upload runs on the copy stream: while the kernels of the previous batch work on the compute stream, this
+  // batch's compressed bytes cross PCIe into the other arena.
+  uint8_t* base = d_huff_[slot];
+  RN_CUDA(cudaMemcpyAsync(base + o_stream, h_stream, stage_bytes, cudaMemcpyHostToDevice, copy_));
+  RN_CUDA(cudaMemcpyAsync(base + o_bds, bds.data(), nb * sizeof(HuffBlockDesc), cudaMemcpyHostToDevice, copy_));
+  RN_CUDA(cudaMemcpyAsync(base + o_fds, fds.data(), nf * sizeof(HuffFileDesc), cudaMemcpyHostToDevice, copy_));
+  RN_CUDA(cudaMemcpyAsync(base + o_tabs, tabs.data(), tabs.size() * sizeof(DevHuffTable), cudaMemcpyHostToDevice, copy_));
+  RN_CUDA(cudaMemsetAsync(base + o_err, 0, nf * 4 + 8, copy_));
+  RN_CUDA(cudaEventRecord(ev_huff_up_[slot], copy_));
+  stg.o_err = o_err;
+  HuffBatch& hb = stg.hb;
+  hb = HuffBatch{};
   hb.files = reinterpret_cast<const HuffFileDesc*>(base + o_fds);
   hb.blocks = reinterpret_cast<const HuffBlockDesc*>(base + o_bds);
   hb.tables = reinterpret_cast<const DevHuffTable*>(base + o_tabs);
@@ -329,8 +344,20 @@ cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size
   hb.n_files = nf;
   hb.n_blocks = nb;
   hb.rounds_out = &jpeg_huffman_rounds_;
+  return cudaSuccess;
+}
+
+// Second half of the stage: the Huffman kernels of the batch uploaded into `slot` (enqueued on compute_).
+cudaError_t Replica::JpegHuffRun(JpegBatch* b, int slot, std::vector<int>* err) {
+  const int m = static_cast<int>(b->index.size());
+  err->assign(m, 0);
+  HuffStage& stg = huff_stage_[slot];
+  huff_file_of_.clear();
+  if (!stg.any) return cudaSuccess;
+  RN_CUDA(cudaStreamWaitEvent(compute_, ev_huff_up_[slot], 0));
+  RN_CUDA(cudaMemsetAsync(d_coef_, 0, stg.coef_bytes, compute_));
   {
-    cudaError_t e = HuffDecode(hb, compute_);
+    cudaError_t e = HuffDecode(stg.hb, compute_);
     if (e != cudaSuccess) {
       err_ = std::string("device Huffman decode: ") + cudaGetErrorString(e);
       return e;
@@ -339,15 +366,12 @@ cudaError_t Replica::JpegHuffmanOnDevice(const uint8_t* const* files, const size
   if (jpeg_huffman_rounds_ < 0) {  // no fixed point within the launch budget: every file of the batch goes to the host path
     for (int k = 0; k < m; ++k)
       if (b->st[k] == kJpegOk) b->st[k] = kJpegUnsupported;
-    huff_file_of_.clear();
     return cudaSuccess;
   }
   last_launches_ += 4 + jpeg_huffman_rounds_ + 1;
   // error flags travel back with the rest of the batch (valid after the caller's stream synchronisation)
-  RN_CUDA(cudaMemcpyAsync(h_huff_flags_ + 16, base + o_err, nf * sizeof(int), cudaMemcpyDeviceToHost, compute_));
-  huff_file_of_ = file_of;
-  h_huff_flags_[1] = 0;
-  (void)err;
+  RN_CUDA(cudaMemcpyAsync(h_huff_flags_ + 16, d_huff_[slot] + stg.o_err, stg.nf * sizeof(int), cudaMemcpyDeviceToHost, compute_));
+  huff_file_of_ = stg.file_of;
   return cudaSuccess;
 }
 
@@ -390,7 +414,9 @@ cudaError_t Replica::DecodeJpeg(const uint8_t* file, size_t size, uint8_t* out, 
   bool on_device = false;
   if (!(flags_ & RN_FLAG_JPEG_HOST_HUFFMAN)) {
     std::vector<int> err;
-    e = JpegHuffmanOnDevice(&file, &sz, &b, 1, &err, nullptr);
+    e = JpegHuffUpload(&file, &sz, &b, 1, nullptr, 0);
+    if (e != cudaSuccess) return e;
+    e = JpegHuffRun(&b, 0, &err);
     if (e != cudaSuccess) return e;
     if (b.st[0] == kJpegOk) {
       e = JpegToRaw(b, nullptr, &crops, &ok, status);
@@ -598,6 +624,7 @@ cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes
       cudaError_t e = GrowJpegBuffers((max_stage + 1) / 2 * 2, 0, 0, 0, std::min(nbat, kJpegRing));
       if (e != cudaSuccess) return e;
       RN_CUDA(cudaStreamSynchronize(compute_));
+      RN_CUDA(cudaStreamSynchronize(copy_));
     }
     std::mutex mu;
     std::condition_variable cv;
@@ -664,8 +691,24 @@ cudaError_t Replica::InferJpegs(const uint8_t* const* files, const size_t* sizes
           cv.notify_all();
         }
       } release{mu, cv, released, bi + 1};
-      cudaError_t e = JpegHuffmanOnDevice(files, sizes, &b, threads, &err,
-                                          reinterpret_cast<const uint8_t*>(h_coef_[bi % kJpegRing]));
+      // this batch was uploaded during the previous iteration; upload the next one now, so that its bytes cross PCIe
+      // while this batch's kernels run
+      cudaError_t e = cudaSuccess;
+      if (bi == 0) {
+        e = JpegHuffUpload(files, sizes, &b, threads, reinterpret_cast<const uint8_t*>(h_coef_[0]), 0);
+        if (e != cudaSuccess) return e;
+      }
+      if (bi + 1 < nbat) {
+        JpegBatch& nx = batches[bi + 1];
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return done[bi + 1].load() == static_cast<int>(nx.index.size()); });
+        }
+        e = JpegHuffUpload(files, sizes, &nx, threads, reinterpret_cast<const uint8_t*>(h_coef_[(bi + 1) % kJpegRing]),
+                           (bi + 1) & 1);
+        if (e != cudaSuccess) return e;
+      }
+      e = JpegHuffRun(&b, bi & 1, &err);
       if (e != cudaSuccess) return e;
       // entries the device did not take: JpegToRaw must skip them, the host path picks them up below
       e = JpegToRaw(b, nullptr, &crops, &ok, nullptr);
