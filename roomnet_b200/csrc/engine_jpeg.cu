@@ -291,7 +291,7 @@ cudaError_t Replica::JpegHuffUpload(const uint8_t* const* files, const size_t* s
                o_loc = take(n_sub_total * 4);
   const size_t o_bsum = take(nb * 4), o_bflag = take(nb * 4), o_carry = take(nb * 4), o_bds = take(nb * sizeof(HuffBlockDesc));
   const size_t o_fds = take(nf * sizeof(HuffFileDesc)), o_tabs = take(tabs.size() * sizeof(DevHuffTable));
-  const size_t o_dc = take(dc_total * 2), o_err = take(nf * 4 + 8);
+  const size_t o_dc = take(dc_total * 2), o_err = take(nf * 4 + 8), o_dcp = take(static_cast<size_t>(nf) * 3 * 8 * 2 * 4);
   {
     auto grow = [&](void** p, size_t* cap, size_t need) -> cudaError_t {
       if (need <= *cap) return cudaSuccess;
@@ -338,6 +338,7 @@ cudaError_t Replica::JpegHuffUpload(const uint8_t* const* files, const size_t* s
   hb.carry = reinterpret_cast<unsigned*>(base + o_carry);
   hb.coefs = d_coef_;
   hb.dcdiff = reinterpret_cast<int16_t*>(base + o_dc);
+  hb.dc_part = reinterpret_cast<int*>(base + o_dcp);
   hb.file_error = reinterpret_cast<int*>(base + o_err);
   hb.changed = reinterpret_cast<int*>(base + o_err) + nf;
   hb.h_changed = h_huff_flags_;

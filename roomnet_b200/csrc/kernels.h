@@ -105,6 +105,7 @@ struct HuffBatch {
   unsigned* carry;
   int16_t* coefs;    // zero-initialised by the caller
   int16_t* dcdiff;
+  int* dc_part;      // scratch of the DC scan: 2 * (n_files * 3 * 8) ints
   int* file_error;   // zero-initialised by the caller; non-zero = damaged stream, decode that file on the host
   int* changed;      // device scratch
   int* h_changed;    // pinned host scratch

@@ -388,48 +388,63 @@ huff_write_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* _
 }
 
 // DC prediction: per (file, component) an inclusive sum of the differences in scan order, reset at restart segments.
-// One CUDA block per (file, component); thread chunks + a segmented scan over the chunk sums.
-__global__ void __launch_bounds__(1024)
-huff_dc_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict__ dcdiff, int16_t* coefs) {
-  __shared__ int s_sum[1024];
-  __shared__ int s_flag[1024];
-  const HuffFileDesc& f = files[blockIdx.x / 3];
-  const int c = blockIdx.x % 3;
-  if (c >= f.ncomp) return;
+// The sequence of a component is cut into kDcParts parts, one CUDA block each: a first kernel reduces every part to
+// (sum since the last reset, reset seen), the second scans inside the parts with the carry of the parts before.
+constexpr int kDcParts = 8;
+constexpr int kDcThreads = 256;
+
+struct DcRange {
+  const int16_t* dd;
+  int j0, per;
+  unsigned seg_len, lo, hi;  // this thread's elements [lo, hi) of the component's sequence
+  bool valid;
+};
+__device__ __forceinline__ DcRange dc_range(const HuffFileDesc& f, const int16_t* dcdiff, int c, int part) {
+  DcRange r{};
+  r.valid = c < f.ncomp;
+  if (!r.valid) return r;
   // blocks of component c inside an MCU are consecutive: [j0, j0 + per)
-  int j0 = 0;
-  for (int cc = 0; cc < c; ++cc) j0 += f.comp_h[cc] * f.comp_v[cc];
-  const int per = f.ncomp == 1 ? 1 : f.comp_h[c] * f.comp_v[c];
+  r.j0 = 0;
+  for (int cc = 0; cc < c; ++cc) r.j0 += f.comp_h[cc] * f.comp_v[cc];
+  r.per = f.ncomp == 1 ? 1 : f.comp_h[c] * f.comp_v[c];
   const unsigned mcus = f.total_blocks / f.bpm;
-  const unsigned n = mcus * per;                       // blocks of this component in scan order
-  const unsigned seg_len = (f.seg_blocks / f.bpm) * per;  // ... per restart segment
-  const int16_t* dd = dcdiff + f.dc_off;
-  const unsigned chunk = (n + blockDim.x - 1) / blockDim.x;
-  const unsigned lo = min(threadIdx.x * chunk, n), hi = min(lo + chunk, n);
-  // element t of the component = block (t / per) * bpm + j0 + t % per of the scan; walked with counters
-  unsigned mcu0 = lo / per, q0 = lo - mcu0 * per, left0 = seg_len - lo % seg_len;  // left0: elements until the next reset
+  const unsigned n = mcus * r.per;                 // blocks of this component in scan order
+  r.seg_len = (f.seg_blocks / f.bpm) * r.per;      // ... per restart segment
+  r.dd = dcdiff + f.dc_off;
+  const unsigned plen = (n + kDcParts - 1) / kDcParts;
+  const unsigned plo = min(part * plen, n), phi = min(plo + plen, n);
+  const unsigned chunk = (phi - plo + kDcThreads - 1) / kDcThreads;
+  r.lo = min(plo + threadIdx.x * chunk, phi);
+  r.hi = min(r.lo + chunk, phi);
+  return r;
+}
+// (sum since the last reset, reset seen) of this thread's elements; element t = block (t / per) * bpm + j0 + t % per
+__device__ __forceinline__ void dc_chunk_sum(const HuffFileDesc& f, const DcRange& r, int* sum_out, int* flag_out) {
+  unsigned mcu = r.lo / r.per, q = r.lo - mcu * r.per, left = r.lo % r.seg_len ? r.seg_len - r.lo % r.seg_len : 0;
   int sum = 0, flag = 0;
-  {
-    unsigned mcu = mcu0, q = q0, left = left0 == seg_len ? 0 : left0;
-    for (unsigned t = lo; t < hi; ++t) {
-      if (left == 0) {
-        sum = 0;
-        flag = 1;
-        left = seg_len;
-      }
-      --left;
-      sum += dd[mcu * f.bpm + j0 + q];
-      if (++q == static_cast<unsigned>(per)) {
-        q = 0;
-        ++mcu;
-      }
+  for (unsigned t = r.lo; t < r.hi; ++t) {
+    if (left == 0) {
+      sum = 0;
+      flag = 1;
+      left = r.seg_len;
+    }
+    --left;
+    sum += r.dd[mcu * f.bpm + r.j0 + q];
+    if (++q == static_cast<unsigned>(r.per)) {
+      q = 0;
+      ++mcu;
     }
   }
-  s_sum[threadIdx.x] = sum;
-  s_flag[threadIdx.x] = flag;
+  *sum_out = sum;
+  *flag_out = flag;
+}
+// inclusive segmented scan over the block's threads; returns this thread's inclusive (sum, flag)
+__device__ __forceinline__ void dc_block_scan(int* s_sum, int* s_flag, int* v_io, int* fl_io) {
+  int v = *v_io, fl = *fl_io;
+  s_sum[threadIdx.x] = v;
+  s_flag[threadIdx.x] = fl;
   __syncthreads();
-  int v = sum, fl = flag;
-  for (int d = 1; d < 1024; d <<= 1) {
+  for (int d = 1; d < kDcThreads; d <<= 1) {
     int pv = 0, pf = 0;
     if (threadIdx.x >= static_cast<unsigned>(d)) {
       pv = s_sum[threadIdx.x - d];
@@ -444,20 +459,62 @@ huff_dc_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict
     }
     __syncthreads();
   }
-  int pred = threadIdx.x ? s_sum[threadIdx.x - 1] : 0;  // predictor entering this thread's chunk
-  unsigned mcu = mcu0, q = q0, left = left0 == seg_len ? 0 : left0;
+  *v_io = v;
+  *fl_io = fl;
+}
+
+// grid: n_files * 3 * kDcParts; part_sum / part_flag: one entry per CUDA block
+__global__ void __launch_bounds__(kDcThreads)
+huff_dc_part_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict__ dcdiff, int* part_sum,
+                    int* part_flag) {
+  __shared__ int s_sum[kDcThreads];
+  __shared__ int s_flag[kDcThreads];
+  const int part = blockIdx.x % kDcParts, fc = blockIdx.x / kDcParts;
+  const HuffFileDesc& f = files[fc / 3];
+  const DcRange r = dc_range(f, dcdiff, fc % 3, part);
+  if (!r.valid) return;
+  int v, fl;
+  dc_chunk_sum(f, r, &v, &fl);
+  dc_block_scan(s_sum, s_flag, &v, &fl);
+  if (threadIdx.x == kDcThreads - 1) {
+    part_sum[blockIdx.x] = v;
+    part_flag[blockIdx.x] = fl;
+  }
+}
+
+__global__ void __launch_bounds__(kDcThreads)
+huff_dc_kernel(const HuffFileDesc* __restrict__ files, const int16_t* __restrict__ dcdiff, const int* __restrict__ part_sum,
+               const int* __restrict__ part_flag, int16_t* coefs) {
+  __shared__ int s_sum[kDcThreads];
+  __shared__ int s_flag[kDcThreads];
+  const int part = blockIdx.x % kDcParts, fc = blockIdx.x / kDcParts;
+  const HuffFileDesc& f = files[fc / 3];
+  const DcRange r = dc_range(f, dcdiff, fc % 3, part);
+  if (!r.valid) return;
+  // predictor entering this part: the parts before it, combined in order
+  int enter = 0;
+  for (int p = 0; p < part; ++p) {
+    const int b = blockIdx.x - part + p;
+    enter = part_flag[b] ? part_sum[b] : enter + part_sum[b];
+  }
+  int v, fl;
+  dc_chunk_sum(f, r, &v, &fl);
+  if (threadIdx.x == 0 && !fl) v += enter;
+  dc_block_scan(s_sum, s_flag, &v, &fl);
+  int pred = threadIdx.x ? s_sum[threadIdx.x - 1] : enter;  // predictor entering this thread's chunk
+  unsigned mcu = r.lo / r.per, q = r.lo - mcu * r.per, left = r.lo % r.seg_len ? r.seg_len - r.lo % r.seg_len : 0;
   unsigned my = mcu / f.mcus_x, mx = mcu - my * f.mcus_x;
-  for (unsigned t = lo; t < hi; ++t) {
+  for (unsigned t = r.lo; t < r.hi; ++t) {
     if (left == 0) {
       pred = 0;
-      left = seg_len;
+      left = r.seg_len;
     }
     --left;
-    const unsigned b = mcu * f.bpm + j0 + q;
-    pred += dd[b];
-    int16_t* dst = mcu_block_dst(f, coefs, mx, my, j0 + q, b);
+    const unsigned b = mcu * f.bpm + r.j0 + q;
+    pred += r.dd[b];
+    int16_t* dst = mcu_block_dst(f, coefs, mx, my, r.j0 + q, b);
     if (dst) dst[0] = static_cast<int16_t>(pred);
-    if (++q == static_cast<unsigned>(per)) {
+    if (++q == static_cast<unsigned>(r.per)) {
       q = 0;
       ++mcu;
       if (++mx == static_cast<unsigned>(f.mcus_x)) {
@@ -516,7 +573,8 @@ cudaError_t HuffDecode(const HuffBatch& b, cudaStream_t st) {
   huff_write_kernel<<<b.n_blocks, kHuffThreads, smem, st>>>(b.files, b.blocks, b.tables, b.streams, b.sub_seg,
                                                            b.start_used, b.local_off, b.carry, b.coefs, b.dcdiff,
                                                            b.file_error);
-  huff_dc_kernel<<<b.n_files * 3, 1024, 0, st>>>(b.files, b.dcdiff, b.coefs);
+  huff_dc_part_kernel<<<b.n_files * 3 * kDcParts, kDcThreads, 0, st>>>(b.files, b.dcdiff, b.dc_part, b.dc_part + b.n_files * 3 * kDcParts);
+  huff_dc_kernel<<<b.n_files * 3 * kDcParts, kDcThreads, 0, st>>>(b.files, b.dcdiff, b.dc_part, b.dc_part + b.n_files * 3 * kDcParts, b.coefs);
   if (b.rounds_out) *b.rounds_out = rounds;
   return cudaGetLastError();
 }
