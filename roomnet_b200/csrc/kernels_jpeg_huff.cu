@@ -23,6 +23,7 @@ constexpr int kSubBits = kSubseqBytes * 8;
 constexpr int kHuffThreads = 256;  // subsequences per CUDA block
 constexpr int kMaxInner = 64;      // re-synchronisation sweeps inside a block per launch
 constexpr int kMaxRounds = 16;     // launches before the batch is handed to the host decoder
+constexpr int kGuessBits = 256;    // how much of a subsequence the first (guessed) decode covers
 
 __device__ __constant__ unsigned char kZigzagDev[80] = {
     0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
@@ -182,7 +183,14 @@ huff_sync_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __
                  unsigned* nblk, int first_round, int* changed) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SmemHuff& sm = *reinterpret_cast<SmemHuff*>(smem_raw);
+  // per subsequence of this CUDA block: end state, the start state it was decoded from, blocks completed (bit 31 =
+  // decoded in this launch); any thread may decode any subsequence (see the work list below)
   __shared__ unsigned long long s_state[kHuffThreads];
+  __shared__ unsigned long long s_used[kHuffThreads];
+  __shared__ unsigned s_cnt[kHuffThreads];
+  __shared__ unsigned short s_list[kHuffThreads];
+  __shared__ int s_n;
+  constexpr unsigned kDirty = 0x80000000u;
   const HuffBlockDesc bd = blocks[blockIdx.x];
   const HuffFileDesc& f = files[bd.file];
   load_block(sm, f, tables, streams, bd.first_sub);
@@ -193,47 +201,68 @@ huff_sync_kernel(const HuffFileDesc* __restrict__ files, const HuffBlockDesc* __
   const unsigned win_bit0 = bd.first_sub * kSubBits;
   const bool first = active && (i == 0 || sub_seg[gi] != sub_seg[gi - 1]);
   const unsigned long long fixed = pack_state(i * kSubBits, 0, 0);  // what a restart segment starts with
-  unsigned long long used = 0, mine = 0;
-  unsigned cnt = 0;
-  bool any = false;
-  if (active) {
-    if (first_round) {
-      used = fixed;
-      mine = decode_span<false>(sm, win_bit0, i * kSubBits, 0, 0, (i + 1) * kSubBits, f.bpm, comp_of, &cnt, nullptr);
-      any = true;
-    } else {
-      used = start_used[gi];
-      mine = state[gi];
-      cnt = nblk[gi];
+  {
+    unsigned long long used = 0, mine = 0;
+    unsigned cnt = 0;
+    if (active) {
+      if (first_round) {
+        if (first) {
+          used = fixed;
+          mine = decode_span<false>(sm, win_bit0, i * kSubBits, 0, 0, (i + 1) * kSubBits, f.bpm, comp_of, &cnt, nullptr);
+        } else {
+          // the guess only has to END in the right state: decoding the last kGuessBits of the subsequence is enough
+          // for the decoder to fall into step; `used` = a state no predecessor can end in, so the first sweep decodes
+          // the whole subsequence from the predecessor's end state
+          used = ~0ull;
+          mine = decode_span<false>(sm, win_bit0, (i + 1) * kSubBits - kGuessBits, 0, 0, (i + 1) * kSubBits, f.bpm,
+                                    comp_of, &cnt, nullptr);
+        }
+        cnt |= kDirty;
+      } else {
+        used = start_used[gi];
+        mine = state[gi];
+        cnt = nblk[gi];
+      }
     }
+    s_state[threadIdx.x] = mine;
+    s_used[threadIdx.x] = used;
+    s_cnt[threadIdx.x] = cnt;
   }
-  s_state[threadIdx.x] = mine;
-  __syncthreads();
   for (int it = 0; it < kMaxInner; ++it) {
-    unsigned long long prev = fixed;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    // which subsequences start from a state their predecessor no longer ends in?  They go on a work list, so that the
+    // re-decoding below keeps whole warps busy even when only a few subsequences are left.
     if (active && !first) {
       // across CUDA blocks the predecessor's state comes from the previous launch (none yet in the first round)
+      unsigned long long prev = s_used[threadIdx.x];
       if (threadIdx.x) prev = s_state[threadIdx.x - 1];
-      else prev = first_round ? used : __ldcg(&state[gi - 1]);
+      else if (!first_round) prev = __ldcg(&state[gi - 1]);
       const unsigned pbit = static_cast<unsigned>(prev);
-      if (pbit < i * kSubBits || pbit >= i * kSubBits + 32) prev = used;  // (cannot happen; keeps reads inside the window)
+      const bool sane = pbit >= i * kSubBits && pbit < i * kSubBits + 32;  // (always; keeps reads inside the window)
+      if (sane && prev != s_used[threadIdx.x]) {
+        s_used[threadIdx.x] = prev;
+        s_list[atomicAdd(&s_n, 1)] = static_cast<unsigned short>(threadIdx.x);
+      }
     }
     __syncthreads();
-    bool ch = false;
-    if (active && !first && prev != used) {
-      used = prev;
-      mine = decode_span<false>(sm, win_bit0, static_cast<unsigned>(prev), static_cast<unsigned>(prev >> 32) & 255,
-                                static_cast<unsigned>(prev >> 40) & 255, (i + 1) * kSubBits, f.bpm, comp_of, &cnt, nullptr);
-      s_state[threadIdx.x] = mine;
-      ch = true;
-      any = true;
+    const int n = s_n;
+    if (n == 0) break;
+    if (static_cast<int>(threadIdx.x) < n) {
+      const unsigned j = s_list[threadIdx.x];
+      const unsigned long long st = s_used[j];
+      unsigned cnt = 0;
+      s_state[j] = decode_span<false>(sm, win_bit0, static_cast<unsigned>(st), static_cast<unsigned>(st >> 32) & 255,
+                                      static_cast<unsigned>(st >> 40) & 255, (bd.first_sub + j + 1) * kSubBits, f.bpm,
+                                      comp_of, &cnt, nullptr);
+      s_cnt[j] = cnt | kDirty;
     }
-    if (!__syncthreads_or(ch)) break;
+    __syncthreads();
   }
-  if (active && any) {
-    state[gi] = mine;
-    start_used[gi] = used;
-    nblk[gi] = cnt;
+  if (active && (s_cnt[threadIdx.x] & kDirty)) {
+    state[gi] = s_state[threadIdx.x];
+    start_used[gi] = s_used[threadIdx.x];
+    nblk[gi] = s_cnt[threadIdx.x] & ~kDirty;
     if (!first_round) *changed = 1;
   }
 }
